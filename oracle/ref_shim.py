@@ -1,0 +1,80 @@
+"""Import the UNMODIFIED reference (`trphysx`) from /root/reference in THIS container.
+
+TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing under `-m gpu`,
+smoke() or bench.py may call this.  It is used by tests/golden/make_golden.py (fixture generation) and
+by tests/test_oracle_vs_reference.py (which skips when the reference is absent).
+
+`trphysx/__init__.py:5-10` eagerly imports data_utils (h5py) and utils -> viz (matplotlib); neither is
+installed and neither is touched by the hot path, so empty stub packages are served for them
+(SURVEY.md Appendix A).
+"""
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("TRPX_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "trphysx"))
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        v = type(k, (), {"__init__": lambda s, *a, **kw: None, "__call__": lambda s, *a, **kw: s,
+                         "__getattr__": lambda s, k2: s})
+        setattr(self, k, v)
+        return v
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    NAMES = ("h5py", "matplotlib", "mpl_toolkits")
+
+    def find_spec(self, name, path=None, target=None):
+        if name.split(".")[0] in self.NAMES:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _Stub(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+_loaded = None
+
+
+def load():
+    """Returns the imported `trphysx` package (reference tree is read-only: no bytecode is written)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    sys.dont_write_bytecode = True
+    missing = [n for n in _Finder.NAMES if importlib.util.find_spec(n) is None]
+    if missing:
+        sys.meta_path.insert(0, _Finder())
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    ros = os.path.join(REF_ROOT, "examples", "rossler")
+    if ros not in sys.path:
+        sys.path.append(ros)
+    import trphysx  # noqa
+    _loaded = trphysx
+    return trphysx
+
+
+def rossler_modules():
+    load()
+    from rossler_module.configuration_rossler import RosslerConfig
+    from rossler_module.embedding_rossler import RosslerEmbedding, RosslerEmbeddingTrainer
+    return RosslerConfig, RosslerEmbedding, RosslerEmbeddingTrainer

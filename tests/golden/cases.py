@@ -1,0 +1,33 @@
+"""Table of golden cases shared by make_golden.py (reference side) and the parity tests."""
+
+# kind/over -> config; seed -> weights (seed), forward input (seed+1), second chunk (seed+2),
+# generation context (seed+3).  `ctx` > 1 exercises "only the last context token is used" (fact 2);
+# max_length > n_ctx + ctx exercises the saturated sliding window (fact 5).
+GPT2_CASES = {
+    # Lorenz shape (E=32, 4 layers, 4 heads, n_ctx=64), reference-style init
+    "lorenz_init":   dict(kind="lorenz", seed=101, stress=False, B=3, T=64, Tp=20, T2=30, ctx=1, max_length=150),
+    "lorenz_stress": dict(kind="lorenz", seed=102, stress=True,  B=3, T=64, Tp=33, T2=31, ctx=5, max_length=150),
+    # Rossler shape (n_ctx=32)
+    "rossler_stress": dict(kind="rossler", seed=103, stress=True, B=4, T=32, Tp=7, T2=25, ctx=1, max_length=100),
+    # tiny context so the window is saturated almost immediately
+    "tiny_ctx8":     dict(kind="lorenz", over=dict(n_ctx=8), seed=104, stress=True, B=5, T=8, Tp=3, T2=5, ctx=3, max_length=40),
+    # odd shapes: 2 layers, 2 heads (hd=16)
+    "two_heads":     dict(kind="lorenz", over=dict(n_ctx=16, n_layer=2, n_head=2), seed=105, stress=True, B=2, T=11, Tp=4, T2=9, ctx=2, max_length=40),
+    # Cylinder shape (E=128, 6 layers, hd=32, n_ctx=16)
+    "cylinder_init":   dict(kind="cylinder", seed=106, stress=False, B=2, T=16, Tp=6, T2=10, ctx=1, max_length=48),
+    "cylinder_stress": dict(kind="cylinder", over=dict(n_layer=3), seed=107, stress=True, B=2, T=16, Tp=5, T2=11, ctx=1, max_length=40),
+}
+
+LORENZ_CASES = {
+    "lorenz":  dict(kind="lorenz", seed=201, N=37),
+    "rossler": dict(kind="rossler", seed=202, N=16),
+}
+
+CYL_CASES = {
+    "cyl": dict(seed=301, N=2),
+}
+
+TRAIN_CASES = {
+    "lorenz":  dict(kind="lorenz", seed=401, B=24, T=6, iters=2),
+    "rossler": dict(kind="rossler", seed=402, B=16, T=4, iters=1),
+}

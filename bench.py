@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout hot path (BASELINE.json metric: rollout trajectory-steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE pass of the hot path over one batch of synthetic initial states:
+    embed(x0) -> generate(max_length = horizon+1, use_cache=True) -> recover(all tokens)
+Workload at every N (weak scaling): the per-GPU shard of BASELINE config[1] — Rossler, 65,536 trajectories
+sharded over 8 GPUs = 8,192 trajectories per GPU, horizon 256.  No collective on the data path.
+
+  value    trajectory-steps/s, whole job, inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e      same metric through the public module API with HOST buffers: pinned x0 -> H2D, ..., states -> D2H
+  roofline the rollout kernel alone (CUDA events around it): algorithmic FLOPs / duration vs the FP32 FMA peak
+           measured in the same run (MEASURED_PEAKS.json has no FP32 entry); HBM view reported beside it
+  cpu_baseline   the oracle port (torch CPU, all host threads) on a bounded sample, rank 0 only
+
+--impl reference times the CPU path alone (oracle port: the reference itself is Python and its tree does not
+exist on the GPU box) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "transformer-physx_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "rollout_trajectory_steps_per_sec"
+UNIT = "trajectory-steps/s"
+
+WORKLOADS = {
+    # name: (config kind, per-GPU trajectories, horizon)
+    "rossler": ("rossler", 8192, 256),      # BASELINE config[1]: 65,536 trajectories over 8 GPUs
+    "lorenz": ("lorenz", 8192, 128),        # BASELINE config[0] architecture at a GPU-sized batch
+    "lorenz256": ("lorenz", 256, 128),      # BASELINE config[0] as stated (256 trajectories, 128 steps)
+}
+
+
+def algorithmic_flops_per_traj_step(cfg, horizon, use_cache=True):
+    """n_layer*(24 E^2 + 4 L E) + 2 E^2 with L keys in the window, averaged over the horizon."""
+    E, nl, C = cfg.n_embd, cfg.n_layer, cfg.n_ctx
+    tot = 0.0
+    for s in range(horizon):
+        L = min(s + 1, C) if use_cache else 1
+        tot += nl * (24 * E * E + 4 * L * E) + 2 * E * E
+    return tot / horizon
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_modules(kind, device):
+    from oracle import synth
+    from tests.util import make_gpt2, make_lorenz
+    cfg = synth.make_config(kind)
+    emb = make_lorenz(cfg, 2024, "lorenz" if kind == "lorenz" else "rossler", device)
+    tr = make_gpt2(cfg, 2025, False, device)        # random init like the reference's _init_weights
+    return cfg, emb, tr
+
+
+def initial_states(kind, n, seed):
+    from oracle import synth
+    gen = synth.lorenz_trajectories if kind == "lorenz" else synth.rossler_trajectories
+    return torch.from_numpy(gen(n, 1, seed=seed)[:, 0].copy())
+
+
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(kind, B, S, threads):
+    """One pass of the CPU path (oracle port of the reference modules): embed -> generate(use_cache) -> recover."""
+    from oracle import synth, trpx_oracle as O
+    cfg = synth.make_config(kind)
+    sd_e = O.to_torch(synth.lorenz_embedding_weights(cfg, 2024))
+    sd_t = O.to_torch(synth.gpt2_weights(cfg, 2025, stress=False))
+    x0 = initial_states(kind, B, 7)
+    torch.set_num_threads(threads)
+
+    def run():
+        with torch.no_grad():
+            g0 = O.lorenz_embed(sd_e, cfg, x0)
+            out, _ = O.gpt2_generate(sd_t, cfg, g0.unsqueeze(1), S + 1, use_cache=True)
+            return O.lorenz_recover(sd_e, cfg, out.reshape(-1, cfg.n_embd))
+    return run
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, _, horizon = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    B, S = args.cpu_batch, min(args.cpu_horizon, horizon)
+    run = cpu_reference_pass(kind, B, S, threads)
+    for _ in range(max(1, min(args.warmup, 2))):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = B * S / dt
+    sample = f"{kind} B={B} horizon={S} use_cache=True embed+generate+recover, torch CPU fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    kind, B, S = WORKLOADS[args.workload]
+    B = args.batch or B
+    S = args.horizon or S
+    return f"{kind}_rollout B={B}/GPU horizon={S} use_cache=True (embed+generate+recover)"
+
+
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from trphysx_b200 import _native as N
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kind, B, S = WORKLOADS[args.workload]
+    B = args.batch or B
+    S = args.horizon or S
+    cfg, emb, tr = build_modules(kind, dev)
+    if args.tune:
+        tr.set_rollout_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(","))})
+    E = cfg.n_embd
+    x0_host = initial_states(kind, B, 1000 + rank).pin_memory()
+    x0_dev = x0_host.to(dev)
+    states_host = torch.empty((B, S + 1, 3), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)     # > 126 MB L2
+
+    def pass_device():
+        g0 = emb.embed(x0_dev)
+        out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True, return_presents=False)[0]
+        return emb.recover(out.view(B * (S + 1), E))
+
+    def pass_e2e():
+        x = x0_host.to(dev, non_blocking=True)
+        g0 = emb.embed(x)
+        out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True, return_presents=False)[0]
+        st = emb.recover(out.view(B * (S + 1), E))
+        states_host.copy_(st.view(B, S + 1, 3), non_blocking=True)
+
+    def timed(fn, steps, warmup, sampler=None):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+                flush.fill_(1.0)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if sampler:
+                sampler.start()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for a, b in ev:
+                flush.fill_(float(len(ev)))          # evict L2 between timed iterations (outside the event pair)
+                a.record()
+                fn()
+                b.record()
+            torch.cuda.synchronize()
+            clocks = sampler.stop() if sampler else None
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, clocks = timed(pass_device, args.steps, args.warmup, sampler)
+    ms_e2e, _ = timed(pass_e2e, args.steps, max(1, args.warmup // 2))
+    units = world * B * S
+    value = units / (ms_dev * 1e-3)
+    e2e = units / (ms_e2e * 1e-3)
+
+    # ---- the dominant kernel alone: rollout -------------------------------------------------------------
+    with torch.no_grad():
+        g0 = emb.embed(x0_dev).unsqueeze(1).contiguous()
+        kev = []
+        for _ in range(3):
+            tr.generate(g0, max_length=S + 1, use_cache=True, return_presents=False)
+        for _ in range(max(3, args.steps)):
+            flush.fill_(2.0)
+            out = torch.empty((B, S + 1, E), device=dev)
+            out[:, :1] = g0
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h = tr._handle(dev)
+            a.record()
+            N.check(N.lib().trpx_gpt2_rollout(h, out.data_ptr(), out.stride(0), out[:, 1:].data_ptr(), out.stride(0),
+                                              B, S, 1, None, N.stream_ptr(dev)))
+            b.record()
+            kev.append((a, b))
+        torch.cuda.synchronize()
+        k_ms = statistics.median(a.elapsed_time(b) for a, b in kev)
+        launch = tr.last_launch()
+        # Markov (reference default use_cache=False) mode, for the record
+        for _ in range(2):
+            tr.generate(g0, max_length=S + 1, use_cache=False)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        tr.generate(g0, max_length=S + 1, use_cache=False)
+        b.record()
+        torch.cuda.synchronize()
+        nocache_ms = a.elapsed_time(b)
+        # embed / recover alone
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        emb.embed(x0_dev)
+        b.record()
+        emb.recover(out.view(B * (S + 1), E))
+        c.record()
+        torch.cuda.synchronize()
+        embed_ms, recover_ms = a.elapsed_time(b), b.elapsed_time(c)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    fp32 = N.ctypes.c_float()
+    N.check(N.lib().trpx_probe_fp32_fma(local, N.ctypes.byref(fp32)))
+    flops_step = algorithmic_flops_per_traj_step(cfg, S)
+    k_flops = flops_step * B * S
+    achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    out_bytes = B * S * E * 4                       # algorithmic HBM traffic of the rollout: the generated tokens
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "weights": "random init (reference _init_weights)",
+                   "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"traj-shard x{world}",
+                   "rollout_launch": launch},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 3 * 4,
+                "d2h_bytes_per_step": B * (S + 1) * 3 * 4},
+        "gpu_launches": 3 * args.steps,
+        "roofline": {"bound": "fp32", "kernel": "rollout_e32_kernel" if launch["variant"] == 2 else "rollout_generic_kernel",
+                     "achieved": achieved_tf, "peak": fp32.value, "unit": "TFLOP/s", "frac": achieved_tf / fp32.value,
+                     "peak_source": "FP32 FMA microbenchmark in this run (trpx_probe_fp32_fma); MEASURED_PEAKS.json has no FP32 entry",
+                     "traffic": None, "kernel_ms": k_ms, "flops_per_traj_step": flops_step,
+                     "kernel_traj_steps_per_s": B * S / (k_ms * 1e-3),
+                     "hbm_view": {"algorithmic_GBps": out_bytes / (k_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak,
+                                  "frac": out_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "breakdown_ms": {"embed": embed_ms, "rollout": k_ms, "recover": recover_ms, "rollout_use_cache_false": nocache_ms},
+    }
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        Bc, Sc = args.cpu_batch, min(args.cpu_horizon, S)
+        run = cpu_reference_pass(kind, Bc, Sc, threads)
+        run()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            run()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {"value": Bc * Sc / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{kind} B={Bc} horizon={Sc} use_cache=True embed+generate+recover, "
+                                          f"oracle port (torch CPU fp32), {reps} passes"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rossler", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU trajectories (default: workload's)")
+    ap.add_argument("--horizon", type=int, default=0)
+    ap.add_argument("--tune", default="", help="e.g. warps_per_cta=8,traj_per_warp=8")
+    ap.add_argument("--cpu-batch", type=int, default=1024)
+    ap.add_argument("--cpu-horizon", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

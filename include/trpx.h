@@ -1,0 +1,170 @@
+/*
+ * trpx.h — C ABI of the B200-native rollout path of transformer-physx (libtrpx.so).
+ *
+ * The reference (zabaras/transformer-physx, `trphysx` 0.0.8) is pure Python/PyTorch and has no FFI
+ * layer of its own; the boundary below is what a binding for its rollout hot path would call.  Each
+ * entry point names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer on the handle's device;
+ *     all tensors are float32, row-major contiguous unless a stride argument says otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls only ENQUEUE work;
+ *   - return value 0 = OK, non-zero = error (TRPX_E_*); trpx_last_error() returns the message of the
+ *     last failing call on the calling thread.  No C++ exception crosses this boundary;
+ *   - a handle is bound to one device, is not re-entrant, and owns only packed weights + workspace
+ *     (KV windows, scratch).  Inputs/outputs are always caller-owned.
+ *   - there is NO CPU implementation behind any of these calls.
+ */
+#ifndef TRPX_H
+#define TRPX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRPX_OK              0
+#define TRPX_E_INVALID       1   /* bad argument / unsupported configuration */
+#define TRPX_E_CUDA          2   /* a CUDA runtime call failed */
+#define TRPX_E_STATE         3   /* weights not loaded, handle destroyed, ... */
+
+const char* trpx_last_error(void);
+int         trpx_version(void);                 /* 100*major + minor */
+/* SM count / max opt-in shared memory of `device` (for tests and the bench) */
+int         trpx_device_info(int device, int* sm_count, int* smem_optin_bytes);
+/* Measured FP32 FMA throughput of `device` in TFLOP/s (register-only FMA chains; the roofline denominator of
+ * the FP32-bound kernels, which MEASURED_PEAKS.json does not carry).  Synchronous. */
+int         trpx_probe_fp32_fma(int device, float* tflops_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Transformer decoder stack: PhysformerGPT2 (trphysx/transformer/phys_transformer_gpt2.py:120-269)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct trpx_gpt2* trpx_gpt2_t;
+
+typedef struct {
+    int   n_ctx;     /* PhysConfig.n_ctx   (configuration_phys.py:54) */
+    int   n_embd;    /* PhysConfig.n_embd  (:55)  multiple of 32, <= 256 */
+    int   n_layer;   /* PhysConfig.n_layer (:56) */
+    int   n_head;    /* PhysConfig.n_head  (:57)  n_embd % n_head == 0 */
+    float ln_eps;    /* PhysConfig.layer_norm_epsilon (:68) */
+} trpx_gpt2_config;
+
+/* PhysformerGPT2.__init__ (phys_transformer_gpt2.py:126-146): allocates the packed-weight blob. */
+int trpx_gpt2_create(const trpx_gpt2_config* cfg, int device, trpx_gpt2_t* out);
+int trpx_gpt2_destroy(trpx_gpt2_t h);
+
+/* Number of weight tensors trpx_gpt2_load_weights expects: 12*n_layer + 4. */
+int trpx_gpt2_num_weight_tensors(trpx_gpt2_t h);
+
+/* load_state_dict (phys_transformer_base.py:120-137).  `w_dev[i]` are device pointers, in this order:
+ *   for l in 0..n_layer-1:  h.l.ln_1.weight[E] ln_1.bias[E] attn.c_attn.weight[E,3E] attn.c_attn.bias[3E]
+ *                           attn.c_proj.weight[E,E] attn.c_proj.bias[E] ln_2.weight[E] ln_2.bias[E]
+ *                           mlp.c_fc.weight[E,4E] mlp.c_fc.bias[4E] mlp.c_proj.weight[4E,E] mlp.c_proj.bias[E]
+ *   then ln_f.weight[E] ln_f.bias[E] mlp_f.weight[E_out,E_in] mlp_f.bias[E]
+ * Conv1D weights are [in,out] (utils.py:37-39); mlp_f is nn.Linear [out,in] and is transposed here.
+ * `pe_table_dev` = position embedding [n_ctx, E] (phys_transformer_gpt2.py:215-219) or NULL to have the
+ * library compute it (even channels sin(p/10000^(2j/E)), odd channels cos(p)). */
+int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w_dev, int n_tensors,
+                           const float* pe_table_dev, void* stream);
+
+/* GenerationMixin.generate / _generate_time_series (generate_utils.py:66-169).
+ *   x0_dev            last context token of each trajectory, element (b, e) at x0_dev[b*x0_stride + e]
+ *   out_dev           generated tokens, element (b, s, e) at out_dev[b*out_stride + s*E + e], s in [0,S)
+ *   use_cache != 0    sliding KV window of n_ctx keys, position id min(s, n_ctx-1)  (generate_utils.py:156-157)
+ *   use_cache == 0    the reference default: every step is a 1-token forward at position 0
+ *   presents_dev      NULL, or (use_cache only) [n_layer][2][B][n_head][Tk][hd] with Tk = min(S, n_ctx):
+ *                     the `presents` of the LAST step in chronological order (attention.py:188)
+ * One launch covers the whole horizon; trajectories are independent. */
+int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0_dev, long long x0_stride,
+                      float* out_dev, long long out_stride, int B, int S, int use_cache,
+                      float* presents_dev, void* stream);
+
+/* Tuning knobs of the rollout kernel (0 = automatic).  `variant`: 0 auto, 1 generic kernel only. */
+int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp,
+                                 int max_ctas);
+/* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 e32 warp kernel), grid, block,
+ * dynamic smem bytes, trajectories per warp/CTA group. */
+int trpx_gpt2_last_launch(trpx_gpt2_t h, int* variant, int* grid, int* block, int* smem, int* group);
+
+/* PhysformerGPT2.forward (phys_transformer_gpt2.py:147-269) with position_ids/prop_embeds/
+ * attention_mask/head_mask = None.
+ *   x_dev         [B,T,E]
+ *   past_dev      NULL or n_layer device pointers to contiguous [2,B,H,Tp,hd]     (attention.py:182-185)
+ *   hidden_dev    [B,T,E]    mlp_f(ln_f(h))
+ *   presents_dev  NULL or n_layer device pointers to [2,B,H,Tp+T,hd]              (attention.py:188)
+ *   attn_dev      NULL or n_layer device pointers to [B,H,T,Tp+T] softmax weights (attention.py:109)
+ * Requires Tp + T <= n_ctx (the causal-mask buffer is n_ctx x n_ctx, attention.py:101-102). */
+int trpx_gpt2_forward(trpx_gpt2_t h, const float* x_dev, const float* const* past_dev, int Tp,
+                      float* hidden_dev, float* const* presents_dev, float* const* attn_dev,
+                      int B, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lorenz / Rossler Koopman embedding (trphysx/embedding/embedding_lorenz.py:25-167,
+ * examples/rossler/rossler_module/embedding_rossler.py:23-161)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct trpx_mlpemb* trpx_mlpemb_t;
+
+typedef struct {
+    int   state_dim;   /* config.state_dims[0] = 3 */
+    int   hidden;      /* hard-coded 500 (embedding_lorenz.py:39) */
+    int   n_embd;      /* 32 */
+    float ln_eps;
+} trpx_mlpemb_config;
+
+int trpx_mlpemb_create(const trpx_mlpemb_config* cfg, int device, trpx_mlpemb_t* out);
+int trpx_mlpemb_destroy(trpx_mlpemb_t h);
+/* 14 device pointers: mu[3] std[3] observableNet.0.weight[500,3] .0.bias[500] observableNet.2.weight[32,500]
+ * .2.bias[32] observableNet.3.weight[32] .3.bias[32] recoveryNet.0.weight[500,32] .0.bias[500]
+ * recoveryNet.2.weight[3,500] .2.bias[3] kMatrixDiag[32] kMatrixUT[61]   (all nn.Linear [out,in]) */
+int trpx_mlpemb_load_weights(trpx_mlpemb_t h, const float* const* w_dev, int n_tensors, void* stream);
+/* LorenzEmbedding.embed (embedding_lorenz.py:94-105): x[N,3] -> g[N,32] */
+int trpx_mlpemb_embed(trpx_mlpemb_t h, const float* x_dev, float* g_dev, long long N, void* stream);
+/* LorenzEmbedding.recover (:107-118): g[N,32] -> x[N,3] */
+int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g_dev, float* x_dev, long long N, void* stream);
+/* LorenzEmbedding.koopmanOperation (:120-142) as a banded matvec: g[N,32] -> g'[N,32] */
+int trpx_mlpemb_koopman(trpx_mlpemb_t h, const float* g_dev, float* gnext_dev, long long N, void* stream);
+/* LorenzEmbedding.koopmanOperator (:144-157): dense K[32,32] */
+int trpx_mlpemb_koopman_matrix(trpx_mlpemb_t h, float* K_dev, void* stream);
+
+/* LorenzEmbeddingTrainer.forward + backward (embedding_lorenz.py:181-221; enn_trainer.py:93-96).
+ *   states_dev [B,T,3];  w_recon 1e4 (Lorenz) / 1e3 (Rossler); w_dyn 1; w_reg 1e-1
+ *   loss2_dev[2] = {loss, loss_reconstruct};  grad_dev = flat gradient [36192] in nn.Module.parameters()
+ *   order: kMatrixDiag, kMatrixUT, observableNet.{0.w,0.b,2.w,2.b,3.w,3.b}, recoveryNet.{0.w,0.b,2.w,2.b}.
+ *   `grad_scale` multiplies the gradient (1/world_size before a SUM all-reduce). */
+int trpx_mlpemb_train_fwd_bwd(trpx_mlpemb_t h, const float* states_dev, int B, int T,
+                              float w_recon, float w_dyn, float w_reg, float grad_scale,
+                              float* loss2_dev, float* grad_dev, void* stream);
+long long trpx_mlpemb_num_params(trpx_mlpemb_t h);
+
+/* clip_grad_norm_(max_norm) + torch.optim.Adam step on flat buffers (enn_trainer.py:97-99):
+ * param/grad/m/v [n] device; step >= 1; norm_out_dev[1] receives the pre-clip global L2 norm. */
+int trpx_clip_adam(float* param_dev, const float* grad_dev, float* m_dev, float* v_dev, long long n,
+                   int step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float max_norm, float* norm_out_dev, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cylinder Koopman embedding (trphysx/embedding/embedding_cylinder.py:25-222)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct trpx_cyl* trpx_cyl_t;
+
+int trpx_cyl_create(int n_embd /*128*/, float ln_eps, int device, trpx_cyl_t* out);
+int trpx_cyl_destroy(trpx_cyl_t h);
+/* 36 device pointers: mu[4] std[4]; observableNet.{0,2,4,6,8}.{weight,bias}; observableNetFC.0.{weight,bias};
+ * recoveryNet.{1,4,7,10,12}.{weight,bias}; kMatrixDiagNet.{0,2}.{weight,bias}; kMatrixUT.{0,2}.{weight,bias};
+ * kMatrixLT.{0,2}.{weight,bias}.  Conv weights are [Cout,Cin,3,3]. */
+int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w_dev, int n_tensors, void* stream);
+/* Frames per encoder/decoder pass (default 64): intermediates of one pass stay L2-resident. */
+int trpx_cyl_set_chunk(trpx_cyl_t h, int frames);
+/* CylinderEmbedding.embed (:138-154): x[N,3,64,128], visc[N] -> g[N,128] */
+int trpx_cyl_embed(trpx_cyl_t h, const float* x_dev, const float* visc_dev, float* g_dev, int N, void* stream);
+/* CylinderEmbedding.recover (:156-170): g[N,128] -> x[N,3,64,128]; apply_mask=1 zeroes the cylinder
+ * cells (recover) and 0 leaves them (the decode half of forward(), :128-134). */
+int trpx_cyl_recover(trpx_cyl_t h, const float* g_dev, float* x_dev, int N, int apply_mask, void* stream);
+/* CylinderEmbedding.koopmanOperation (:172-196): g[N,128], visc[N] -> g'[N,128];
+ * kdiag_dev NULL or [N,128] (self.kMatrixDiag); kmat_dev NULL or [N,128,128] dense operator (self.kMatrix) */
+int trpx_cyl_koopman(trpx_cyl_t h, const float* g_dev, const float* visc_dev, float* gnext_dev,
+                     float* kdiag_dev, float* kmat_dev, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRPX_H */

@@ -1,0 +1,159 @@
+"""-m gpu: embedding kernels (Lorenz/Rossler MLP, Cylinder convs, Koopman operators, training step) against the
+reference's recorded outputs and the CPU oracle.  FP32 tolerance rel-L2 <= 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, trpx_oracle as O
+from tests.golden.cases import LORENZ_CASES, CYL_CASES, TRAIN_CASES
+from tests.util import make_lorenz, make_cylinder, torch_sd
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("name", list(LORENZ_CASES))
+def test_lorenz_embedding_matches_reference(golden_dir, dev, name):
+    c = LORENZ_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"emb_{name}.npz"))
+    cfg = synth.make_config(c["kind"])
+    m = make_lorenz(cfg, c["seed"], c["kind"], dev)
+    gen = synth.lorenz_trajectories if c["kind"] == "lorenz" else synth.rossler_trajectories
+    x = torch.from_numpy(gen(c["N"], 4, seed=c["seed"])[:, -1]).to(dev)
+    with torch.no_grad():
+        g = m.embed(x)
+        assert O.rel_l2(g.cpu(), gold["embed"]) < TOL
+        assert O.rel_l2(m.recover(g).cpu(), gold["recover"]) < TOL
+        g2, xhat = m(x)
+        assert O.rel_l2(g2.cpu(), gold["fwd_g"]) < TOL and O.rel_l2(xhat.cpu(), gold["fwd_xhat"]) < TOL
+        assert O.rel_l2(m.koopmanOperation(g).cpu(), gold["koopman"]) < TOL
+        assert np.array_equal(m.koopmanOperator.cpu().numpy(), gold["kmatrix"])
+        assert m.koopmanDiag is m.kMatrixDiag
+
+
+@pytest.mark.parametrize("N", [1, 2, 255, 100_003])
+def test_lorenz_embed_recover_vs_oracle_sizes(dev, N):
+    cfg = synth.make_config("lorenz")
+    m = make_lorenz(cfg, 31, "lorenz", dev)
+    sd = O.to_torch(synth.lorenz_embedding_weights(cfg, 31))
+    x = torch.from_numpy(synth.normal_embeds((N, 3), 8, scale=9.0))
+    with torch.no_grad():
+        g = m.embed(x.to(dev))
+        g_ref = O.lorenz_embed(sd, cfg, x)
+        assert O.rel_l2(g.cpu(), g_ref) < TOL
+        assert O.rel_l2(m.recover(g).cpu(), O.lorenz_recover(sd, cfg, g_ref)) < TOL
+        assert O.rel_l2(m.koopmanOperation(g).cpu(), O.lorenz_koopman(sd, cfg, g_ref)) < TOL
+        assert m.embed(x[:0].to(dev)).shape == (0, 32)
+
+
+def test_mu_std_assignment_is_picked_up(dev):
+    """Scripts overwrite model.mu / model.std by attribute assignment (examples/lorenz/train_lorenz_enn.py:55-57)."""
+    cfg = synth.make_config("lorenz")
+    m = make_lorenz(cfg, 32, "lorenz", dev)
+    sd = O.to_torch(synth.lorenz_embedding_weights(cfg, 32))
+    x = torch.from_numpy(synth.normal_embeds((64, 3), 3, scale=5.0))
+    with torch.no_grad():
+        m.embed(x.to(dev))
+        m.mu = torch.tensor([1.0, 2.0, 3.0]).to(dev)
+        m.std = torch.tensor([4.0, 5.0, 6.0]).to(dev)
+        sd["mu"], sd["std"] = m.mu.cpu(), m.std.cpu()
+        assert O.rel_l2(m.embed(x.to(dev)).cpu(), O.lorenz_embed(sd, cfg, x)) < TOL
+        m.observableNet[0].weight.mul_(1.5)              # in-place parameter update -> repack
+        sd["observableNet.0.weight"] = m.observableNet[0].weight.cpu()
+        assert O.rel_l2(m.embed(x.to(dev)).cpu(), O.lorenz_embed(sd, cfg, x)) < TOL
+
+
+@pytest.mark.parametrize("name", list(CYL_CASES))
+def test_cylinder_embedding_matches_reference(golden_dir, dev, name):
+    c = CYL_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"cyl_{name}.npz"))
+    cfg = synth.make_config("cylinder")
+    m = make_cylinder(cfg, c["seed"], dev)
+    x, visc = synth.cylinder_fields(c["N"], seed=c["seed"])
+    x, visc = torch.from_numpy(x).to(dev), torch.from_numpy(visc).to(dev)
+    with torch.no_grad():
+        g = m.embed(x, visc)
+        assert O.rel_l2(g.cpu(), gold["embed"]) < TOL
+        rec = m.recover(g)
+        assert O.rel_l2(rec.cpu(), gold["recover"]) < TOL
+        assert torch.equal(rec.cpu() == 0, torch.from_numpy(gold["recover"]) == 0) or \
+            int((rec[0, 0] == 0).sum()) >= 196
+        g2, xhat = m(x, visc)
+        assert O.rel_l2(xhat[:, 0].cpu(), gold["fwd_xhat_ch0"]) < TOL          # forward() does not mask
+        assert O.rel_l2(m.koopmanOperation(g, visc).cpu(), gold["koopman"]) < TOL
+        assert O.rel_l2(m.koopmanDiag.cpu(), gold["kdiag"]) < TOL
+        assert O.rel_l2(m.koopmanOperator[0].cpu(), gold["kmatrix0"]) < TOL
+
+
+@pytest.mark.parametrize("N,chunk", [(1, 64), (5, 2), (70, 64)])
+def test_cylinder_vs_oracle_chunking(dev, N, chunk):
+    cfg = synth.make_config("cylinder")
+    m = make_cylinder(cfg, 55, dev)
+    sd = O.to_torch(synth.cylinder_embedding_weights(cfg, 55))
+    x, visc = synth.cylinder_fields(N, seed=3)
+    x, visc = torch.from_numpy(x), torch.from_numpy(visc)
+    with torch.no_grad():
+        g = m.embed(x.to(dev), visc.to(dev))
+        m.set_chunk(chunk)
+        g_ref = O.cylinder_embed(sd, cfg, x, visc)
+        assert O.rel_l2(g.cpu(), g_ref) < TOL
+        assert O.rel_l2(m.embed(x.to(dev), visc.to(dev)).cpu(), g_ref) < TOL
+        assert O.rel_l2(m.recover(g).cpu(), O.cylinder_recover(sd, cfg, g_ref)) < TOL
+        assert O.rel_l2(m.koopmanOperation(g, visc.to(dev)).cpu(), O.cylinder_koopman(sd, cfg, g_ref, visc)) < TOL
+
+
+@pytest.mark.parametrize("name", list(TRAIN_CASES))
+def test_koopman_train_step_matches_reference(golden_dir, dev, name):
+    """loss, loss_reconstruct, flat gradient, clip norm and post-Adam parameters vs. the reference step body
+    (embedding_lorenz.py:181-221 + enn_trainer.py:93-102)."""
+    from trphysx_b200.config import PhysConfig
+    from trphysx_b200.embedding import LorenzEmbeddingTrainer, RosslerEmbeddingTrainer
+    from trphysx_b200.optim import FusedClipAdam
+    c = TRAIN_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"train_{name}.npz"))
+    cfg_ns = synth.make_config(c["kind"])
+    head = (LorenzEmbeddingTrainer if c["kind"] == "lorenz" else RosslerEmbeddingTrainer)(PhysConfig(**vars(cfg_ns)))
+    head.embedding_model.load_state_dict(torch_sd(synth.lorenz_embedding_weights(cfg_ns, c["seed"])))
+    head.to(dev)
+    gen = synth.lorenz_trajectories if c["kind"] == "lorenz" else synth.rossler_trajectories
+    states = torch.from_numpy(gen(c["B"], c["T"] - 1, seed=c["seed"])).to(dev)
+    opt = FusedClipAdam(head.parameters(), lr=1e-3, weight_decay=1e-8, max_norm=0.1)
+    for it in range(c["iters"]):
+        loss, loss_rec = head(states)
+        loss = loss.sum()
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in head.parameters()])
+        assert abs(float(loss) - float(gold[f"loss{it}"])) <= 2e-5 * abs(float(gold[f"loss{it}"]))
+        assert abs(float(loss_rec) - float(gold[f"loss_rec{it}"])) <= 2e-5 * abs(float(gold[f"loss_rec{it}"]))
+        assert O.rel_l2(flat.cpu(), gold[f"grad{it}"]) < TOL
+        norm = opt.step()
+        opt.zero_grad()
+        assert abs(float(norm) - float(gold[f"norm{it}"])) <= 2e-5 * float(gold[f"norm{it}"])
+    after = torch.cat([p.detach().reshape(-1) for p in head.parameters()])
+    assert O.rel_l2(after.cpu(), gold["params_after"]) < 1e-6
+
+
+def test_train_step_config3_vs_oracle(dev):
+    """BASELINE config 3 shape: states [512, 16, 3]."""
+    from trphysx_b200.config import PhysConfig
+    from trphysx_b200.embedding import LorenzEmbeddingTrainer
+    cfg_ns = synth.make_config("lorenz")
+    head = LorenzEmbeddingTrainer(PhysConfig(**vars(cfg_ns)))
+    head.embedding_model.load_state_dict(torch_sd(synth.lorenz_embedding_weights(cfg_ns, 77)))
+    head.to(dev)
+    states = torch.from_numpy(synth.lorenz_trajectories(512, 15, seed=77))
+    loss, loss_rec = head(states.to(dev))
+    loss.backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in head.parameters()])
+    sd = O.to_torch(synth.lorenz_embedding_weights(cfg_ns, 77))
+    l_ref, lr_ref, g_ref = O.lorenz_train_grads(sd, cfg_ns, states)
+    assert abs(float(loss) - float(l_ref)) <= 2e-5 * abs(float(l_ref))
+    assert abs(float(loss_rec) - float(lr_ref)) <= 2e-5 * abs(float(lr_ref))
+    assert O.rel_l2(flat.cpu(), g_ref) < TOL

@@ -1,0 +1,140 @@
+"""-m gpu: the CUDA decoder path (through the C ABI, via the drop-in PhysformerGPT2) against
+(1) the reference's recorded outputs (tests/golden), (2) the CPU oracle on fresh seeded inputs, and
+(3) size-independent properties at BASELINE sizes.  FP32 tolerance: rel-L2 <= 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, trpx_oracle as O
+from tests.golden.cases import GPT2_CASES
+from tests.util import make_gpt2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _gold(golden_dir, name):
+    return np.load(os.path.join(golden_dir, f"gpt2_{name}.npz"))
+
+
+@pytest.mark.parametrize("name", list(GPT2_CASES))
+def test_forward_matches_reference(golden_dir, dev, name):
+    c = GPT2_CASES[name]
+    gold = _gold(golden_dir, name)
+    cfg = synth.make_config(c["kind"], **c.get("over", {}))
+    m = make_gpt2(cfg, c["seed"], c["stress"], dev)
+    B, T, E = c["B"], c["T"], cfg.n_embd
+    x = torch.from_numpy(synth.normal_embeds((B, T, E), c["seed"] + 1)).to(dev)
+    with torch.no_grad():
+        hid, presents = m(x, use_cache=True)
+        assert O.rel_l2(hid.cpu(), gold["fwd_hidden"]) < TOL
+        assert O.rel_l2(presents[0].cpu(), gold["fwd_present_first"]) < TOL
+        assert O.rel_l2(presents[-1].cpu(), gold["fwd_present_last"]) < TOL
+        x2 = torch.from_numpy(synth.normal_embeds((B, c["T2"], E), c["seed"] + 2)).to(dev)
+        past = [p[:, :, :, :c["Tp"]] for p in presents]          # non-contiguous slices, like generate() makes
+        hid2, pres2 = m(x2, past=past, use_cache=True)
+        assert O.rel_l2(hid2.cpu(), gold["fwd2_hidden"]) < TOL
+        assert O.rel_l2(pres2[-1].cpu(), gold["fwd2_present_last"]) < TOL
+        (only_hidden,) = m(x, use_cache=False)
+        assert torch.equal(only_hidden, hid)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])      # auto (E=32 warp kernel when eligible), generic, no-TMA staging
+@pytest.mark.parametrize("name", list(GPT2_CASES))
+def test_generate_matches_reference(golden_dir, dev, name, variant):
+    c = GPT2_CASES[name]
+    gold = _gold(golden_dir, name)
+    cfg = synth.make_config(c["kind"], **c.get("over", {}))
+    m = make_gpt2(cfg, c["seed"], c["stress"], dev)
+    m.set_rollout_tuning(variant=variant)
+    ctx = torch.from_numpy(synth.normal_embeds((c["B"], c["ctx"], cfg.n_embd), c["seed"] + 3)).to(dev)
+    out = m.generate(ctx, max_length=c["max_length"], use_cache=True)
+    assert len(out) == 2 and len(out[1]) == cfg.n_layer
+    assert O.rel_l2(out[0].cpu(), gold["gen_cache"]) < TOL
+    assert tuple(out[1][-1].shape) == gold["gen_cache_present_last"].shape
+    assert O.rel_l2(out[1][-1].cpu(), gold["gen_cache_present_last"]) < TOL
+    out0 = m.generate(ctx, max_length=c["max_length"], use_cache=False)
+    assert len(out0) == 1
+    assert O.rel_l2(out0[0].cpu(), gold["gen_nocache"]) < TOL
+    info = m.last_launch()
+    e32 = cfg.n_embd == 32 and cfg.n_head == 4 and cfg.n_ctx <= 64
+    assert info["variant"] == (1 if (variant == 1 or not e32) else 2)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("kind,B,S", [("lorenz", 19, 90), ("rossler", 37, 70)])
+def test_rollout_vs_oracle_all_group_sizes(dev, kind, B, S, G):
+    """Fresh seeded inputs, ragged batch (B not a multiple of the group size), every trajectories-per-warp variant."""
+    cfg = synth.make_config(kind)
+    m = make_gpt2(cfg, 900 + G, True, dev)
+    m.set_rollout_tuning(traj_per_warp=G)
+    sd = O.to_torch(synth.gpt2_weights(cfg, 900 + G, stress=True))
+    x0 = torch.from_numpy(synth.normal_embeds((B, 1, cfg.n_embd), 77))
+    for uc in (True, False):
+        ref, ref_pres = O.gpt2_generate(sd, cfg, x0, S + 1, use_cache=uc)
+        out = m.generate(x0.to(dev), max_length=S + 1, use_cache=uc)
+        assert m.last_launch()["group"] == G
+        assert O.rel_l2(out[0].cpu(), ref) < TOL
+        per_step = (out[0].cpu() - ref).flatten(2).norm(dim=2).max(0).values / ref.flatten(2).norm(dim=2).max(0).values
+        assert float(per_step.max()) < 5 * TOL
+        if uc:
+            for l in range(cfg.n_layer):
+                assert O.rel_l2(out[1][l].cpu(), ref_pres[l]) < TOL
+
+
+def test_generate_edge_cases(dev):
+    cfg = synth.make_config("rossler")
+    m = make_gpt2(cfg, 5, True, dev)
+    x = torch.from_numpy(synth.normal_embeds((3, 4, 32), 9)).to(dev)
+    with pytest.raises(AssertionError):
+        m.generate(x, max_length=4)                       # cur_len < max_length (generate_utils.py:137-139)
+    with pytest.raises(AssertionError):
+        m.generate(x, max_length=8, use_cache=1)          # `use_cache` must be a bool (:94)
+    with pytest.raises(NotImplementedError):
+        m.generate(x.cpu(), max_length=8)                 # no CPU fallback
+    with pytest.raises(NotImplementedError):
+        m.generate(x, max_length=8, attention_mask=torch.ones(3, 4, device=dev))
+    # single generated step, batch of one, context longer than n_ctx (only the last token matters)
+    one = m.generate(x[:1], max_length=5, use_cache=True)
+    assert one[0].shape == (1, 5, 32) and one[1][0].shape == (2, 1, 4, 1, 8)
+    long_ctx = torch.from_numpy(synth.normal_embeds((2, 40, 32), 10)).to(dev)
+    a = m.generate(long_ctx, max_length=50, use_cache=True)[0]
+    b = m.generate(long_ctx[:, -1:], max_length=11, use_cache=True)[0]
+    assert torch.equal(a[:, 40:], b[:, 1:])
+    assert torch.equal(a[:, :40], long_ctx)
+    # empty batch
+    empty = m.generate(x[:0], max_length=6, use_cache=True)
+    assert empty[0].shape == (0, 6, 32)
+
+
+def test_full_size_properties(dev):
+    """BASELINE-size shard (8,192 Rossler trajectories x 256 steps): properties that need no oracle run.
+    (a) batch-composition independence: trajectory b gives the same bits alone, in a small batch and in the
+        full batch with a different trajectories-per-warp grouping;
+    (b) Markov property of the default use_cache=False mode: out[s+1] == generate(out[s], 1 step);
+    (c) a 256-trajectory sample of the full run matches the CPU oracle."""
+    cfg = synth.make_config("rossler")
+    m = make_gpt2(cfg, 321, True, dev)
+    sd = O.to_torch(synth.gpt2_weights(cfg, 321, stress=True))
+    B, S = 8192, 256
+    x0 = torch.from_numpy(synth.normal_embeds((B, 1, 32), 4242)).to(dev)
+    full = m.generate(x0, max_length=S + 1, use_cache=True, return_presents=False)[0]
+    assert m.last_launch()["variant"] == 2 and m.last_launch()["group"] == 8
+    assert torch.isfinite(full).all()
+    idx = torch.arange(0, B, 32, device=dev)
+    m.set_rollout_tuning(traj_per_warp=2)
+    sub = m.generate(x0[idx], max_length=S + 1, use_cache=True, return_presents=False)[0]
+    assert float((sub - full[idx]).abs().max()) <= 2e-6 * float(full.abs().max())
+    m.set_rollout_tuning()
+    ref, _ = O.gpt2_generate(sd, cfg, x0[idx].cpu(), S + 1, use_cache=True)
+    assert O.rel_l2(full[idx].cpu(), ref) < TOL
+    nc = m.generate(x0[:4096], max_length=65, use_cache=False)[0]
+    step = m.generate(nc[:, 10:11].contiguous(), max_length=2, use_cache=False)[0]
+    assert torch.equal(step[:, 1], nc[:, 11])

@@ -1,0 +1,127 @@
+"""CPU-only checks of the host-side mirror of the reference interface: state_dict compatibility, registries,
+error behaviour, sharding helper.  Where /root/reference is present the key sets are compared live."""
+import pytest
+import torch
+
+from oracle import ref_shim, synth
+from tests.util import torch_sd
+from trphysx_b200 import AutoEmbeddingModel, AutoPhysConfig, AutoPhysTransformer, shard_bounds
+from trphysx_b200.config import CylinderConfig, LorenzConfig, PhysConfig, RosslerConfig
+from trphysx_b200.embedding import CylinderEmbedding, LorenzEmbedding, RosslerEmbedding
+from trphysx_b200.transformer import PhysformerGPT2, PhysformerTrain
+from trphysx_b200.transformer.phys_transformer_gpt2 import position_table
+
+
+def test_state_dict_layouts_load_synth_weights():
+    for kind, cfgc in (("lorenz", LorenzConfig), ("rossler", RosslerConfig), ("cylinder", CylinderConfig)):
+        ns = synth.make_config(kind)
+        m = PhysformerGPT2(cfgc(), kind)
+        m.load_state_dict(torch_sd(synth.gpt2_weights(ns, 1)), strict=True)
+        assert m.model_name == "transformer_" + kind
+    LorenzEmbedding(LorenzConfig()).load_state_dict(torch_sd(synth.lorenz_embedding_weights(synth.make_config("lorenz"), 1)))
+    RosslerEmbedding(RosslerConfig()).load_state_dict(torch_sd(synth.lorenz_embedding_weights(synth.make_config("rossler"), 1)))
+    CylinderEmbedding(CylinderConfig()).load_state_dict(torch_sd(synth.cylinder_embedding_weights(synth.make_config("cylinder"), 1)))
+
+
+def test_parameter_counts_match_reference_notebooks():
+    # examples/lorenz/train_lorenz_enn.ipynb:437, examples/cylinder/train_cylinder_transformer.ipynb:479,481
+    assert LorenzEmbedding(LorenzConfig()).num_parameters == 36192
+    assert CylinderEmbedding(CylinderConfig()).num_parameters == 262535
+    assert PhysformerGPT2(CylinderConfig(), "cylinder")._num_parameters() == 1208448
+    assert PhysformerGPT2(LorenzConfig(), "lorenz")._num_parameters() == 53984
+
+
+def _pe_like_forward(cfg):
+    """phys_transformer_gpt2.py:215-219 evaluated the way forward() does it."""
+    pos = torch.arange(0, cfg.n_ctx, dtype=torch.float).unsqueeze(0)
+    pe = torch.zeros(1, cfg.n_ctx, cfg.n_embd)
+    i = torch.arange(0, cfg.n_embd // 2, dtype=torch.float).unsqueeze(0).unsqueeze(0)
+    pe[:, :, ::2] = torch.sin(pos.unsqueeze(-1) / 10000 ** (2 * i / cfg.n_embd))
+    i = i[:, :, cfg.n_embd % 2]
+    pe[:, :, 1::2] = torch.cos(pos.unsqueeze(-1) / 10000 ** (2 * i / cfg.n_embd))
+    return pe[0]
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_state_dict_keys_equal_reference():
+    ref_shim.load()
+    from trphysx.config.configuration_lorenz import LorenzConfig as RL
+    from trphysx.config.configuration_cylinder import CylinderConfig as RC
+    from trphysx.embedding import LorenzEmbedding as RLE, CylinderEmbedding as RCE
+    from trphysx.transformer import PhysformerGPT2 as RG
+
+    def sig(m):
+        return {k: (tuple(v.shape), v.dtype) for k, v in m.state_dict().items()}
+
+    assert sig(PhysformerGPT2(LorenzConfig(), "x")) == sig(RG(RL(), "x"))
+    assert sig(PhysformerGPT2(CylinderConfig(), "x")) == sig(RG(RC(), "x"))
+    assert sig(LorenzEmbedding(LorenzConfig())) == sig(RLE(RL()))
+    assert sig(CylinderEmbedding(CylinderConfig())) == sig(RCE(RC()))
+    # a reference config object is accepted as-is, and reference checkpoints load
+    ours = PhysformerGPT2(RL(), "lorenz")
+    ours.load_state_dict(RG(RL(), "lorenz").state_dict(), strict=True)
+    assert torch.equal(position_table(64, 32), _pe_like_forward(RL()))
+
+
+def test_registries_and_errors(tmp_path):
+    assert isinstance(AutoPhysConfig.load_config("lorenz"), LorenzConfig)
+    assert AutoPhysConfig.load_config("cylinder").n_embd == 128
+    with pytest.raises(EnvironmentError):
+        AutoEmbeddingModel()
+    with pytest.raises(EnvironmentError):
+        AutoPhysConfig()
+    with pytest.raises(ValueError):
+        AutoEmbeddingModel.init_model("nope", LorenzConfig())
+    with pytest.raises(KeyError):
+        AutoEmbeddingModel.init_trainer("nope", LorenzConfig())
+    assert isinstance(AutoEmbeddingModel.init_model("lorenz", LorenzConfig()), LorenzEmbedding)
+    assert isinstance(AutoPhysTransformer.init_model("rossler"), PhysformerGPT2)
+    m = AutoEmbeddingModel.init_model("lorenz", LorenzConfig())
+    m.save_model(str(tmp_path), epoch=3)
+    assert (tmp_path / "embedding_lorenz3.pth").exists()
+    m2 = AutoEmbeddingModel.load_model("lorenz", LorenzConfig(), str(tmp_path), epoch=3)
+    assert torch.equal(m2.kMatrixUT, m.kMatrixUT)
+    with pytest.raises(FileNotFoundError):
+        m.load_model(str(tmp_path / "missing"))
+    t = PhysformerGPT2(LorenzConfig(), "lorenz")
+    t.save_model(str(tmp_path), epoch=1)
+    assert (tmp_path / "transformer_lorenz1.pth").exists()
+    with pytest.raises(AssertionError):
+        t.save_model(str(tmp_path / "transformer_lorenz1.pth"))
+    cfg = LorenzConfig(n_ctx=16, foo=3)
+    assert cfg.n_ctx == 16 and cfg.foo == 3 and cfg.hidden_size == 32
+    cfg.save_pretrained(str(tmp_path / "cfg"))
+    again = AutoPhysConfig.load_config(str(tmp_path / "cfg"))
+    assert again.n_ctx == 16 and isinstance(again, LorenzConfig)
+    with pytest.raises(KeyError):
+        PhysConfig(n_ctx=1)
+
+
+def test_cpu_tensors_are_refused_not_silently_computed():
+    t = PhysformerGPT2(LorenzConfig(), "lorenz").eval()
+    x = torch.zeros(2, 1, 32)
+    with pytest.raises(NotImplementedError):
+        t.generate(x, max_length=4)
+    with pytest.raises(NotImplementedError):
+        t(x)
+    e = LorenzEmbedding(LorenzConfig()).eval()
+    with pytest.raises(NotImplementedError):
+        e.embed(torch.zeros(2, 3))
+    with pytest.raises(NotImplementedError):
+        e.recover(torch.zeros(2, 32))
+    with pytest.raises(NotImplementedError):
+        PhysformerGPT2(LorenzConfig(activation_function="relu"))
+    head = PhysformerTrain(LorenzConfig(), t)
+    assert head.transformer is t
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 65536, 65537):
+        for w in (1, 2, 3, 8):
+            parts = [shard_bounds(n, w, r) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)

@@ -1,0 +1,105 @@
+// Shared helpers for libtrpx (sm_100a).  Error plumbing for the C ABI + small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include "../../include/trpx.h"
+
+namespace trpx {
+
+// thread-local message returned by trpx_last_error()
+char* err_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define TRPX_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return ::trpx::set_error(TRPX_E_CUDA, "%s failed: %s (%s:%d)", #call,                    \
+                                     cudaGetErrorString(e__), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define TRPX_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                             \
+        if (!(cond)) return ::trpx::set_error(TRPX_E_INVALID, __VA_ARGS__);                          \
+    } while (0)
+
+// RAII device switch: every entry point runs on its handle's device and restores the caller's.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            switched = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float gelu_new(float x) {
+    // trphysx/transformer/utils.py:57-60 : 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
+    const float c = 0.7978845608028654f;
+    float x3 = x * x * x;
+    return 0.5f * x * (1.0f + tanhf(c * (x + 0.044715f * x3)));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// 256-bit global load (LDG.E.256 on sm_100a): one full 32-byte sector per lane.
+__device__ __forceinline__ void ldg256(const float* p, float (&a)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
+                 : "l"(p)
+                 : "memory");
+}
+
+// ---- TMA bulk copy global -> shared with an mbarrier (cp.async.bulk, SASS: UBLKCP) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TRPX_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TRPX_DONE_%=;\n"
+        "bra TRPX_WAIT_%=;\n"
+        "TRPX_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+}  // namespace trpx

@@ -1,0 +1,562 @@
+// Cylinder Koopman embedding (K5 conv encoder, K6 upsample+conv decoder, K4 per-sample banded Koopman).
+// Reference: trphysx/embedding/embedding_cylinder.py:42-67 (encoder), :70-88 (decoder), :138-170
+// (embed / recover), :172-196 (koopmanOperation).  All convs are 3x3 cross-correlations with
+// padding=1, padding_mode='replicate'; upsampling is bilinear x2 with align_corners=True.
+#include "common.cuh"
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+using namespace trpx;
+
+namespace {
+constexpr int CYL_H = 64, CYL_W = 128;
+constexpr int NBAND = 4;
+}  // namespace
+
+struct trpx_cyl {
+    uint32_t magic = 0x63796c31u;
+    int E = 128;
+    float eps = 1e-5f;
+    int device = 0;
+    int sm_count = 0;
+    bool loaded = false;
+    float* blob = nullptr;               // all 36 tensors back to back
+    size_t off[36] = {0};
+    size_t total = 0;
+    unsigned char* mask = nullptr;       // [64][128] cylinder mask
+    float* ws = nullptr;                 // activation workspace for one chunk of frames
+    size_t ws_bytes = 0;
+    int chunk = 64;                      // frames per decoder/encoder pass (intermediates stay in L2)
+};
+
+namespace {
+
+bool valid(trpx_cyl_t h) { return h != nullptr && h->magic == 0x63796c31u; }
+
+// tensor sizes, in the order documented in include/trpx.h
+void tensor_sizes(int E, size_t (&n)[36]) {
+    const int c4 = E / 32;
+    const int nband = (E - 1) + (E - 2) + (E - 3) + (E - 4);
+    size_t s[36] = {4, 4,
+                    16 * 4 * 9, 16, 32 * 16 * 9, 32, 64 * 32 * 9, 64, 128 * 64 * 9, 128, (size_t)c4 * 128 * 9, (size_t)c4,
+                    (size_t)E, (size_t)E,
+                    (size_t)128 * c4 * 9, 128, 64 * 128 * 9, 64, 32 * 64 * 9, 32, 16 * 32 * 9, 16, 3 * 16 * 9, 3,
+                    50, 50, (size_t)E * 50, (size_t)E,
+                    50, 50, (size_t)nband * 50, (size_t)nband,
+                    50, 50, (size_t)nband * 50, (size_t)nband};
+    for (int i = 0; i < 36; i++) n[i] = s[i];
+}
+
+enum { T_MU = 0, T_STD = 1, T_ENC = 2, T_LNW = 12, T_LNB = 13, T_DEC = 14, T_KD = 24, T_KU = 28, T_KL = 32 };
+
+// ---- bilinear x2 (align_corners=True) source index / weight, as aten's area_pixel_compute_* ------------
+struct Lerp {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_idx(int dst, int in_size, float scale) {
+    // real = scale * dst ; i0 = min(int(real), in-1) ; l1 = clamp(real - i0, 0, 1) ; i1 = i0 + (i0 < in-1)
+    const float real = scale * (float)dst;
+    Lerp r;
+    r.i0 = min((int)real, in_size - 1);
+    r.l1 = fminf(fmaxf(real - (float)r.i0, 0.f), 1.f);
+    r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+    r.l0 = 1.f - r.l1;
+    return r;
+}
+
+// ---- encoder input: cat(x, visc) then (x - mu) / std  (embedding_cylinder.py:149-150, 198-200) ----------
+__global__ void cyl_prep_kernel(const float* __restrict__ x, const float* __restrict__ visc, const float* __restrict__ mu,
+                                const float* __restrict__ sd, float* __restrict__ out, int N) {
+    const int HW = CYL_H * CYL_W;
+    const long long total = (long long)N * 4 * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % HW);
+        const int c = (int)((i / HW) % 4);
+        const int n = (int)(i / (4LL * HW));
+        const float v = (c < 3) ? x[((long long)n * 3 + c) * HW + pix] : visc[n] * 1.0f;
+        out[i] = (v - __ldg(mu + c)) / __ldg(sd + c);
+    }
+}
+
+// ---- simple direct conv (small layers): one thread per output element ------------------------------------
+// in [N][Cin][Hs][Ws]; if UP the conv runs on the x2 bilinear upsampling of `in`.  out [N][Cout][Ho][Wo].
+template <bool UP>
+__global__ void conv3x3_naive_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                     const float* __restrict__ bias, float* __restrict__ out, int N, int Cin, int Hs,
+                                     int Ws, int Cout, int stride, int relu) {
+    const int Hi = UP ? 2 * Hs : Hs, Wi = UP ? 2 * Ws : Ws;       // conv input size
+    const int Ho = (Hi - 1) / stride + 1, Wo = (Wi - 1) / stride + 1;
+    const long long total = (long long)N * Cout * Ho * Wo;
+    const float sh = UP ? (float)(Hs - 1) / (float)(Hi - 1) : 0.f;
+    const float sw = UP ? (float)(Ws - 1) / (float)(Wi - 1) : 0.f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int xo = (int)(idx % Wo);
+        const int yo = (int)((idx / Wo) % Ho);
+        const int co = (int)((idx / ((long long)Wo * Ho)) % Cout);
+        const int n = (int)(idx / ((long long)Wo * Ho * Cout));
+        float acc = __ldg(bias + co);
+        const float* wp = w + (size_t)co * Cin * 9;
+        const float* ip = in + (size_t)n * Cin * Hs * Ws;
+        for (int ci = 0; ci < Cin; ci++) {
+            const float* ic = ip + (size_t)ci * Hs * Ws;
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++) {
+                const int yy = min(max(yo * stride + dy - 1, 0), Hi - 1);       // replicate padding
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const int xx = min(max(xo * stride + dx - 1, 0), Wi - 1);
+                    float v;
+                    if (UP) {
+                        const Lerp ly = lerp_idx(yy, Hs, sh), lx = lerp_idx(xx, Ws, sw);
+                        const float v00 = ic[ly.i0 * Ws + lx.i0], v01 = ic[ly.i0 * Ws + lx.i1];
+                        const float v10 = ic[ly.i1 * Ws + lx.i0], v11 = ic[ly.i1 * Ws + lx.i1];
+                        v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+                    } else {
+                        v = ic[yy * Ws + xx];
+                    }
+                    acc = fmaf(v, __ldg(wp + ci * 9 + dy * 3 + dx), acc);
+                }
+            }
+        }
+        if (relu) acc = fmaxf(acc, 0.f);
+        out[idx] = acc;
+    }
+}
+
+// ---- tiled direct conv for the heavy decoder layers (stride 1) -----------------------------------------
+// CTA = (frame, 16x32 output tile, 2*CT output channels), 256 threads: thread = 4 x-adjacent pixels x CT
+// channels.  Per chunk of CC input channels the CTA builds the (optionally upsampled, replicate-padded)
+// input patch and the weight slice in shared memory; weights are read as warp-uniform broadcasts.
+constexpr int TH = 16, TW = 32, PW = 36, CC = 8, CONV_THREADS = 256;   // static smem stays < 48 KB
+
+struct ConvEpilogue {
+    int relu;
+    int unnorm;                     // y = sd[c]*y + mu[c]   (embedding_cylinder.py:202-203)
+    const float* mu;
+    const float* sd;
+    const unsigned char* mask;      // nullptr or [H][W]: zero where set (:168-169)
+};
+
+template <int CT, bool UP>
+__global__ void __launch_bounds__(CONV_THREADS) conv3x3_tiled_kernel(const float* __restrict__ in,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ bias,
+                                                                     float* __restrict__ out, int Cin, int Hs, int Ws,
+                                                                     int Cout, ConvEpilogue ep) {
+    constexpr int COT = 2 * CT;
+    __shared__ __align__(16) float patch[CC][TH + 2][PW];
+    __shared__ __align__(16) float wsm[CC][9][COT];
+    __shared__ Lerp ylut[TH + 2], xlut[TW + 2];
+    const int H = UP ? 2 * Hs : Hs, W = UP ? 2 * Ws : Ws;
+    const int tiles_x = (W + TW - 1) / TW;
+    const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW;
+    const int co0 = blockIdx.y * COT;
+    const int n = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int grp = tid >> 7;                 // channel group (warp-uniform)
+    const int pos = tid & 127;
+    const int py = pos >> 3, px = (pos & 7) * 4;
+
+    // per-tile lookup of the source rows/cols feeding each patch row/col
+    if (tid < TH + 2) {
+        const int yy = min(max(ty0 + tid - 1, 0), H - 1);
+        Lerp l;
+        if (UP) l = lerp_idx(yy, Hs, (float)(Hs - 1) / (float)(H - 1));
+        else { l.i0 = yy; l.i1 = yy; l.l0 = 1.f; l.l1 = 0.f; }
+        ylut[tid] = l;
+    } else if (tid >= 64 && tid < 64 + TW + 2) {
+        const int t = tid - 64;
+        const int xx = min(max(tx0 + t - 1, 0), W - 1);
+        Lerp l;
+        if (UP) l = lerp_idx(xx, Ws, (float)(Ws - 1) / (float)(W - 1));
+        else { l.i0 = xx; l.i1 = xx; l.l0 = 1.f; l.l1 = 0.f; }
+        xlut[t] = l;
+    }
+
+    float acc[4][CT];
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+        const int co = co0 + grp * CT + c;
+        const float b = (co < Cout) ? __ldg(bias + co) : 0.f;
+#pragma unroll
+        for (int p = 0; p < 4; p++) acc[p][c] = b;
+    }
+    const float* ip = in + (size_t)n * Cin * Hs * Ws;
+    __syncthreads();
+
+    for (int c0 = 0; c0 < Cin; c0 += CC) {
+        // weights slice: wsm[ci][tap][co]
+        for (int i = tid; i < CC * 9 * COT; i += CONV_THREADS) {
+            const int co = i % COT, r = i / COT;
+            const int tap = r % 9, ci = r / 9;
+            const int gco = co0 + co, gci = c0 + ci;
+            wsm[ci][tap][co] = (gco < Cout && gci < Cin) ? __ldg(w + ((size_t)gco * Cin + gci) * 9 + tap) : 0.f;
+        }
+        // input patch
+        for (int i = tid; i < CC * (TH + 2) * (TW + 2); i += CONV_THREADS) {
+            const int xx = i % (TW + 2), r = i / (TW + 2);
+            const int yy = r % (TH + 2), ci = r / (TH + 2);
+            float v = 0.f;
+            if (c0 + ci < Cin) {
+                const float* ic = ip + (size_t)(c0 + ci) * Hs * Ws;
+                const Lerp ly = ylut[yy], lx = xlut[xx];
+                if (UP) {
+                    const float v00 = __ldg(ic + ly.i0 * Ws + lx.i0), v01 = __ldg(ic + ly.i0 * Ws + lx.i1);
+                    const float v10 = __ldg(ic + ly.i1 * Ws + lx.i0), v11 = __ldg(ic + ly.i1 * Ws + lx.i1);
+                    v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+                } else {
+                    v = __ldg(ic + ly.i0 * Ws + lx.i0);
+                }
+            }
+            patch[ci][yy][xx] = v;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int ci = 0; ci < CC; ci++) {
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++) {
+                const float* row = &patch[ci][py + dy][px];
+                const float4 a = *reinterpret_cast<const float4*>(row);
+                const float2 b = *reinterpret_cast<const float2*>(row + 4);
+                const float iv[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    float wv[CT];
+                    const float* wp = &wsm[ci][dy * 3 + dx][grp * CT];
+                    if constexpr (CT % 4 == 0) {
+#pragma unroll
+                        for (int j = 0; j < CT / 4; j++) {
+                            const float4 t = *reinterpret_cast<const float4*>(wp + 4 * j);
+                            wv[4 * j] = t.x; wv[4 * j + 1] = t.y; wv[4 * j + 2] = t.z; wv[4 * j + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CT; j++) wv[j] = wp[j];
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; p++)
+#pragma unroll
+                        for (int c = 0; c < CT; c++) acc[p][c] = fmaf(iv[p + dx], wv[c], acc[p][c]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int y = ty0 + py, x = tx0 + px;
+    if (y < H && x < W) {
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+            const int co = co0 + grp * CT + c;
+            if (co >= Cout) continue;
+            float v[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                float t = acc[p][c];
+                if (ep.relu) t = fmaxf(t, 0.f);
+                if (ep.unnorm) t = __ldg(ep.sd + co) * t + __ldg(ep.mu + co);
+                if (ep.mask && x + p < W && ep.mask[y * W + x + p]) t = 0.f;
+                v[p] = t;
+            }
+            float* op = out + (((size_t)n * Cout + co) * H + y) * W + x;
+            if (x + 3 < W) *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+            else
+                for (int p = 0; p < 4 && x + p < W; p++) op[p] = v[p];
+        }
+    }
+}
+
+// ---- LayerNorm over the flattened encoder output (observableNetFC, embedding_cylinder.py:62-67) --------
+__global__ void cyl_ln_kernel(const float* __restrict__ z, const float* __restrict__ lw, const float* __restrict__ lb,
+                              float* __restrict__ g, int N, int E, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N) return;
+    const float* zr = z + (size_t)warp * E;
+    float s = 0.f;
+    for (int c = lane; c < E; c += 32) s += zr[c];
+    const float mean = warp_sum(s) / (float)E;
+    float v = 0.f;
+    for (int c = lane; c < E; c += 32) {
+        const float d = zr[c] - mean;
+        v = fmaf(d, d, v);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + eps);
+    for (int c = lane; c < E; c += 32) g[(size_t)warp * E + c] = (zr[c] - mean) * rstd * __ldg(lw + c) + __ldg(lb + c);
+}
+
+// ---- K4 (cylinder): viscosity-conditioned banded Koopman operator --------------------------------------
+// D = kMatrixDiagNet(100 visc) [E]; U = kMatrixUT(100 visc), L = kMatrixLT(100 visc) [502] with band o at
+// offset sum_{q<o}(E-q); K[r][r+o] = U_o[r], K[r+o][r] = L_o[r]  (embedding_cylinder.py:95-101, 183-191).
+struct KoopNets {
+    const float *d0w, *d0b, *d2w, *d2b, *u0w, *u0b, *u2w, *u2b, *l0w, *l0b, *l2w, *l2b;
+};
+
+__global__ void cyl_koopman_kernel(KoopNets k, const float* __restrict__ g, const float* __restrict__ visc,
+                                   float* __restrict__ gnext, float* __restrict__ kdiag, float* __restrict__ kmat, int E) {
+    __shared__ float hd[50], hu[50], hl[50];
+    extern __shared__ float band[];            // D[E] | U[nband] | L[nband]
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int nband = 4 * E - 10;
+    const float v = 100.f * visc[n];
+    if (tid < 50) hd[tid] = fmaxf(fmaf(__ldg(k.d0w + tid), v, __ldg(k.d0b + tid)), 0.f);
+    else if (tid >= 64 && tid < 114) hu[tid - 64] = fmaxf(fmaf(__ldg(k.u0w + tid - 64), v, __ldg(k.u0b + tid - 64)), 0.f);
+    else if (tid >= 128 && tid < 178) hl[tid - 128] = fmaxf(fmaf(__ldg(k.l0w + tid - 128), v, __ldg(k.l0b + tid - 128)), 0.f);
+    __syncthreads();
+    float* D = band;
+    float* U = band + E;
+    float* Lw = U + nband;
+    for (int i = tid; i < E + 2 * nband; i += blockDim.x) {
+        const float* wrow;
+        const float* hh;
+        float acc;
+        if (i < E) { wrow = k.d2w + (size_t)i * 50; hh = hd; acc = 0.f; }
+        else if (i < E + nband) { wrow = k.u2w + (size_t)(i - E) * 50; hh = hu; acc = 0.f; }
+        else { wrow = k.l2w + (size_t)(i - E - nband) * 50; hh = hl; acc = 0.f; }
+        for (int j = 0; j < 50; j++) acc = fmaf(hh[j], __ldg(wrow + j), acc);
+        if (i < E) acc += __ldg(k.d2b + i);
+        else if (i < E + nband) acc += __ldg(k.u2b + i - E);
+        else acc += __ldg(k.l2b + i - E - nband);
+        band[i] = acc;
+    }
+    __syncthreads();
+    const float* gr = g + (size_t)n * E;
+    for (int i = tid; i < E; i += blockDim.x) {
+        float acc = 0.f;
+        int off[NBAND + 1];
+        off[1] = 0;
+        for (int o = 2; o <= NBAND; o++) off[o] = off[o - 1] + (E - (o - 1));
+        for (int o = NBAND; o >= 1; o--)
+            if (i - o >= 0) acc = fmaf(Lw[off[o] + i - o], gr[i - o], acc);
+        acc = fmaf(D[i], gr[i], acc);
+        for (int o = 1; o <= NBAND; o++)
+            if (i + o < E) acc = fmaf(U[off[o] + i], gr[i + o], acc);
+        gnext[(size_t)n * E + i] = acc;
+        if (kdiag) kdiag[(size_t)n * E + i] = D[i];
+    }
+    if (kmat) {
+        float* Km = kmat + (size_t)n * E * E;
+        for (int idx = tid; idx < E * E; idx += blockDim.x) {
+            const int r = idx / E, c = idx % E;
+            const int o = c - r;
+            float val = 0.f;
+            if (o == 0) val = D[r];
+            else if (o > 0 && o <= NBAND) {
+                int off = 0;
+                for (int q = 1; q < o; q++) off += E - q;
+                val = U[off + r];
+            } else if (o < 0 && -o <= NBAND) {
+                int off = 0;
+                for (int q = 1; q < -o; q++) off += E - q;
+                val = Lw[off + c];
+            }
+            Km[idx] = val;
+        }
+    }
+}
+
+int ensure_ws(trpx_cyl_t h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return TRPX_OK;
+    if (h->ws) {
+        TRPX_CUDA(cudaDeviceSynchronize());
+        TRPX_CUDA(cudaFree(h->ws));
+        h->ws = nullptr;
+        h->ws_bytes = 0;
+    }
+    TRPX_CUDA(cudaMalloc(&h->ws, bytes));
+    h->ws_bytes = bytes;
+    return TRPX_OK;
+}
+
+template <int CT, bool UP>
+int launch_tiled(const float* in, const float* w, const float* b, float* out, int N, int Cin, int Hs, int Ws, int Cout,
+                 ConvEpilogue ep, cudaStream_t st) {
+    const int H = UP ? 2 * Hs : Hs, W = UP ? 2 * Ws : Ws;
+    dim3 grid(((H + TH - 1) / TH) * ((W + TW - 1) / TW), (Cout + 2 * CT - 1) / (2 * CT), N);
+    conv3x3_tiled_kernel<CT, UP><<<grid, CONV_THREADS, 0, st>>>(in, w, b, out, Cin, Hs, Ws, Cout, ep);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+template <bool UP>
+int launch_naive(const float* in, const float* w, const float* b, float* out, int N, int Cin, int Hs, int Ws, int Cout,
+                 int stride, int relu, cudaStream_t st) {
+    const int Hi = UP ? 2 * Hs : Hs, Wi = UP ? 2 * Ws : Ws;
+    const long long total = (long long)N * Cout * ((Hi - 1) / stride + 1) * ((Wi - 1) / stride + 1);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    conv3x3_naive_kernel<UP><<<blocks, 256, 0, st>>>(in, w, b, out, N, Cin, Hs, Ws, Cout, stride, relu);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int trpx_cyl_create(int n_embd, float ln_eps, int device, trpx_cyl_t* out) {
+    TRPX_REQUIRE(out != nullptr, "null argument");
+    TRPX_REQUIRE(n_embd == 128, "n_embd=%d unsupported: the 64x128 conv stack flattens to 4*4*8=128", n_embd);
+    int ndev = 0;
+    TRPX_CUDA(cudaGetDeviceCount(&ndev));
+    TRPX_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    DeviceGuard guard(device);
+    trpx_cyl* h = new (std::nothrow) trpx_cyl();
+    TRPX_REQUIRE(h != nullptr, "out of host memory");
+    h->E = n_embd;
+    h->eps = ln_eps;
+    h->device = device;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    size_t n[36];
+    tensor_sizes(n_embd, n);
+    size_t o = 0;
+    for (int i = 0; i < 36; i++) {
+        h->off[i] = o;
+        o += (n[i] + 3) & ~(size_t)3;          // keep every tensor 16-byte aligned
+    }
+    h->total = o;
+    // cylinder mask, embedding_cylinder.py:38-39: sqrt(X^2 + Y^2) < 1 on linspace(-2,14,128) x linspace(-4,4,64)
+    std::vector<unsigned char> mk(CYL_H * CYL_W);
+    for (int y = 0; y < CYL_H; y++)
+        for (int x = 0; x < CYL_W; x++) {
+            const double X = (x == CYL_W - 1) ? 14.0 : -2.0 + x * (16.0 / (CYL_W - 1));
+            const double Y = (y == CYL_H - 1) ? 4.0 : -4.0 + y * (8.0 / (CYL_H - 1));
+            mk[y * CYL_W + x] = std::sqrt(X * X + Y * Y) < 1.0 ? 1 : 0;
+        }
+    if (cudaMalloc(&h->blob, sizeof(float) * h->total) != cudaSuccess ||
+        cudaMalloc(&h->mask, mk.size()) != cudaSuccess ||
+        cudaMemcpy(h->mask, mk.data(), mk.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(h->blob);
+        cudaFree(h->mask);
+        delete h;
+        return set_error(TRPX_E_CUDA, "allocation of the cylinder handle failed");
+    }
+    *out = h;
+    return TRPX_OK;
+}
+
+int trpx_cyl_destroy(trpx_cyl_t h) {
+    if (!valid(h)) return set_error(TRPX_E_STATE, "trpx_cyl_destroy: invalid handle");
+    DeviceGuard guard(h->device);
+    cudaFree(h->blob);
+    cudaFree(h->mask);
+    cudaFree(h->ws);
+    h->magic = 0;
+    delete h;
+    return TRPX_OK;
+}
+
+int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w, int n, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    TRPX_REQUIRE(w != nullptr && n == 36, "expected 36 weight tensors, got %d", n);
+    for (int i = 0; i < n; i++) TRPX_REQUIRE(w[i] != nullptr, "weight tensor %d is null", i);
+    DeviceGuard guard(h->device);
+    size_t sz[36];
+    tensor_sizes(h->E, sz);
+    for (int i = 0; i < 36; i++)
+        TRPX_CUDA(cudaMemcpyAsync(h->blob + h->off[i], w[i], sz[i] * sizeof(float), cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
+    h->loaded = true;
+    return TRPX_OK;
+}
+
+int trpx_cyl_set_chunk(trpx_cyl_t h, int frames) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    TRPX_REQUIRE(frames >= 1 && frames <= 65535, "chunk must be in [1, 65535]");
+    h->chunk = frames;
+    return TRPX_OK;
+}
+
+int trpx_cyl_embed(trpx_cyl_t h, const float* x, const float* visc, float* g, int N, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(N >= 0 && (N == 0 || (x && visc && g)), "bad arguments");
+    if (N == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = CYL_H * CYL_W;
+    const int c4 = h->E / 32;
+    // per-frame activation sizes: normalised input, 4 strided convs, final conv
+    const size_t a0 = 4 * HW, a1 = 16 * HW / 4, a2 = 32 * HW / 16, a3 = 64 * HW / 64, a4 = 128 * HW / 256, a5 = (size_t)c4 * 32;
+    const size_t per = a0 + a1 + a2 + a3 + a4 + a5;
+    const int chunk = std::min(N, h->chunk);
+    int rc = ensure_ws(h, per * chunk * sizeof(float));
+    if (rc) return rc;
+    const float* B = h->blob;
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int nn = std::min(chunk, N - n0);
+        float* p0 = h->ws;
+        float* p1 = p0 + a0 * chunk;
+        float* p2 = p1 + a1 * chunk;
+        float* p3 = p2 + a2 * chunk;
+        float* p4 = p3 + a3 * chunk;
+        float* p5 = p4 + a4 * chunk;
+        cyl_prep_kernel<<<std::min(nn * 32, 148 * 8), 256, 0, st>>>(x + (size_t)n0 * 3 * HW, visc + n0, B + h->off[T_MU],
+                                                                    B + h->off[T_STD], p0, nn);
+        TRPX_CUDA(cudaGetLastError());
+        if ((rc = launch_naive<false>(p0, B + h->off[T_ENC + 0], B + h->off[T_ENC + 1], p1, nn, 4, 64, 128, 16, 2, 1, st))) return rc;
+        if ((rc = launch_naive<false>(p1, B + h->off[T_ENC + 2], B + h->off[T_ENC + 3], p2, nn, 16, 32, 64, 32, 2, 1, st))) return rc;
+        if ((rc = launch_naive<false>(p2, B + h->off[T_ENC + 4], B + h->off[T_ENC + 5], p3, nn, 32, 16, 32, 64, 2, 1, st))) return rc;
+        if ((rc = launch_naive<false>(p3, B + h->off[T_ENC + 6], B + h->off[T_ENC + 7], p4, nn, 64, 8, 16, 128, 2, 1, st))) return rc;
+        if ((rc = launch_naive<false>(p4, B + h->off[T_ENC + 8], B + h->off[T_ENC + 9], p5, nn, 128, 4, 8, c4, 1, 0, st))) return rc;
+        cyl_ln_kernel<<<(nn * 32 + 255) / 256, 256, 0, st>>>(p5, B + h->off[T_LNW], B + h->off[T_LNB], g + (size_t)n0 * h->E,
+                                                             nn, h->E, h->eps);
+        TRPX_CUDA(cudaGetLastError());
+    }
+    return TRPX_OK;
+}
+
+int trpx_cyl_recover(trpx_cyl_t h, const float* g, float* x, int N, int apply_mask, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(N >= 0 && (N == 0 || (x && g)), "bad arguments");
+    if (N == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = CYL_H * CYL_W;
+    const int c4 = h->E / 32;
+    const size_t a1 = 128 * 8 * 16, a2 = 64 * 16 * 32, a3 = 32 * 32 * 64, a4 = 16 * 64 * 128;
+    const size_t per = a1 + a2 + a3 + a4;
+    const int chunk = std::min(N, h->chunk);
+    int rc = ensure_ws(h, per * chunk * sizeof(float));
+    if (rc) return rc;
+    const float* B = h->blob;
+    ConvEpilogue relu{1, 0, nullptr, nullptr, nullptr};
+    ConvEpilogue fin{0, 1, B + h->off[T_MU], B + h->off[T_STD], apply_mask ? h->mask : nullptr};
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int nn = std::min(chunk, N - n0);
+        float* p1 = h->ws;
+        float* p2 = p1 + a1 * chunk;
+        float* p3 = p2 + a2 * chunk;
+        float* p4 = p3 + a3 * chunk;
+        // g.view(-1, 4, 4, 8) -> up x2 -> conv(4->128) -> relu        (embedding_cylinder.py:71-73)
+        if ((rc = launch_naive<true>(g + (size_t)n0 * h->E, B + h->off[T_DEC + 0], B + h->off[T_DEC + 1], p1, nn, c4, 4, 8, 128, 1, 1, st))) return rc;
+        if ((rc = launch_tiled<8, true>(p1, B + h->off[T_DEC + 2], B + h->off[T_DEC + 3], p2, nn, 128, 8, 16, 64, relu, st))) return rc;
+        if ((rc = launch_tiled<8, true>(p2, B + h->off[T_DEC + 4], B + h->off[T_DEC + 5], p3, nn, 64, 16, 32, 32, relu, st))) return rc;
+        if ((rc = launch_tiled<8, true>(p3, B + h->off[T_DEC + 6], B + h->off[T_DEC + 7], p4, nn, 32, 32, 64, 16, relu, st))) return rc;
+        if ((rc = launch_tiled<2, false>(p4, B + h->off[T_DEC + 8], B + h->off[T_DEC + 9], x + (size_t)n0 * 3 * HW, nn, 16, 64, 128, 3, fin, st))) return rc;
+    }
+    return TRPX_OK;
+}
+
+int trpx_cyl_koopman(trpx_cyl_t h, const float* g, const float* visc, float* gnext, float* kdiag, float* kmat, int N,
+                     void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(N >= 0 && (N == 0 || (g && visc && gnext)), "bad arguments");
+    TRPX_REQUIRE(g != gnext, "in-place Koopman step is not supported");
+    if (N == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    const float* B = h->blob;
+    KoopNets k{B + h->off[T_KD], B + h->off[T_KD + 1], B + h->off[T_KD + 2], B + h->off[T_KD + 3],
+               B + h->off[T_KU], B + h->off[T_KU + 1], B + h->off[T_KU + 2], B + h->off[T_KU + 3],
+               B + h->off[T_KL], B + h->off[T_KL + 1], B + h->off[T_KL + 2], B + h->off[T_KL + 3]};
+    const int nband = 4 * h->E - 10;
+    const size_t smem = sizeof(float) * (h->E + 2 * nband);
+    cyl_koopman_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(k, g, visc, gnext, kdiag, kmat, h->E);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+}  // extern "C"

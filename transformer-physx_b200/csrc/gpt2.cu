@@ -1,0 +1,1036 @@
+// Decoder stack of the rollout path: weight packer, rollout kernels (K1), teacher-forced forward (K2).
+//
+// Reference arithmetic restated once (validated by oracle/trpx_oracle.py):
+//   h = x + PE(p);  per layer:  a = LN1(h); [q|k|v] = a Wqkv + b;  window <- (k,v);
+//   per head: w = softmax(q K^T / sqrt(hd)); o = w V;  h += o Wproj + b;
+//   f = LN2(h);  h += gelu_new(f Wfc + b) Wpr + b;      x' = LN_f(h) Wf^T + bf
+// generate(): trphysx/transformer/generate_utils.py:112-169 ; forward(): phys_transformer_gpt2.py:147-269 ;
+// attention: attention.py:75-119, 153-200.
+#include "common.cuh"
+#include "gpt2_layout.cuh"
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+using namespace trpx;
+
+struct trpx_gpt2 {
+    uint32_t magic = 0x67707432u;
+    trpx_gpt2_config cfg{};
+    Gpt2Layout lay{};
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    float* blob = nullptr;
+    float* pe = nullptr;
+    bool loaded = false;
+    float* kv = nullptr;          // rollout workspace (KV windows of the groups in flight)
+    size_t kv_bytes = 0;
+    int tune_variant = 0, tune_warps = 0, tune_g = 0, tune_max_ctas = 0;
+    int last_variant = 0, last_grid = 0, last_block = 0, last_smem = 0, last_group = 0;
+};
+
+namespace {
+
+constexpr int GEN_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// building blocks shared by the generic rollout kernel and the forward kernel (CTA-cooperative)
+// ------------------------------------------------------------------------------------------------
+
+// y[g][n] = bias[n] + sum_k aT[k*G+g] * W[k*N+n]   (W row-major [K][N] in global memory, read once per CTA)
+// Threads own output columns; when N < blockDim the K range is split across thread groups and
+// combined through `part` (>= blockDim*G floats).  epi(n, g, value) consumes the result.
+// All threads of the CTA must call this; the caller synchronises afterwards.
+template <int G, class Epi>
+__device__ __forceinline__ void block_gemv(const float* __restrict__ W, const float* __restrict__ bias, int K,
+                                           int N, const float* aT, float* part, Epi epi) {
+    const int NT = blockDim.x, tid = threadIdx.x;
+    if (N >= NT) {
+        for (int n = tid; n < N; n += NT) {
+            float acc[G];
+            const float b = __ldg(bias + n);
+#pragma unroll
+            for (int g = 0; g < G; g++) acc[g] = b;
+#pragma unroll 4
+            for (int k = 0; k < K; k++) {
+                const float w = __ldg(W + (size_t)k * N + n);
+#pragma unroll
+                for (int g = 0; g < G; g++) acc[g] = fmaf(aT[k * G + g], w, acc[g]);
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) epi(n, g, acc[g]);
+        }
+    } else {
+        const int ks = NT / N;
+        const int kc = (K + ks - 1) / ks;
+        const int my = tid / N, n = tid - my * N;
+        if (my < ks) {
+            float acc[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) acc[g] = 0.f;
+            const int k0 = my * kc, k1 = min(K, k0 + kc);
+#pragma unroll 4
+            for (int k = k0; k < k1; k++) {
+                const float w = __ldg(W + (size_t)k * N + n);
+#pragma unroll
+                for (int g = 0; g < G; g++) acc[g] = fmaf(aT[k * G + g], w, acc[g]);
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) part[(my * N + n) * G + g] = acc[g];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < N * G; idx += NT) {
+            const int nn = idx / G, g = idx - nn * G;
+            float s = __ldg(bias + nn);
+            for (int j = 0; j < ks; j++) s += part[(j * N + nn) * G + g];
+            epi(nn, g, s);
+        }
+    }
+}
+
+// One warp: softmax(q K^T / sqrt(hd)) V for one (query, head).  K/V rows have `E` floats, this head's
+// slice starts at column head*hd.  q element d is q[d*qs]; output element d goes to out[d*os].
+// pbuf: per-warp scratch of >= L floats.  If attn_out != nullptr the L weights are stored there.
+__device__ __forceinline__ void warp_attention(const float* q, int qs, const float* Kr, const float* Vr, int E,
+                                               int hd, int L, float* pbuf, float* out, int os, float* attn_out) {
+    const int lane = threadIdx.x & 31;
+    const float scale = sqrtf((float)hd);          // attention.py:99  w / (float(v.size(-1)) ** 0.5)
+    float m = -INFINITY;
+    for (int slot = lane; slot < L; slot += 32) {
+        const float* kr = Kr + (size_t)slot * E;
+        float s = 0.f;
+        for (int d = 0; d < hd; d++) s = fmaf(q[d * qs], kr[d], s);
+        s = s / scale;
+        pbuf[slot] = s;
+        m = fmaxf(m, s);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int slot = lane; slot < L; slot += 32) {
+        const float p = expf(pbuf[slot] - m);
+        pbuf[slot] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    for (int slot = lane; slot < L; slot += 32) {
+        const float p = pbuf[slot] / sum;
+        pbuf[slot] = p;
+        if (attn_out) attn_out[slot] = p;
+    }
+    __syncwarp();
+    const int ld = hd < 32 ? hd : 32;              // lanes along the head dimension
+    const int nsp = 32 / ld;                       // slot partitions
+    const int sp = lane / ld, d0 = lane - sp * ld;
+    for (int d = d0; d < hd; d += ld) {
+        float acc = 0.f;
+        for (int slot = sp; slot < L; slot += nsp) acc = fmaf(pbuf[slot], Vr[(size_t)slot * E + d], acc);
+        for (int o = ld; o < 32; o <<= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (sp == 0) out[d * os] = acc;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (generic): one CTA per group of G trajectories, whole horizon in one launch.
+// Activations live in shared memory, transposed [channel][g]; weights stream from L2; the KV window of
+// the group is a ring in the global workspace.  Handles any n_embd (multiple of 32) / head size.
+// ------------------------------------------------------------------------------------------------
+struct RolloutParams {
+    const float* blob;
+    const float* pe;
+    const float* x0;
+    long long x0_stride;
+    float* out;
+    long long out_stride;
+    float* kv;
+    float* presents;
+    int B, S, use_cache;
+    float eps;
+    Gpt2Layout lay;
+    int use_tma;
+};
+
+template <int G>
+__device__ __forceinline__ void block_ln_T(const float* xT, float* outT, const float* __restrict__ w,
+                                           const float* __restrict__ b, int E, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int g = warp; g < G; g += nw) {
+        float s = 0.f;
+        for (int c = lane; c < E; c += 32) s += xT[c * G + g];
+        const float mean = warp_sum(s) / (float)E;
+        float v = 0.f;
+        for (int c = lane; c < E; c += 32) {
+            const float d = xT[c * G + g] - mean;
+            v = fmaf(d, d, v);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + eps);
+        for (int c = lane; c < E; c += 32)
+            outT[c * G + g] = (xT[c * G + g] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(GEN_THREADS) rollout_generic_kernel(RolloutParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const Gpt2Layout& L = p.lay;
+    const int E = L.E, H = L.n_head, hd = L.hd, C = L.n_ctx;
+    float* xT = sm;                       // [E][G]   residual stream
+    float* aT = xT + E * G;               // [E][G]   gemv input / attention output
+    float* qT = aT + E * G;               // [3E][G]  q | k | v
+    float* hT = qT + 3 * E * G;           // [4E][G]  MLP hidden
+    float* part = hT + 4 * E * G;         // [blockDim*G]
+    float* pbuf = part + GEN_THREADS * G; // [nwarps][C]
+    const int tid = threadIdx.x, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int b0 = blockIdx.x * G;
+    const size_t kv_per_g = (size_t)L.n_layer * 2 * C * E;
+    float* kvb = p.kv + (size_t)blockIdx.x * G * kv_per_g;
+
+    for (int i = tid; i < E * G; i += blockDim.x) {
+        const int c = i / G, g = i - c * G;
+        const int b = b0 + g;
+        const float x = (b < p.B) ? p.x0[(size_t)b * p.x0_stride + c] : 0.f;
+        xT[i] = x + __ldg(p.pe + c);      // position 0
+    }
+    __syncthreads();
+
+    for (int s = 0; s < p.S; s++) {
+        const int Lk = p.use_cache ? min(s + 1, C) : 1;
+        const int slot = p.use_cache ? (s % C) : 0;
+        for (int l = 0; l < L.n_layer; l++) {
+            const float* w = p.blob + (size_t)l * L.layer_stride;
+            block_ln_T<G>(xT, aT, w + L.ln1w, w + L.ln1b, E, p.eps);
+            __syncthreads();
+            block_gemv<G>(w + L.wqkv, w + L.bqkv, E, 3 * E, aT, part,
+                          [&](int n, int g, float v) { qT[n * G + g] = v; });
+            __syncthreads();
+            // append (k, v) to the ring
+            for (int i = tid; i < 2 * E * G; i += blockDim.x) {
+                const int g = i / (2 * E), r = i - g * 2 * E;
+                const int which = r / E, e = r - which * E;
+                kvb[(size_t)g * kv_per_g + ((size_t)(l * 2 + which) * C + slot) * E + e] =
+                    qT[((1 + which) * E + e) * G + g];
+            }
+            __syncthreads();
+            for (int pair = warp; pair < G * H; pair += nw) {
+                const int g = pair / H, hh = pair - g * H;
+                const float* Kr = kvb + (size_t)g * kv_per_g + (size_t)(l * 2 + 0) * C * E + hh * hd;
+                const float* Vr = kvb + (size_t)g * kv_per_g + (size_t)(l * 2 + 1) * C * E + hh * hd;
+                warp_attention(qT + (hh * hd) * G + g, G, Kr, Vr, E, hd, Lk, pbuf + warp * C,
+                               aT + (hh * hd) * G + g, G, nullptr);
+            }
+            __syncthreads();
+            block_gemv<G>(w + L.wproj, w + L.bproj, E, E, aT, part,
+                          [&](int n, int g, float v) { xT[n * G + g] += v; });
+            __syncthreads();
+            block_ln_T<G>(xT, aT, w + L.ln2w, w + L.ln2b, E, p.eps);
+            __syncthreads();
+            block_gemv<G>(w + L.wfc, w + L.bfc, E, 4 * E, aT, part,
+                          [&](int n, int g, float v) { hT[n * G + g] = gelu_new(v); });
+            __syncthreads();
+            block_gemv<G>(w + L.wpr, w + L.bpr, 4 * E, E, hT, part,
+                          [&](int n, int g, float v) { xT[n * G + g] += v; });
+            __syncthreads();
+        }
+        block_ln_T<G>(xT, aT, p.blob + L.lnfw, p.blob + L.lnfb, E, p.eps);
+        __syncthreads();
+        const int pnext = p.use_cache ? min(s + 1, C - 1) : 0;
+        block_gemv<G>(p.blob + L.wf, p.blob + L.bf, E, E, aT, part, [&](int n, int g, float v) {
+            const int b = b0 + g;
+            if (b < p.B) p.out[(size_t)b * p.out_stride + (size_t)s * E + n] = v;
+            xT[n * G + g] = v + __ldg(p.pe + pnext * E + n);
+        });
+        __syncthreads();
+    }
+
+    if (p.presents != nullptr && p.use_cache) {
+        // presents[l][which][b][h][t][d], chronological t; entry s lives in ring slot s % C
+        const int Tk = min(p.S, C);
+        const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+        for (int g = 0; g < G; g++) {
+            const int b = b0 + g;
+            if (b >= p.B) break;
+            for (int i = tid; i < L.n_layer * 2 * Tk * E; i += blockDim.x) {
+                const int e = i % E;
+                int r = i / E;
+                const int t = r % Tk;
+                r /= Tk;
+                const int which = r & 1, l = r >> 1;
+                const int sl = (p.S - Tk + t) % C;
+                const int hh = e / hd, d = e - hh * hd;
+                p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                    kvb[(size_t)g * kv_per_g + ((size_t)(l * 2 + which) * C + sl) * E + e];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (E = 32, head size 8): persistent warp-autonomous rollout.
+//   * every weight of the model (<= 227 KB) is staged ONCE per CTA into shared memory by TMA bulk copies;
+//   * one warp owns G trajectories for the whole horizon: lane n owns channel n of the residual stream
+//     (registers), GEMVs are register-blocked over the G trajectories with weights read from smem
+//     (one conflict-free row per k) and activations broadcast from a per-warp transposed tile;
+//   * no CTA-wide barrier inside the step loop (only __syncwarp);
+//   * the KV window of the G trajectories is a ring in a per-warp slice of the global workspace that is
+//     reused wave after wave, so it stays L2-resident; window reads are 256-bit loads.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void load_a(const float* s, float (&a)[G]) {
+    if constexpr (G == 8) {
+        const float4 u = *reinterpret_cast<const float4*>(s);
+        const float4 v = *reinterpret_cast<const float4*>(s + 4);
+        a[0] = u.x; a[1] = u.y; a[2] = u.z; a[3] = u.w; a[4] = v.x; a[5] = v.y; a[6] = v.z; a[7] = v.w;
+    } else if constexpr (G == 4) {
+        const float4 u = *reinterpret_cast<const float4*>(s);
+        a[0] = u.x; a[1] = u.y; a[2] = u.z; a[3] = u.w;
+    } else if constexpr (G == 2) {
+        const float2 u = *reinterpret_cast<const float2*>(s);
+        a[0] = u.x; a[1] = u.y;
+    } else {
+        a[0] = s[0];
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void store_T(float* scr, int row, const float (&x)[G]) {
+    float* d = scr + row * G;
+    if constexpr (G == 8) {
+        *reinterpret_cast<float4*>(d) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    } else if constexpr (G == 4) {
+        *reinterpret_cast<float4*>(d) = make_float4(x[0], x[1], x[2], x[3]);
+    } else if constexpr (G == 2) {
+        *reinterpret_cast<float2*>(d) = make_float2(x[0], x[1]);
+    } else {
+        d[0] = x[0];
+    }
+}
+
+// LayerNorm over the 32 channels of each of the G trajectories, in place on the transposed tile
+// scr[c*G+g].  Lane `lane` touches flat elements i*32+lane (conflict-free); its trajectory is lane % G.
+template <int G>
+__device__ __forceinline__ void warp_ln_T(float* scr, const float* lw, const float* lb, float eps, int lane) {
+    float x[G];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+        x[i] = scr[i * 32 + lane];
+        s += x[i];
+    }
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) s += __shfl_xor_sync(FULL, s, o);
+    const float mean = s * (1.0f / 32.0f);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+        x[i] -= mean;
+        v = fmaf(x[i], x[i], v);
+    }
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+    const float rstd = 1.0f / sqrtf(v * (1.0f / 32.0f) + eps);
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+        const int c = (i * 32 + lane) / G;
+        scr[i * 32 + lane] = x[i] * rstd * lw[c] + lb[c];
+    }
+}
+
+// acc[c][g] += sum_k scr[k*G+g] * W[k*ldw + lane + 32*c]
+template <int G, int C>
+__device__ __forceinline__ void warp_gemv(const float* scr, const float* W, int K, int ldw, int lane,
+                                          float (&acc)[C][G]) {
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        float a[G];
+        load_a<G>(scr + k * G, a);
+        float w[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) w[c] = W[k * ldw + lane + 32 * c];
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+            for (int g = 0; g < G; g++) acc[c][g] = fmaf(a[g], w[c], acc[c][g]);
+    }
+}
+
+// attention of one trajectory for all 4 heads (hd = 8): lane = (head = lane/8, sg = lane%8); the lane
+// scores slots sg, sg+8, ... of its head, then the 8 lanes of a head reduce-scatter the output so that
+// lane n ends up with channel n.  MAXI = ceil(n_ctx / 8).
+template <int MAXI>
+__device__ __forceinline__ float warp_attn_hd8(float qmine, const float* Kp, const float* Vp, int L, int lane) {
+    const int hb = lane & 24, sg = lane & 7;
+    float qh[8];
+#pragma unroll
+    for (int d = 0; d < 8; d++) qh[d] = __shfl_sync(FULL, qmine, hb + d);
+    float sc[MAXI];
+    float m = -INFINITY;
+    const float scale = 2.8284271247461903f;       // sqrt(8)
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) {
+        const int slot = sg + 8 * i;
+        sc[i] = -INFINITY;
+        if (slot < L) {
+            float kk[8];
+            ldg256(Kp + slot * 32 + hb, kk);
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < 8; d++) s = fmaf(qh[d], kk[d], s);
+            sc[i] = s / scale;
+        }
+        m = fmaxf(m, sc[i]);
+    }
+    m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) {
+        sc[i] = (sg + 8 * i < L) ? expf(sc[i] - m) : 0.f;
+        sum += sc[i];
+    }
+    sum += __shfl_xor_sync(FULL, sum, 1);
+    sum += __shfl_xor_sync(FULL, sum, 2);
+    sum += __shfl_xor_sync(FULL, sum, 4);
+    float o[8];
+#pragma unroll
+    for (int d = 0; d < 8; d++) o[d] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) {
+        const int slot = sg + 8 * i;
+        if (slot < L) {
+            float vv[8];
+            ldg256(Vp + slot * 32 + hb, vv);
+            const float pw = sc[i] / sum;
+#pragma unroll
+            for (int d = 0; d < 8; d++) o[d] = fmaf(pw, vv[d], o[d]);
+        }
+    }
+    // reduce-scatter across the 8 lanes of the head: lane sg keeps dimension sg
+    float t[4];
+    const bool b4 = sg & 4, b2 = sg & 2, b1 = sg & 1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float send = b4 ? o[j] : o[j + 4];
+        const float keep = b4 ? o[j + 4] : o[j];
+        t[j] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    float u[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const float send = b2 ? t[j] : t[j + 2];
+        const float keep = b2 ? t[j + 2] : t[j];
+        u[j] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    const float send = b1 ? u[0] : u[1];
+    const float keep = b1 ? u[1] : u[0];
+    return keep + __shfl_xor_sync(FULL, send, 1);
+}
+
+template <int G, int MAXI, bool CACHE>
+__global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t bar;
+    const Gpt2Layout& L = p.lay;
+    const int C = L.n_ctx, NL = L.n_layer;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, W = blockDim.x >> 5;
+    float* wsm = sm;
+    float* scr = sm + L.total + warp * (64 * G);
+
+    // ---- stage all weights into shared memory ----
+    if (p.use_tma) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)L.total * 4u;
+            mbar_expect_tx(&bar, bytes);
+            const uint32_t CH = 32768u;
+            for (uint32_t off = 0; off < bytes; off += CH) {
+                const uint32_t n = min(CH, bytes - off);
+                bulk_g2s(reinterpret_cast<char*>(wsm) + off, reinterpret_cast<const char*>(p.blob) + off, n, &bar);
+            }
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(p.blob);
+        float4* dst = reinterpret_cast<float4*>(wsm);
+        for (int i = tid; i < L.total / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+
+    const int ngroups = (p.B + G - 1) / G;
+    const size_t kv_per_g = (size_t)NL * 2 * C * 32;
+    float* kvw = CACHE ? p.kv + (size_t)(blockIdx.x * W + warp) * G * kv_per_g : nullptr;
+    const float* gw = wsm + L.lnfw;     // globals: lnfw, lnfb, wf, bf are consecutive
+
+    for (int grp = blockIdx.x * W + warp; grp < ngroups; grp += gridDim.x * W) {
+        const int b0 = grp * G;
+        float h[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int b = b0 + g;
+            h[g] = (b < p.B ? p.x0[(size_t)b * p.x0_stride + lane] : 0.f) + __ldg(p.pe + lane);
+        }
+        for (int s = 0; s < p.S; s++) {
+            const int Lk = CACHE ? min(s + 1, C) : 1;
+            const int slot = CACHE ? (s % C) : 0;
+            for (int l = 0; l < NL; l++) {
+                const float* w = wsm + l * L.layer_stride;
+                // ---- LN1 ----
+                store_T<G>(scr, lane, h);
+                __syncwarp();
+                warp_ln_T<G>(scr, w + L.ln1w, w + L.ln1b, p.eps, lane);
+                __syncwarp();
+                float o[G];
+                if constexpr (CACHE) {
+                    float qkv[3][G];
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int g = 0; g < G; g++) qkv[c][g] = w[L.bqkv + lane + 32 * c];
+                    warp_gemv<G, 3>(scr, w + L.wqkv, 32, 96, lane, qkv);
+                    // ---- append (k, v) to the ring, then attend over the window ----
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        float* kp = kvw + (size_t)g * kv_per_g + (size_t)(l * 2) * C * 32;
+                        kp[slot * 32 + lane] = qkv[1][g];
+                        kp[C * 32 + slot * 32 + lane] = qkv[2][g];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const float* kp = kvw + (size_t)g * kv_per_g + (size_t)(l * 2) * C * 32;
+                        o[g] = warp_attn_hd8<MAXI>(qkv[0][g], kp, kp + C * 32, Lk, lane);
+                    }
+                } else {
+                    // window of one key: softmax == 1 exactly, so the head output is v itself
+                    float vv[1][G];
+#pragma unroll
+                    for (int g = 0; g < G; g++) vv[0][g] = w[L.bqkv + 64 + lane];
+                    warp_gemv<G, 1>(scr, w + L.wqkv + 64, 32, 96, lane, vv);
+#pragma unroll
+                    for (int g = 0; g < G; g++) o[g] = vv[0][g];
+                }
+                // ---- output projection + residual ----
+                __syncwarp();
+                store_T<G>(scr, lane, o);
+                __syncwarp();
+                {
+                    float acc[1][G];
+#pragma unroll
+                    for (int g = 0; g < G; g++) acc[0][g] = w[L.bproj + lane];
+                    warp_gemv<G, 1>(scr, w + L.wproj, 32, 32, lane, acc);
+#pragma unroll
+                    for (int g = 0; g < G; g++) h[g] += acc[0][g];
+                }
+                // ---- LN2 + MLP ----
+                __syncwarp();
+                store_T<G>(scr, lane, h);
+                __syncwarp();
+                warp_ln_T<G>(scr, w + L.ln2w, w + L.ln2b, p.eps, lane);
+                __syncwarp();
+                float f[4][G];
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int g = 0; g < G; g++) f[c][g] = w[L.bfc + lane + 32 * c];
+                warp_gemv<G, 4>(scr, w + L.wfc, 32, 128, lane, f);
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int g = 0; g < G; g++) f[c][g] = gelu_new(f[c][g]);
+                float acc[1][G];
+#pragma unroll
+                for (int g = 0; g < G; g++) acc[0][g] = w[L.bpr + lane];
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    __syncwarp();
+                    store_T<G>(scr, lane, f[2 * half]);
+                    store_T<G>(scr, lane + 32, f[2 * half + 1]);
+                    __syncwarp();
+                    warp_gemv<G, 1>(scr, w + L.wpr + half * 64 * 32, 64, 32, lane, acc);
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) h[g] += acc[0][g];
+                __syncwarp();
+            }
+            // ---- final LN + linear head ----
+            store_T<G>(scr, lane, h);
+            __syncwarp();
+            warp_ln_T<G>(scr, gw, gw + 32, p.eps, lane);
+            __syncwarp();
+            float y[1][G];
+#pragma unroll
+            for (int g = 0; g < G; g++) y[0][g] = gw[64 + 1024 + lane];
+            warp_gemv<G, 1>(scr, gw + 64, 32, 32, lane, y);
+            const int pnext = CACHE ? min(s + 1, C - 1) : 0;
+            const float pe = __ldg(p.pe + pnext * 32 + lane);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int b = b0 + g;
+                if (b < p.B) p.out[(size_t)b * p.out_stride + (size_t)s * 32 + lane] = y[0][g];
+                h[g] = y[0][g] + pe;
+            }
+            __syncwarp();
+        }
+        if (CACHE && p.presents != nullptr) {
+            const int Tk = min(p.S, C);
+            const int H = 4, hd = 8;
+            const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+            const int hh = lane >> 3, d = lane & 7;
+            for (int g = 0; g < G; g++) {
+                const int b = b0 + g;
+                if (b >= p.B) break;
+                for (int r = 0; r < NL * 2 * Tk; r++) {
+                    const int t = r % Tk, lw = r / Tk;          // lw = l*2 + which
+                    const int which = lw & 1, l = lw >> 1;
+                    const int sl = (p.S - Tk + t) % C;
+                    p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                        kvw[(size_t)g * kv_per_g + ((size_t)lw * C + sl) * 32 + lane];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: teacher-forced forward of T tokens (optional past of Tp keys), one CTA per batch element.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_FWD_LAYERS = 32;
+
+struct ForwardParams {
+    const float* blob;
+    const float* pe;
+    const float* x;
+    const float* past[MAX_FWD_LAYERS];      // per-layer pointers (passed by value), valid if has_past
+    float* hidden;
+    float* presents[MAX_FWD_LAYERS];
+    float* attn[MAX_FWD_LAYERS];
+    int has_past, has_presents, has_attn;
+    int B, T, Tp;
+    float eps;
+    Gpt2Layout lay;
+};
+
+constexpr int TG = 8;              // tokens per GEMV register block
+
+__global__ void __launch_bounds__(GEN_THREADS) forward_kernel(ForwardParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const Gpt2Layout& L = p.lay;
+    const int E = L.E, H = L.n_head, hd = L.hd, C = L.n_ctx;
+    const int T = p.T, Tp = p.Tp, Tk = Tp + T;
+    const int nch = (T + TG - 1) / TG, TP = nch * TG;
+    float* x = sm;                         // [TP][E]   residual, row-major
+    float* a = x + TP * E;                 // [nch][E][TG]  gemv input (chunked, transposed)
+    float* q = a + TP * E;                 // [TP][E]   queries, row-major
+    float* ks = q + TP * E;                // [C][E]
+    float* vs = ks + C * E;                // [C][E]
+    float* hb = vs + C * E;                // [nch][4E][TG]
+    float* part = hb + TP * 4 * E;         // [blockDim*TG]
+    float* pbuf = part + GEN_THREADS * TG; // [nwarps][C]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const int b = blockIdx.x;
+
+    for (int i = tid; i < TP * E; i += blockDim.x) {
+        const int t = i / E, c = i - t * E;
+        // position id = past_length + t as float (phys_transformer_gpt2.py:198)
+        x[i] = (t < T) ? p.x[((size_t)b * T + t) * E + c] + __ldg(p.pe + (Tp + t) * E + c) : 0.f;
+    }
+    __syncthreads();
+
+    auto ln_to_a = [&](const float* lw, const float* lb) {
+        for (int t = warp; t < TP; t += nw) {
+            float s = 0.f;
+            for (int c = lane; c < E; c += 32) s += x[t * E + c];
+            const float mean = warp_sum(s) / (float)E;
+            float v = 0.f;
+            for (int c = lane; c < E; c += 32) {
+                const float d = x[t * E + c] - mean;
+                v = fmaf(d, d, v);
+            }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + p.eps);
+            float* dst = a + (t / TG) * E * TG + (t % TG);
+            for (int c = lane; c < E; c += 32)
+                dst[c * TG] = (x[t * E + c] - mean) * rstd * __ldg(lw + c) + __ldg(lb + c);
+        }
+    };
+
+    for (int l = 0; l < L.n_layer; l++) {
+        const float* w = p.blob + (size_t)l * L.layer_stride;
+        // past keys/values -> window rows [0, Tp)
+        if (Tp > 0) {
+            const float* pk = p.past[l];       // [2][B][H][Tp][hd]
+            for (int i = tid; i < 2 * Tp * E; i += blockDim.x) {
+                const int which = i / (Tp * E);
+                int r = i - which * Tp * E;
+                const int t = r / E, e = r - t * E;
+                const int hh = e / hd, d = e - hh * hd;
+                const float v = pk[((((size_t)which * p.B + b) * H + hh) * Tp + t) * hd + d];
+                (which ? vs : ks)[t * E + e] = v;
+            }
+        }
+        ln_to_a(w + L.ln1w, w + L.ln1b);
+        __syncthreads();
+        for (int ch = 0; ch < nch; ch++) {
+            block_gemv<TG>(w + L.wqkv, w + L.bqkv, E, 3 * E, a + ch * E * TG, part, [&](int n, int g, float v) {
+                const int t = ch * TG + g;
+                if (t >= T) return;
+                if (n < E) q[t * E + n] = v;
+                else if (n < 2 * E) ks[(Tp + t) * E + (n - E)] = v;
+                else vs[(Tp + t) * E + (n - 2 * E)] = v;
+            });
+            __syncthreads();
+        }
+        if (p.has_presents) {
+            float* pr = p.presents[l];         // [2][B][H][Tk][hd]
+            for (int i = tid; i < 2 * Tk * E; i += blockDim.x) {
+                const int which = i / (Tk * E);
+                int r = i - which * Tk * E;
+                const int t = r / E, e = r - t * E;
+                const int hh = e / hd, d = e - hh * hd;
+                pr[((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] = (which ? vs : ks)[t * E + e];
+            }
+        }
+        // causal attention: query t sees keys [0, Tp + t]
+        for (int pair = warp; pair < T * H; pair += nw) {
+            const int t = pair / H, hh = pair - t * H;
+            float* ao = nullptr;
+            if (p.has_attn) {
+                ao = p.attn[l] + (((size_t)b * H + hh) * T + t) * Tk;
+                for (int j = Tp + t + 1 + lane; j < Tk; j += 32) ao[j] = 0.f;   // masked: exp(-1e4 - max) == 0
+            }
+            warp_attention(q + t * E + hh * hd, 1, ks + hh * hd, vs + hh * hd, E, hd, Tp + t + 1, pbuf + warp * C,
+                           a + (t / TG) * E * TG + (hh * hd) * TG + (t % TG), TG, ao);
+        }
+        __syncthreads();
+        for (int ch = 0; ch < nch; ch++) {
+            block_gemv<TG>(w + L.wproj, w + L.bproj, E, E, a + ch * E * TG, part, [&](int n, int g, float v) {
+                const int t = ch * TG + g;
+                if (t < T) x[t * E + n] += v;
+            });
+            __syncthreads();
+        }
+        ln_to_a(w + L.ln2w, w + L.ln2b);
+        __syncthreads();
+        for (int ch = 0; ch < nch; ch++) {
+            block_gemv<TG>(w + L.wfc, w + L.bfc, E, 4 * E, a + ch * E * TG, part, [&](int n, int g, float v) {
+                hb[ch * 4 * E * TG + n * TG + g] = gelu_new(v);
+            });
+            __syncthreads();
+        }
+        for (int ch = 0; ch < nch; ch++) {
+            block_gemv<TG>(w + L.wpr, w + L.bpr, 4 * E, E, hb + ch * 4 * E * TG, part, [&](int n, int g, float v) {
+                const int t = ch * TG + g;
+                if (t < T) x[t * E + n] += v;
+            });
+            __syncthreads();
+        }
+    }
+    ln_to_a(p.blob + L.lnfw, p.blob + L.lnfb);
+    __syncthreads();
+    for (int ch = 0; ch < nch; ch++) {
+        block_gemv<TG>(p.blob + L.wf, p.blob + L.bf, E, E, a + ch * E * TG, part, [&](int n, int g, float v) {
+            const int t = ch * TG + g;
+            if (t < T) p.hidden[((size_t)b * T + t) * E + n] = v;
+        });
+        __syncthreads();
+    }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    // out[c][r] = in[r][c]
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) {
+        const int r = i / cols, c = i - r * cols;
+        out[(size_t)c * rows + r] = in[i];
+    }
+}
+
+bool valid(trpx_gpt2_t h) { return h != nullptr && h->magic == 0x67707432u; }
+
+size_t generic_rollout_smem(const Gpt2Layout& L, int G) {
+    return sizeof(float) * ((size_t)(L.E * G) * (1 + 1 + 3 + 4) + (size_t)GEN_THREADS * G +
+                            (size_t)(GEN_THREADS / 32) * L.n_ctx);
+}
+
+template <int G>
+int launch_generic(trpx_gpt2_t h, const RolloutParams& p, int grid, size_t smem, cudaStream_t st) {
+    TRPX_CUDA(cudaFuncSetAttribute(rollout_generic_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_generic_kernel<G><<<grid, GEN_THREADS, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+template <int G, int MAXI, bool CACHE>
+int launch_e32_one(const RolloutParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    TRPX_CUDA(cudaFuncSetAttribute(rollout_e32_kernel<G, MAXI, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    rollout_e32_kernel<G, MAXI, CACHE><<<grid, block, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+template <int G>
+int launch_e32(const RolloutParams& p, int maxi, int grid, int block, size_t smem, cudaStream_t st) {
+    if (!p.use_cache) return launch_e32_one<G, 1, false>(p, grid, block, smem, st);
+    switch (maxi) {
+        case 1: return launch_e32_one<G, 1, true>(p, grid, block, smem, st);
+        case 2: return launch_e32_one<G, 2, true>(p, grid, block, smem, st);
+        case 4: return launch_e32_one<G, 4, true>(p, grid, block, smem, st);
+        default: return launch_e32_one<G, 8, true>(p, grid, block, smem, st);
+    }
+}
+
+int ensure_kv(trpx_gpt2_t h, size_t bytes) {
+    if (bytes <= h->kv_bytes) return TRPX_OK;
+    if (h->kv) {
+        TRPX_CUDA(cudaDeviceSynchronize());
+        TRPX_CUDA(cudaFree(h->kv));
+        h->kv = nullptr;
+        h->kv_bytes = 0;
+    }
+    TRPX_CUDA(cudaMalloc(&h->kv, bytes));
+    h->kv_bytes = bytes;
+    return TRPX_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int trpx_gpt2_create(const trpx_gpt2_config* cfg, int device, trpx_gpt2_t* out) {
+    TRPX_REQUIRE(cfg != nullptr && out != nullptr, "trpx_gpt2_create: null argument");
+    TRPX_REQUIRE(cfg->n_embd > 0 && cfg->n_embd % 32 == 0 && cfg->n_embd <= 256,
+                 "n_embd=%d unsupported (multiple of 32, <= 256)", cfg->n_embd);
+    TRPX_REQUIRE(cfg->n_head > 0 && cfg->n_embd % cfg->n_head == 0, "n_embd %% n_head != 0");
+    TRPX_REQUIRE(cfg->n_layer > 0 && cfg->n_layer <= 64, "n_layer=%d unsupported", cfg->n_layer);
+    TRPX_REQUIRE(cfg->n_ctx > 0 && cfg->n_ctx <= 1024, "n_ctx=%d unsupported", cfg->n_ctx);
+    int ndev = 0;
+    TRPX_CUDA(cudaGetDeviceCount(&ndev));
+    TRPX_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    DeviceGuard guard(device);
+    trpx_gpt2* h = new (std::nothrow) trpx_gpt2();
+    TRPX_REQUIRE(h != nullptr, "out of host memory");
+    h->cfg = *cfg;
+    h->device = device;
+    h->lay = Gpt2Layout::make(cfg->n_embd, cfg->n_layer, cfg->n_ctx, cfg->n_head);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (cudaMalloc(&h->blob, sizeof(float) * h->lay.total) != cudaSuccess ||
+        cudaMalloc(&h->pe, sizeof(float) * cfg->n_ctx * cfg->n_embd) != cudaSuccess) {
+        cudaFree(h->blob);
+        delete h;
+        return set_error(TRPX_E_CUDA, "cudaMalloc of the weight blob failed");
+    }
+    *out = h;
+    return TRPX_OK;
+}
+
+int trpx_gpt2_destroy(trpx_gpt2_t h) {
+    if (!valid(h)) return set_error(TRPX_E_STATE, "trpx_gpt2_destroy: invalid handle");
+    DeviceGuard guard(h->device);
+    cudaFree(h->blob);
+    cudaFree(h->pe);
+    cudaFree(h->kv);
+    h->magic = 0;
+    delete h;
+    return TRPX_OK;
+}
+
+int trpx_gpt2_num_weight_tensors(trpx_gpt2_t h) { return valid(h) ? 12 * h->cfg.n_layer + 4 : -1; }
+
+int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const float* pe_dev, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    TRPX_REQUIRE(w != nullptr && n == 12 * h->cfg.n_layer + 4, "expected %d weight tensors, got %d",
+                 12 * h->cfg.n_layer + 4, n);
+    for (int i = 0; i < n; i++) TRPX_REQUIRE(w[i] != nullptr, "weight tensor %d is null", i);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Gpt2Layout& L = h->lay;
+    const int E = L.E;
+    auto cp = [&](int off, const float* src, size_t cnt) {
+        return cudaMemcpyAsync(h->blob + off, src, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    };
+    for (int l = 0; l < L.n_layer; l++) {
+        const int base = l * L.layer_stride;
+        const float* const* t = w + 12 * l;
+        const int offs[12] = {L.ln1w, L.ln1b, L.wqkv, L.bqkv, L.wproj, L.bproj, L.ln2w, L.ln2b, L.wfc, L.bfc, L.wpr, L.bpr};
+        const size_t cnts[12] = {(size_t)E, (size_t)E, (size_t)3 * E * E, (size_t)3 * E, (size_t)E * E, (size_t)E,
+                                 (size_t)E, (size_t)E, (size_t)4 * E * E, (size_t)4 * E, (size_t)4 * E * E, (size_t)E};
+        for (int i = 0; i < 12; i++) TRPX_CUDA(cp(base + offs[i], t[i], cnts[i]));
+    }
+    const float* const* g = w + 12 * L.n_layer;
+    TRPX_CUDA(cp(L.lnfw, g[0], E));
+    TRPX_CUDA(cp(L.lnfb, g[1], E));
+    transpose_kernel<<<(E * E + 255) / 256, 256, 0, st>>>(g[2], h->blob + L.wf, E, E);   // [out][in] -> [in][out]
+    TRPX_CUDA(cudaGetLastError());
+    TRPX_CUDA(cp(L.bf, g[3], E));
+    if (pe_dev != nullptr) {
+        TRPX_CUDA(cudaMemcpyAsync(h->pe, pe_dev, sizeof(float) * L.n_ctx * E, cudaMemcpyDeviceToDevice, st));
+    } else {
+        // phys_transformer_gpt2.py:215-219 evaluated in double, rounded once to float
+        std::vector<float> pe((size_t)L.n_ctx * E);
+        for (int p = 0; p < L.n_ctx; p++)
+            for (int c = 0; c < E; c++) {
+                if (c % 2 == 0) {
+                    const float denom = powf(10000.0f, (float)(2.0f * (float)(c / 2) / (float)E));
+                    pe[(size_t)p * E + c] = (float)sin((double)((float)p / denom));
+                } else {
+                    pe[(size_t)p * E + c] = (float)cos((double)p);
+                }
+            }
+        TRPX_CUDA(cudaMemcpyAsync(h->pe, pe.data(), sizeof(float) * pe.size(), cudaMemcpyHostToDevice, st));
+        TRPX_CUDA(cudaStreamSynchronize(st));
+    }
+    h->loaded = true;
+    return TRPX_OK;
+}
+
+int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    TRPX_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0..3");
+    TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 12, "warps_per_cta must be 0..12");
+    TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
+                     traj_per_warp == 8, "traj_per_warp must be 0,1,2,4,8");
+    h->tune_variant = variant;
+    h->tune_warps = warps_per_cta;
+    h->tune_g = traj_per_warp;
+    h->tune_max_ctas = max_ctas;
+    return TRPX_OK;
+}
+
+int trpx_gpt2_last_launch(trpx_gpt2_t h, int* variant, int* grid, int* block, int* smem, int* group) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (variant) *variant = h->last_variant;
+    if (grid) *grid = h->last_grid;
+    if (block) *block = h->last_block;
+    if (smem) *smem = h->last_smem;
+    if (group) *group = h->last_group;
+    return TRPX_OK;
+}
+
+int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float* out, long long out_stride, int B,
+                      int S, int use_cache, float* presents, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "trpx_gpt2_rollout: weights not loaded");
+    TRPX_REQUIRE(x0 != nullptr && out != nullptr, "null tensor");
+    TRPX_REQUIRE(B >= 0 && S >= 0, "negative size");
+    TRPX_REQUIRE(presents == nullptr || use_cache, "presents requires use_cache");
+    if (B == 0 || S == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Gpt2Layout& L = h->lay;
+    RolloutParams p{};
+    p.blob = h->blob; p.pe = h->pe; p.x0 = x0; p.x0_stride = x0_stride; p.out = out; p.out_stride = out_stride;
+    p.presents = presents; p.B = B; p.S = S; p.use_cache = use_cache ? 1 : 0; p.eps = h->cfg.ln_eps; p.lay = L;
+    p.use_tma = (h->tune_variant == 3) ? 0 : 1;
+    const size_t kv_per_traj = (size_t)L.n_layer * 2 * L.n_ctx * L.E * sizeof(float);
+
+    // ---- E = 32 / head size 8 warp kernel, if the whole model fits in shared memory ----
+    const bool e32_shape = (L.E == 32 && L.n_head == 4 && L.n_ctx <= 64);
+    const size_t wbytes = (size_t)L.total * sizeof(float);
+    const int scr_per_warp_g1 = 64 * (int)sizeof(float);
+    bool use_e32 = e32_shape && h->tune_variant != 1 && wbytes + (size_t)scr_per_warp_g1 + 1024 <= (size_t)h->smem_optin;
+    if (use_e32) {
+        const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
+        int G = h->tune_g;
+        if (G == 0) {
+            // enough groups to give every SM at least ~4 warps of work, else shrink the group
+            G = 8;
+            while (G > 1 && (long long)(B + G - 1) / G < (long long)sms * 4) G >>= 1;
+        }
+        const int ngroups = (B + G - 1) / G;
+        const int max_w = (int)std::min<size_t>(12, ((size_t)h->smem_optin - 1024 - wbytes) / ((size_t)64 * G * sizeof(float)));
+        if (max_w < 1) {
+            use_e32 = false;
+        } else {
+            const int grid = std::min(sms, ngroups);
+            const int want = h->tune_warps > 0 ? h->tune_warps : 8;
+            const int Wc = std::max(1, std::min(std::min(want, max_w), (ngroups + grid - 1) / grid));
+            const size_t smem = wbytes + (size_t)Wc * 64 * G * sizeof(float);
+            if (use_cache) {
+                int rc = ensure_kv(h, (size_t)grid * Wc * G * kv_per_traj);
+                if (rc) return rc;
+            }
+            p.kv = h->kv;
+            int maxi = 1;
+            while (maxi * 8 < L.n_ctx) maxi <<= 1;
+            h->last_variant = 2; h->last_grid = grid; h->last_block = Wc * 32; h->last_smem = (int)smem; h->last_group = G;
+            switch (G) {
+                case 8: return launch_e32<8>(p, maxi, grid, Wc * 32, smem, st);
+                case 4: return launch_e32<4>(p, maxi, grid, Wc * 32, smem, st);
+                case 2: return launch_e32<2>(p, maxi, grid, Wc * 32, smem, st);
+                default: return launch_e32<1>(p, maxi, grid, Wc * 32, smem, st);
+            }
+        }
+    }
+
+    // ---- generic kernel ----
+    int G = h->tune_g;
+    if (G == 0) {
+        G = 8;
+        while (G > 1 && (B + G - 1) / G < h->sm_count) G >>= 1;
+    }
+    size_t smem = generic_rollout_smem(L, G);
+    while (G > 1 && smem > (size_t)h->smem_optin) {
+        G >>= 1;
+        smem = generic_rollout_smem(L, G);
+    }
+    TRPX_REQUIRE(smem <= (size_t)h->smem_optin, "configuration needs %zu B of shared memory", smem);
+    const int grid = (B + G - 1) / G;
+    {
+        int rc = ensure_kv(h, (size_t)grid * G * kv_per_traj);
+        if (rc) return rc;
+    }
+    p.kv = h->kv;
+    h->last_variant = 1; h->last_grid = grid; h->last_block = GEN_THREADS; h->last_smem = (int)smem; h->last_group = G;
+    switch (G) {
+        case 8: return launch_generic<8>(h, p, grid, smem, st);
+        case 4: return launch_generic<4>(h, p, grid, smem, st);
+        case 2: return launch_generic<2>(h, p, grid, smem, st);
+        default: return launch_generic<1>(h, p, grid, smem, st);
+    }
+}
+
+int trpx_gpt2_forward(trpx_gpt2_t h, const float* x, const float* const* past, int Tp, float* hidden,
+                      float* const* presents, float* const* attn, int B, int T, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "trpx_gpt2_forward: weights not loaded");
+    TRPX_REQUIRE(x != nullptr && hidden != nullptr, "null tensor");
+    TRPX_REQUIRE(B >= 0 && T >= 0 && Tp >= 0, "negative size");
+    TRPX_REQUIRE((Tp == 0) == (past == nullptr), "past pointer / Tp mismatch");
+    TRPX_REQUIRE(Tp + T <= h->cfg.n_ctx, "past (%d) + tokens (%d) exceeds n_ctx (%d)", Tp, T, h->cfg.n_ctx);
+    if (B == 0 || T == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Gpt2Layout& L = h->lay;
+    const int nl = L.n_layer;
+    TRPX_REQUIRE(nl <= MAX_FWD_LAYERS, "forward supports at most %d layers", MAX_FWD_LAYERS);
+    ForwardParams p{};
+    for (int l = 0; l < nl; l++) {
+        TRPX_REQUIRE(!past || past[l], "past[%d] is null", l);
+        TRPX_REQUIRE(!presents || presents[l], "presents[%d] is null", l);
+        TRPX_REQUIRE(!attn || attn[l], "attn[%d] is null", l);
+        p.past[l] = past ? past[l] : nullptr;
+        p.presents[l] = presents ? presents[l] : nullptr;
+        p.attn[l] = attn ? attn[l] : nullptr;
+    }
+    p.has_past = past != nullptr; p.has_presents = presents != nullptr; p.has_attn = attn != nullptr;
+    p.blob = h->blob; p.pe = h->pe; p.x = x; p.hidden = hidden;
+    p.B = B; p.T = T; p.Tp = Tp; p.eps = h->cfg.ln_eps; p.lay = L;
+    const int TPd = ((T + TG - 1) / TG) * TG;
+    const size_t smem = sizeof(float) * ((size_t)TPd * L.E * 3 + (size_t)2 * L.n_ctx * L.E + (size_t)TPd * 4 * L.E +
+                                         (size_t)GEN_THREADS * TG + (size_t)(GEN_THREADS / 32) * L.n_ctx);
+    TRPX_REQUIRE(smem <= (size_t)h->smem_optin, "forward needs %zu B of shared memory", smem);
+    TRPX_CUDA(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    forward_kernel<<<B, GEN_THREADS, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+}  // extern "C"

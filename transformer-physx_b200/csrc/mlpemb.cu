@@ -1,0 +1,438 @@
+// Lorenz / Rossler Koopman embedding kernels (K3, K4) and the fused clip + Adam step.
+// Reference: trphysx/embedding/embedding_lorenz.py:94-105 (embed), :107-118 (recover), :120-142
+// (koopmanOperation), :144-157 (koopmanOperator); enn_trainer.py:97-99 (clip_grad_norm_ + optimizer.step).
+#include "mlpemb.cuh"
+#include <cmath>
+
+using namespace trpx;
+
+namespace {
+
+constexpr int EMB_THREADS = 128;
+constexpr int SPT = 2;             // samples per thread (weights broadcast from smem are reused SPT times)
+
+// ---- weight packer ---------------------------------------------------------------------------------
+struct PackSrc {
+    const float *mu, *sd, *W1, *b1, *W2, *b2, *lnw, *lnb, *V1, *c1, *V2, *c2, *kd, *ku;
+};
+
+__global__ void mlp_pack_kernel(PackSrc s, float* blob, MlpLayout L) {
+    const int Hd = L.Hd;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.total; i += stride) {
+        float v = 0.f;
+        if (i < L.encB) {                       // encA [Hd][4]
+            const int u = (i - L.encA) >> 2, j = (i - L.encA) & 3;
+            v = j < 3 ? s.W1[u * MS + j] : s.b1[u];
+        } else if (i < L.b2) {                  // encB [Hd][32] = W2[e][u]
+            const int u = (i - L.encB) / ME, e = (i - L.encB) % ME;
+            v = s.W2[e * Hd + u];
+        } else if (i < L.lnw) v = s.b2[i - L.b2];
+        else if (i < L.lnb) v = s.lnw[i - L.lnw];
+        else if (i < L.decA) v = s.lnb[i - L.lnb];
+        else if (i < L.decB) v = s.V1[i - L.decA];
+        else if (i < L.c2) {                    // decB [Hd][4]
+            const int u = (i - L.decB) >> 2, j = (i - L.decB) & 3;
+            v = j < 3 ? s.V2[j * Hd + u] : s.c1[u];
+        } else if (i < L.mu) { const int j = i - L.c2; v = j < 3 ? s.c2[j] : 0.f; }
+        else if (i < L.sd) { const int j = i - L.mu; v = j < 3 ? s.mu[j] : 0.f; }
+        else if (i < L.kd) { const int j = i - L.sd; v = j < 3 ? s.sd[j] : 1.f; }
+        else if (i < L.ku) v = s.kd[i - L.kd];
+        else if (i < L.W2) { const int j = i - L.ku; v = j < 61 ? s.ku[j] : 0.f; }
+        else if (i < L.V2) v = s.W2[i - L.W2];
+        else v = s.V2[i - L.V2];
+        blob[i] = v;
+    }
+}
+
+// ---- K3a: embed  x[N,3] -> g[N,32] --------------------------------------------------------------------
+// Thread-per-sample (SPT samples each): the 500 hidden units are streamed once; per unit the thread does
+// 3 FMAs (layer 1), a ReLU and 32 FMAs into its 32 output accumulators with weights BROADCAST from smem
+// (9 LDS.128 per unit shared by SPT samples).  LayerNorm(32) finishes in registers.
+// Optionally saves the normalised pre-affine activation and 1/std for the training backward.
+__global__ void __launch_bounds__(EMB_THREADS) mlp_embed_kernel(const float* __restrict__ blob, MlpLayout L,
+                                                                const float* __restrict__ x, float* __restrict__ g,
+                                                                long long N, float eps, float* __restrict__ zhat_out,
+                                                                float* __restrict__ rstd_out) {
+    extern __shared__ float4 sm4[];
+    const int Hd = L.Hd;
+    float4* sA = sm4;                 // [Hd]
+    float4* sB = sm4 + Hd;            // [Hd][8]
+    {
+        const float4* src = reinterpret_cast<const float4*>(blob + L.encA);
+        for (int i = threadIdx.x; i < Hd * 9; i += blockDim.x) sm4[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    float mu[MS], sd[MS];
+#pragma unroll
+    for (int j = 0; j < MS; j++) { mu[j] = __ldg(blob + L.mu + j); sd[j] = __ldg(blob + L.sd + j); }
+    const long long step = (long long)gridDim.x * blockDim.x * SPT;
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * SPT; base < N; base += step) {
+        float xn[SPT][MS];
+#pragma unroll
+        for (int s = 0; s < SPT; s++)
+#pragma unroll
+            for (int j = 0; j < MS; j++) {
+                const float v = (base + s < N) ? x[(base + s) * MS + j] : mu[j];
+                xn[s][j] = (v - mu[j]) / sd[j];           // _normalize, embedding_lorenz.py:159-160
+            }
+        float acc[SPT][ME];
+#pragma unroll
+        for (int e = 0; e < ME; e++) {
+            const float b = __ldg(blob + L.b2 + e);
+#pragma unroll
+            for (int s = 0; s < SPT; s++) acc[s][e] = b;
+        }
+#pragma unroll 2
+        for (int u = 0; u < Hd; u++) {
+            const float4 a = sA[u];
+            float hid[SPT];
+#pragma unroll
+            for (int s = 0; s < SPT; s++)
+                hid[s] = fmaxf(fmaf(a.z, xn[s][2], fmaf(a.y, xn[s][1], fmaf(a.x, xn[s][0], a.w))), 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 w = sB[u * 8 + j];
+#pragma unroll
+                for (int s = 0; s < SPT; s++) {
+                    acc[s][4 * j + 0] = fmaf(hid[s], w.x, acc[s][4 * j + 0]);
+                    acc[s][4 * j + 1] = fmaf(hid[s], w.y, acc[s][4 * j + 1]);
+                    acc[s][4 * j + 2] = fmaf(hid[s], w.z, acc[s][4 * j + 2]);
+                    acc[s][4 * j + 3] = fmaf(hid[s], w.w, acc[s][4 * j + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SPT; s++) {
+            if (base + s >= N) break;
+            float m = 0.f;
+#pragma unroll
+            for (int e = 0; e < ME; e++) m += acc[s][e];
+            m *= (1.0f / ME);
+            float v = 0.f;
+#pragma unroll
+            for (int e = 0; e < ME; e++) {
+                acc[s][e] -= m;
+                v = fmaf(acc[s][e], acc[s][e], v);
+            }
+            const float rstd = 1.0f / sqrtf(v * (1.0f / ME) + eps);
+            float4* go = reinterpret_cast<float4*>(g + (base + s) * ME);
+            float4* zo = zhat_out ? reinterpret_cast<float4*>(zhat_out + (base + s) * ME) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float4 z, o;
+                z.x = acc[s][4 * j + 0] * rstd; z.y = acc[s][4 * j + 1] * rstd;
+                z.z = acc[s][4 * j + 2] * rstd; z.w = acc[s][4 * j + 3] * rstd;
+                o.x = z.x * __ldg(blob + L.lnw + 4 * j + 0) + __ldg(blob + L.lnb + 4 * j + 0);
+                o.y = z.y * __ldg(blob + L.lnw + 4 * j + 1) + __ldg(blob + L.lnb + 4 * j + 1);
+                o.z = z.z * __ldg(blob + L.lnw + 4 * j + 2) + __ldg(blob + L.lnb + 4 * j + 2);
+                o.w = z.w * __ldg(blob + L.lnw + 4 * j + 3) + __ldg(blob + L.lnb + 4 * j + 3);
+                go[j] = o;
+                if (zo) zo[j] = z;
+            }
+            if (rstd_out) rstd_out[base + s] = rstd;
+        }
+    }
+}
+
+// ---- K3b: recover  g[N,32] -> x[N,3] ------------------------------------------------------------------
+__global__ void __launch_bounds__(EMB_THREADS) mlp_recover_kernel(const float* __restrict__ blob, MlpLayout L,
+                                                                  const float* __restrict__ g, float* __restrict__ x,
+                                                                  long long N) {
+    extern __shared__ float4 sm4[];
+    const int Hd = L.Hd;
+    float4* sA = sm4;                 // [Hd][8]  V1 rows
+    float4* sB = sm4 + Hd * 8;        // [Hd]     {V2[0..2][u], c1[u]}
+    {
+        const float4* src = reinterpret_cast<const float4*>(blob + L.decA);
+        for (int i = threadIdx.x; i < Hd * 9; i += blockDim.x) sm4[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const long long step = (long long)gridDim.x * blockDim.x * SPT;
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * SPT; base < N; base += step) {
+        float gi[SPT][ME];
+#pragma unroll
+        for (int s = 0; s < SPT; s++) {
+            const long long n = (base + s < N) ? base + s : N - 1;
+            const float4* gp = reinterpret_cast<const float4*>(g + n * ME);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 v = __ldg(gp + j);
+                gi[s][4 * j] = v.x; gi[s][4 * j + 1] = v.y; gi[s][4 * j + 2] = v.z; gi[s][4 * j + 3] = v.w;
+            }
+        }
+        float y[SPT][MS];
+#pragma unroll
+        for (int s = 0; s < SPT; s++)
+#pragma unroll
+            for (int c = 0; c < MS; c++) y[s][c] = __ldg(blob + L.c2 + c);
+#pragma unroll 2
+        for (int u = 0; u < Hd; u++) {
+            const float4 b = sB[u];
+            float p0[SPT], p1[SPT];
+#pragma unroll
+            for (int s = 0; s < SPT; s++) { p0[s] = b.w; p1[s] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 w = sA[u * 8 + j];
+#pragma unroll
+                for (int s = 0; s < SPT; s++) {
+                    p0[s] = fmaf(w.x, gi[s][4 * j + 0], p0[s]);
+                    p1[s] = fmaf(w.y, gi[s][4 * j + 1], p1[s]);
+                    p0[s] = fmaf(w.z, gi[s][4 * j + 2], p0[s]);
+                    p1[s] = fmaf(w.w, gi[s][4 * j + 3], p1[s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SPT; s++) {
+                const float hid = fmaxf(p0[s] + p1[s], 0.f);
+                y[s][0] = fmaf(hid, b.x, y[s][0]);
+                y[s][1] = fmaf(hid, b.y, y[s][1]);
+                y[s][2] = fmaf(hid, b.z, y[s][2]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SPT; s++) {
+            if (base + s >= N) break;
+#pragma unroll
+            for (int c = 0; c < MS; c++)                     // _unnormalize, embedding_lorenz.py:162-163
+                x[(base + s) * MS + c] = __ldg(blob + L.sd + c) * y[s][c] + __ldg(blob + L.mu + c);
+        }
+    }
+}
+
+// ---- K4: banded Koopman matvec ------------------------------------------------------------------------
+// K = diag(d) + U - U^T with U holding offsets +1 (u1[0..30]) and +2 (u2[0..29])  (embedding_lorenz.py:59-66,
+// 130-137).  g'[i] = d[i] g[i] + u1[i] g[i+1] + u2[i] g[i+2] - u1[i-1] g[i-1] - u2[i-2] g[i-2].
+__global__ void mlp_koopman_kernel(const float* __restrict__ blob, MlpLayout L, const float* __restrict__ g,
+                                   float* __restrict__ out, long long N) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * ME) return;
+    const int i = (int)(idx % ME);
+    const float* gr = g + (idx - i);
+    const float* d = blob + L.kd;
+    const float* u1 = blob + L.ku;
+    const float* u2 = blob + L.ku + (ME - 1);
+    // same left-to-right order as the dense row-times-vector product of torch.bmm
+    float acc = 0.f;
+    if (i >= 2) acc = fmaf(-__ldg(u2 + i - 2), gr[i - 2], acc);
+    if (i >= 1) acc = fmaf(-__ldg(u1 + i - 1), gr[i - 1], acc);
+    acc = fmaf(__ldg(d + i), gr[i], acc);
+    if (i + 1 < ME) acc = fmaf(__ldg(u1 + i), gr[i + 1], acc);
+    if (i + 2 < ME) acc = fmaf(__ldg(u2 + i), gr[i + 2], acc);
+    out[idx] = acc;
+}
+
+__global__ void mlp_kmatrix_kernel(const float* __restrict__ blob, MlpLayout L, float* __restrict__ K) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ME * ME) return;
+    const int i = idx / ME, j = idx % ME;
+    const float* u1 = blob + L.ku;
+    const float* u2 = blob + L.ku + (ME - 1);
+    float v = 0.f;
+    if (j == i) v = blob[L.kd + i];
+    else if (j == i + 1) v = u1[i];
+    else if (j == i + 2) v = u2[i];
+    else if (j == i - 1) v = -u1[j];
+    else if (j == i - 2) v = -u2[j];
+    K[idx] = v;
+}
+
+// ---- fused clip_grad_norm_ + Adam ---------------------------------------------------------------------
+constexpr int NORM_BLOCKS = 64;
+
+__global__ void sqnorm_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s = fmaf(g[i], g[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+struct AdamArgs {
+    float lr, beta1, beta2, eps, wd, max_norm, bc1, bc2_sqrt;
+};
+
+__global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, const float* __restrict__ partial, AdamArgs a,
+                                 float* __restrict__ norm_out) {
+    // every block reduces the partial sums in the same fixed order -> identical clip coefficient everywhere
+    float tot = 0.f;
+    for (int i = 0; i < NORM_BLOCKS; i++) tot += partial[i];
+    const float norm = sqrtf(tot);
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+    const float coef = fminf(a.max_norm / (norm + 1e-6f), 1.0f);
+    const float step_size = a.lr / a.bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * coef;
+        const float pi = p[i];
+        gi = fmaf(a.wd, pi, gi);                             // L2 weight decay folded into the gradient (Adam, not AdamW)
+        const float mi = m[i] + (1.0f - a.beta1) * (gi - m[i]);       // exp_avg.lerp_(grad, 1-beta1)
+        const float vi = fmaf(1.0f - a.beta2, gi * gi, v[i] * a.beta2);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
+float* g_norm_partial[16] = {nullptr};      // per-device scratch for trpx_clip_adam
+
+}  // namespace
+
+extern "C" {
+
+int trpx_mlpemb_create(const trpx_mlpemb_config* cfg, int device, trpx_mlpemb_t* out) {
+    TRPX_REQUIRE(cfg != nullptr && out != nullptr, "trpx_mlpemb_create: null argument");
+    TRPX_REQUIRE(cfg->state_dim == MS, "state_dim=%d unsupported (3)", cfg->state_dim);
+    TRPX_REQUIRE(cfg->n_embd == ME, "n_embd=%d unsupported (32)", cfg->n_embd);
+    TRPX_REQUIRE(cfg->hidden > 0 && cfg->hidden <= 1024 && cfg->hidden % 4 == 0, "hidden=%d unsupported", cfg->hidden);
+    int ndev = 0;
+    TRPX_CUDA(cudaGetDeviceCount(&ndev));
+    TRPX_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    DeviceGuard guard(device);
+    trpx_mlpemb* h = new (std::nothrow) trpx_mlpemb();
+    TRPX_REQUIRE(h != nullptr, "out of host memory");
+    h->cfg = *cfg;
+    h->device = device;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const MlpLayout L = MlpLayout::make(cfg->hidden);
+    if (cudaMalloc(&h->blob, sizeof(float) * L.total) != cudaSuccess) {
+        delete h;
+        return set_error(TRPX_E_CUDA, "cudaMalloc of the weight blob failed");
+    }
+    *out = h;
+    return TRPX_OK;
+}
+
+int trpx_mlpemb_destroy(trpx_mlpemb_t h) {
+    if (!valid(h)) return set_error(TRPX_E_STATE, "trpx_mlpemb_destroy: invalid handle");
+    DeviceGuard guard(h->device);
+    cudaFree(h->blob);
+    cudaFree(h->ws);
+    h->magic = 0;
+    delete h;
+    return TRPX_OK;
+}
+
+long long trpx_mlpemb_num_params(trpx_mlpemb_t h) {
+    if (!valid(h)) return -1;
+    const long long Hd = h->cfg.hidden;
+    return ME + 61 + Hd * MS + Hd + ME * Hd + ME + ME + ME + Hd * ME + Hd + MS * Hd + MS;
+}
+
+int trpx_mlpemb_load_weights(trpx_mlpemb_t h, const float* const* w, int n, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    TRPX_REQUIRE(w != nullptr && n == 14, "expected 14 weight tensors, got %d", n);
+    for (int i = 0; i < n; i++) TRPX_REQUIRE(w[i] != nullptr, "weight tensor %d is null", i);
+    DeviceGuard guard(h->device);
+    PackSrc s{w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], w[9], w[10], w[11], w[12], w[13]};
+    const MlpLayout L = MlpLayout::make(h->cfg.hidden);
+    mlp_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(s, h->blob, L);
+    TRPX_CUDA(cudaGetLastError());
+    h->loaded = true;
+    return TRPX_OK;
+}
+
+static int emb_grid(trpx_mlpemb_t h, long long N, int ctas_per_sm) {
+    const long long need = (N + (long long)EMB_THREADS * SPT - 1) / ((long long)EMB_THREADS * SPT);
+    const long long cap = (long long)h->sm_count * ctas_per_sm;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // extern "C"
+
+namespace trpx {
+int mlpemb_embed_ex(trpx_mlpemb_t h, const float* x, float* g, long long N, float* zhat, float* rstd,
+                    void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(N >= 0 && (N == 0 || (x != nullptr && g != nullptr)), "bad arguments");
+    if (N == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    const MlpLayout L = MlpLayout::make(h->cfg.hidden);
+    const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
+    TRPX_CUDA(cudaFuncSetAttribute(mlp_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_embed_kernel<<<emb_grid(h, N, 3), EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, x, g, N, h->cfg.ln_eps,
+                                                                                    zhat, rstd);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+}  // namespace trpx
+
+extern "C" {
+
+int trpx_mlpemb_embed(trpx_mlpemb_t h, const float* x, float* g, long long N, void* stream) {
+    return trpx::mlpemb_embed_ex(h, x, g, N, nullptr, nullptr, stream);
+}
+
+int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g, float* x, long long N, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(N >= 0 && (N == 0 || (x != nullptr && g != nullptr)), "bad arguments");
+    if (N == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    const MlpLayout L = MlpLayout::make(h->cfg.hidden);
+    const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
+    TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_recover_kernel<<<emb_grid(h, N, 3), EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, g, x, N);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int trpx_mlpemb_koopman(trpx_mlpemb_t h, const float* g, float* gnext, long long N, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(N >= 0 && (N == 0 || (g != nullptr && gnext != nullptr)), "bad arguments");
+    TRPX_REQUIRE(g != gnext, "in-place Koopman step is not supported");
+    if (N == 0) return TRPX_OK;
+    DeviceGuard guard(h->device);
+    const MlpLayout L = MlpLayout::make(h->cfg.hidden);
+    const long long total = N * ME;
+    mlp_koopman_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->blob, L, g, gnext, N);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int trpx_mlpemb_koopman_matrix(trpx_mlpemb_t h, float* K, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(K != nullptr, "null output");
+    DeviceGuard guard(h->device);
+    const MlpLayout L = MlpLayout::make(h->cfg.hidden);
+    mlp_kmatrix_kernel<<<(ME * ME + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->blob, L, K);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int trpx_clip_adam(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float max_norm, float* norm_out, int device,
+                   void* stream) {
+    TRPX_REQUIRE(p && g && m && v && n > 0, "bad arguments");
+    TRPX_REQUIRE(step >= 1, "step must be >= 1");
+    TRPX_REQUIRE(device >= 0 && device < 16, "device %d out of range", device);
+    DeviceGuard guard(device);
+    if (g_norm_partial[device] == nullptr) TRPX_CUDA(cudaMalloc(&g_norm_partial[device], sizeof(float) * NORM_BLOCKS));
+    cudaStream_t st = (cudaStream_t)stream;
+    sqnorm_partial_kernel<<<NORM_BLOCKS, 256, 0, st>>>(g, n, g_norm_partial[device]);
+    TRPX_CUDA(cudaGetLastError());
+    AdamArgs a;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.max_norm = max_norm;
+    a.bc1 = (float)(1.0 - std::pow((double)beta1, (double)step));
+    a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)beta2, (double)step));
+    const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    clip_adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, g_norm_partial[device], a, norm_out);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+}  // extern "C"

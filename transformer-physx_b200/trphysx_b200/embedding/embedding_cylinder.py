@@ -1,0 +1,191 @@
+"""Drop-in `CylinderEmbedding` (reference: trphysx/embedding/embedding_cylinder.py:25-222).
+embed = fused normalise + 5 replicate-padded 3x3 convs + LayerNorm; recover = 4 x (bilinear x2 + conv + ReLU)
++ conv + un-normalise + cylinder mask; koopmanOperation = viscosity-conditioned banded matvec — all in libtrpx."""
+import ctypes
+from typing import Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _native as N
+from .embedding_model import EmbeddingModel, EmbeddingTrainingHead
+
+Tensor = torch.Tensor
+
+
+def _conv(cin, cout, stride):
+    return nn.Conv2d(cin, cout, kernel_size=(3, 3), stride=stride, padding=1, padding_mode="replicate")
+
+
+def _up():
+    return nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+
+
+class CylinderEmbedding(EmbeddingModel):
+    model_name = "embedding_cylinder"
+
+    def __init__(self, config) -> None:
+        super().__init__(config)
+        E = config.n_embd
+        X, Y = np.meshgrid(np.linspace(-2, 14, 128), np.linspace(-4, 4, 64))
+        self.mask = torch.tensor(np.sqrt(X ** 2 + Y ** 2) < 1, dtype=torch.bool)
+        self.observableNet = nn.Sequential(
+            _conv(4, 16, 2), nn.ReLU(True), _conv(16, 32, 2), nn.ReLU(True), _conv(32, 64, 2), nn.ReLU(True),
+            _conv(64, 128, 2), nn.ReLU(True), _conv(128, E // 32, 1))
+        self.observableNetFC = nn.Sequential(nn.LayerNorm(E, eps=config.layer_norm_epsilon), nn.Dropout(config.embd_pdrop))
+        self.recoveryNet = nn.Sequential(
+            _up(), _conv(E // 32, 128, 1), nn.ReLU(), _up(), _conv(128, 64, 1), nn.ReLU(),
+            _up(), _conv(64, 32, 1), nn.ReLU(), _up(), _conv(32, 16, 1), nn.ReLU(), _conv(16, 3, 1))
+        self.obsdim = E
+        self.kMatrixDiagNet = nn.Sequential(nn.Linear(1, 50), nn.ReLU(), nn.Linear(50, E))
+        self.xidx = torch.LongTensor(np.concatenate([np.arange(0, E - i) for i in range(1, 5)]))
+        self.yidx = torch.LongTensor(np.concatenate([np.arange(i, E) for i in range(1, 5)]))
+        nband = self.xidx.size(0)
+        self.kMatrixUT = nn.Sequential(nn.Linear(1, 50), nn.ReLU(), nn.Linear(50, nband))
+        self.kMatrixLT = nn.Sequential(nn.Linear(1, 50), nn.ReLU(), nn.Linear(50, nband))
+        self.register_buffer("mu", torch.tensor([0.0, 0.0, 0.0, 0.0]))
+        self.register_buffer("std", torch.tensor([1.0, 1.0, 1.0, 1.0]))
+        self._handles = {}
+        self._last_visc = None
+        self.kMatrixDiag = None
+
+    def _weight_list(self):
+        ws = [self.mu, self.std]
+        for i in (0, 2, 4, 6, 8):
+            ws += [self.observableNet[i].weight, self.observableNet[i].bias]
+        ws += [self.observableNetFC[0].weight, self.observableNetFC[0].bias]
+        for i in (1, 4, 7, 10, 12):
+            ws += [self.recoveryNet[i].weight, self.recoveryNet[i].bias]
+        for net in (self.kMatrixDiagNet, self.kMatrixUT, self.kMatrixLT):
+            ws += [net[0].weight, net[0].bias, net[2].weight, net[2].bias]
+        return ws
+
+    def _handle(self, device: torch.device):
+        lib = N.lib()
+        if self.training and self.config.embd_pdrop:
+            raise NotImplementedError("dropout > 0 in train mode is not implemented in the kernels")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        entry = self._handles.get(idx)
+        if entry is None:
+            h = ctypes.c_void_p()
+            N.check(lib.trpx_cyl_create(self.config.n_embd, self.config.layer_norm_epsilon, idx, ctypes.byref(h)))
+            entry = (h, N.WeightTracker())
+            self._handles[idx] = entry
+        h, tracker = entry
+        ws = self._weight_list()
+        if tracker.changed(ws):
+            tensors = []
+            for w in ws:
+                if w.device != device:
+                    raise NotImplementedError(f"parameter on {w.device} but input on {device}: move the model first")
+                tensors.append(N.require_cuda_f32(w.detach(), "parameter"))
+            N.check(lib.trpx_cyl_load_weights(h, N.ptr_array(tensors), len(tensors), N.stream_ptr(device)))
+            self._keepalive = tensors
+        return h
+
+    def set_chunk(self, frames: int):
+        self._chunk = frames
+        for h, _ in self._handles.values():
+            N.check(N.lib().trpx_cyl_set_chunk(h, frames))
+
+    def __del__(self):
+        try:
+            for h, _ in self._handles.values():
+                N.lib().trpx_cyl_destroy(h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _visc(visc: Tensor, B: int) -> Tensor:
+        visc = N.require_cuda_f32(visc, "visc")
+        if visc.numel() != B:
+            raise ValueError(f"visc must hold one viscosity per sample ([{B}, 1]), got {tuple(visc.shape)}")
+        return visc.reshape(B)
+
+    def embed(self, x: Tensor, visc: Tensor) -> Tensor:
+        """[B,3,64,128], [B,1] -> [B, n_embd]  (embedding_cylinder.py:138-154)"""
+        self._inference_only("embed")
+        x = N.require_cuda_f32(x, "x")
+        assert x.dim() == 4 and tuple(x.shape[1:]) == (3, 64, 128), "x must be [B, 3, 64, 128]"
+        v = self._visc(visc, x.size(0))
+        g = torch.empty((x.size(0), self.obsdim), device=x.device, dtype=torch.float32)
+        N.check(N.lib().trpx_cyl_embed(self._handle(x.device), x.data_ptr(), v.data_ptr(), g.data_ptr(), x.size(0),
+                                       N.stream_ptr(x.device)))
+        return g
+
+    def _decode(self, g: Tensor, apply_mask: bool) -> Tensor:
+        g = N.require_cuda_f32(g, "g").reshape(-1, self.obsdim)
+        x = torch.empty((g.size(0), 3, 64, 128), device=g.device, dtype=torch.float32)
+        N.check(N.lib().trpx_cyl_recover(self._handle(g.device), g.data_ptr(), x.data_ptr(), g.size(0),
+                                         1 if apply_mask else 0, N.stream_ptr(g.device)))
+        return x
+
+    def recover(self, g: Tensor) -> Tensor:
+        """[B, n_embd] -> [B,3,64,128] with the cylinder cells zeroed (embedding_cylinder.py:156-170)"""
+        self._inference_only("recover")
+        return self._decode(g, True)
+
+    def forward(self, x: Tensor, visc: Tensor) -> Tuple[Tensor, Tensor]:
+        """(g, xhat).  As in the reference the mask is NOT applied here: `mask0 = ... is True` is the Python
+        bool False (embedding_cylinder.py:133-134)."""
+        g = self.embed(x, visc)
+        return g, self._decode(g, False)
+
+    def koopmanOperation(self, g: Tensor, visc: Tensor) -> Tensor:
+        """[B, n_embd], [B,1] -> [B, n_embd]  (embedding_cylinder.py:172-196)"""
+        self._inference_only("koopmanOperation")
+        g = N.require_cuda_f32(g, "g")
+        v = self._visc(visc, g.size(0))
+        out = torch.empty_like(g)
+        kdiag = torch.empty_like(g)
+        N.check(N.lib().trpx_cyl_koopman(self._handle(g.device), g.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                         kdiag.data_ptr(), None, g.size(0), N.stream_ptr(g.device)))
+        self.kMatrixDiag = kdiag
+        self._last_visc = v
+        return out
+
+    @property
+    def koopmanOperator(self, requires_grad: bool = True) -> Tensor:
+        """Dense per-sample operator [B, n_embd, n_embd] of the last koopmanOperation call, materialised on demand."""
+        if self._last_visc is None:
+            return None
+        v = self._last_visc
+        B, E = v.numel(), self.obsdim
+        K = torch.empty((B, E, E), device=v.device, dtype=torch.float32)
+        dummy_in = torch.zeros((B, E), device=v.device, dtype=torch.float32)
+        dummy_out = torch.empty_like(dummy_in)
+        N.check(N.lib().trpx_cyl_koopman(self._handle(v.device), dummy_in.data_ptr(), v.data_ptr(), dummy_out.data_ptr(),
+                                         None, K.data_ptr(), B, N.stream_ptr(v.device)))
+        return K
+
+    @property
+    def koopmanDiag(self):
+        return self.kMatrixDiag
+
+
+class CylinderEmbeddingTrainer(EmbeddingTrainingHead):
+    """evaluate() is served by the kernels; the Cylinder Koopman TRAINING step (conv backward) is a "next" row
+     and raises until it is built."""
+
+    def __init__(self, config) -> None:
+        super().__init__()
+        self.embedding_model = CylinderEmbedding(config)
+
+    def forward(self, states: Tensor, viscosity: Tensor):
+        raise NotImplementedError("Cylinder embedding training step (conv backward) is not built yet")
+
+    @torch.no_grad()
+    def evaluate(self, states: Tensor, viscosity: Tensor):
+        """One-step reconstruction error (embedding_cylinder.py:283-313)."""
+        self.embedding_model.eval()
+        m = self.embedding_model
+        device = m.devices[0]
+        y_target = states[:, 1:].to(device)
+        x_input = states[:, :-1].to(device)
+        viscosity = viscosity.to(device)
+        B, T = x_input.size(0), x_input.size(1)
+        flat = N.require_cuda_f32(x_input.reshape(B * T, 3, 64, 128), "states")
+        visc = viscosity.reshape(B, 1).repeat_interleave(T, dim=0)
+        y_pred = m.recover(m.embed(flat, visc)).view(B, T, 3, 64, 128)
+        return nn.functional.mse_loss(y_target, y_pred), y_pred, y_target

@@ -6,8 +6,8 @@
 
 A "step" is ONE pass of the hot path over one batch of synthetic initial states:
     embed(x0) -> generate(max_length = horizon+1, use_cache=True) -> recover(all tokens)
-Workload at every N (weak scaling): the per-GPU shard of BASELINE config[1] — Rossler, 65,536 trajectories
-sharded over 8 GPUs = 8,192 trajectories per GPU, horizon 256.  No collective on the data path.
+Workload at N=1: BASELINE config[1] — the 65,536-trajectory batched Rossler rollout, horizon 256 (it fits one GPU).
+N>1 is weak scaling: every GPU runs its own 65,536-trajectory shard.  No collective on the data path.
 
   value    trajectory-steps/s, whole job, inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e      same metric through the public module API with HOST buffers: pinned x0 -> H2D, ..., states -> D2H
@@ -40,7 +40,8 @@ UNIT = "trajectory-steps/s"
 
 WORKLOADS = {
     # name: (config kind, per-GPU trajectories, horizon)
-    "rossler": ("rossler", 8192, 256),      # BASELINE config[1]: 65,536 trajectories over 8 GPUs
+    "rossler": ("rossler", 65536, 256),     # BASELINE config[1]: the 65,536-trajectory batched Rossler rollout
+    "rossler8k": ("rossler", 8192, 256),    # its 1/8 shard
     "lorenz": ("lorenz", 8192, 128),        # BASELINE config[0] architecture at a GPU-sized batch
     "lorenz256": ("lorenz", 256, 128),      # BASELINE config[0] as stated (256 trajectories, 128 steps)
 }
@@ -266,15 +267,19 @@ def run_ours(args):
         b.record()
         torch.cuda.synchronize()
         nocache_ms = a.elapsed_time(b)
-        # embed / recover alone
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        emb.embed(x0_dev)
-        b.record()
-        emb.recover(out.view(B * (S + 1), E))
-        c.record()
-        torch.cuda.synchronize()
-        embed_ms, recover_ms = a.elapsed_time(b), b.elapsed_time(c)
+        # embed / recover alone (median of 5)
+        em, rc = [], []
+        for _ in range(5):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            emb.embed(x0_dev)
+            b.record()
+            emb.recover(out.view(B * (S + 1), E))
+            c.record()
+            torch.cuda.synchronize()
+            em.append(a.elapsed_time(b))
+            rc.append(b.elapsed_time(c))
+        embed_ms, recover_ms = statistics.median(em), statistics.median(rc)
 
     if rank != 0:
         if world > 1:
@@ -341,7 +346,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU trajectories (default: workload's)")
     ap.add_argument("--horizon", type=int, default=0)
     ap.add_argument("--tune", default="", help="e.g. warps_per_cta=8,traj_per_warp=8")
-    ap.add_argument("--cpu-batch", type=int, default=1024)
+    ap.add_argument("--cpu-batch", type=int, default=2048)
     ap.add_argument("--cpu-horizon", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -47,14 +47,14 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def gpt2_weights(cfg, seed: int, stress: bool = False) -> "OrderedDict[str, np.ndarray]":
+def gpt2_weights(cfg, seed: int, stress: bool = False, stress_sigma: float = 0.3) -> "OrderedDict[str, np.ndarray]":
     """Random transformer state_dict.  stress=False mimics `_init_weights`
     (phys_transformer_base.py:46-57: N(0, initializer_range), zero bias, LN = (1, 0)).
     stress=True draws larger weights, non-zero biases and random LN affine so that attention logits,
     the softmax and the GELU non-linearity are actually exercised (SURVEY.md §8c degeneracy warning)."""
     rng = np.random.default_rng(seed)
     E, L, C = cfg.n_embd, cfg.n_layer, cfg.n_ctx
-    sw = 0.3 if stress else cfg.initializer_range
+    sw = stress_sigma if stress else cfg.initializer_range      # stress_sigma < 0.3: milder, better conditioned
     sd = OrderedDict()
 
     def w(*shape):

@@ -34,3 +34,25 @@ def make_cylinder(cfg_ns, seed, device=None):
     m = CylinderEmbedding(cfg).eval()
     m.load_state_dict(torch_sd(synth.cylinder_embedding_weights(cfg_ns, seed)), strict=True)
     return m.to(device) if device is not None else m
+
+
+_prefix_cache = {}
+
+
+def stable_prefix(cfg_ns, weights_np, ctx, max_length, use_cache, thresh=3e-6):
+    """Free rollouts with the stress weights can be chaotic: the reference's OWN float32 arithmetic then drifts
+    from exact arithmetic exponentially, and no implementation can match it beyond that point.  Returns
+    (n, out32): the number of leading tokens over which the oracle run in float32 stays within `thresh`
+    (per-token rel-L2, worst trajectory) of the same oracle run in float64 — the "stated horizon before chaotic
+    divergence" of BASELINE.json — and the float32 oracle rollout itself."""
+    from oracle import trpx_oracle as O
+    key = (id(weights_np), ctx.shape, float(ctx.sum()), max_length, use_cache, thresh)
+    if key not in _prefix_cache:
+        a, _ = O.gpt2_generate(O.to_torch(weights_np), cfg_ns, ctx, max_length, use_cache=use_cache)
+        b, _ = O.gpt2_generate(O.to_torch(weights_np, torch.float64), cfg_ns, ctx.double(), max_length,
+                               use_cache=use_cache)
+        err = ((a.double() - b).flatten(2).norm(dim=2) / b.flatten(2).norm(dim=2).clamp_min(1e-30)).max(0).values
+        bad = (err > thresh).nonzero()
+        n = int(bad[0]) if len(bad) else max_length
+        _prefix_cache[key] = (n, a)
+    return _prefix_cache[key]

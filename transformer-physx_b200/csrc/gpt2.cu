@@ -355,77 +355,97 @@ __device__ __forceinline__ void warp_gemv(const float* scr, const float* W, int 
     }
 }
 
-// attention of one trajectory for all 4 heads (hd = 8): lane = (head = lane/8, sg = lane%8); the lane
-// scores slots sg, sg+8, ... of its head, then the 8 lanes of a head reduce-scatter the output so that
-// lane n ends up with channel n.  MAXI = ceil(n_ctx / 8).
-template <int MAXI>
-__device__ __forceinline__ float warp_attn_hd8(float qmine, const float* Kp, const float* Vp, int L, int lane) {
-    const int hb = lane & 24, sg = lane & 7;
-    float qh[8];
-#pragma unroll
-    for (int d = 0; d < 8; d++) qh[d] = __shfl_sync(FULL, qmine, hb + d);
-    float sc[MAXI];
-    float m = -INFINITY;
-    const float scale = 2.8284271247461903f;       // sqrt(8)
-#pragma unroll
-    for (int i = 0; i < MAXI; i++) {
-        const int slot = sg + 8 * i;
-        sc[i] = -INFINITY;
-        if (slot < L) {
-            float kk[8];
-            ldg256(Kp + slot * 32 + hb, kk);
-            float s = 0.f;
-#pragma unroll
-            for (int d = 0; d < 8; d++) s = fmaf(qh[d], kk[d], s);
-            sc[i] = s / scale;
-        }
-        m = fmaxf(m, sc[i]);
+// Attention for the G trajectories of a warp, 4 heads of 8 (hd = 8), window of L <= NCTX keys.
+// lane = ((g*4 + head) * P + part) with P = 8/G: for G = 8 every lane owns one (trajectory, head) pair and walks
+// the whole window alone — no shuffles at all; for smaller G the P lanes of a pair split the slots and combine
+// max / sum / output with P-lane xor-shuffles.  All key (then value) rows of a batch are loaded before they are
+// consumed (independent 256-bit loads: memory-level parallelism instead of a load->use chain per slot).
+//   qs   : smem [G][32] queries (row per trajectory)
+//   kvl  : ring of this warp for this layer: trajectory g at kvl + g*kv_per_g, K rows [C][32] then V rows [C][32]
+//   outT : smem transposed tile [32][G] receiving the merged-head output (input of the projection GEMV)
+template <int G, int NCTX>
+__device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl, size_t kv_per_g, int C, int L,
+                                              float* outT, int lane) {
+    constexpr int P = 8 / G;
+    constexpr int NS = NCTX / P;                      // slots per lane
+    constexpr int BS = NS >= 64 ? 4 : (NS < 8 ? NS : 8);   // rows in flight per lane
+    const int part = lane % P, gh = lane / P, hh = gh & 3, g = gh >> 2;
+    float q[8];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(qs + g * 32 + hh * 8);
+        const float4 a = qp[0], b = qp[1];
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
     }
-    m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
-    m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+    __syncwarp();                                     // every lane holds its query: the tile may be overwritten
+    const float* Kp = kvl + (size_t)g * kv_per_g + hh * 8;
+    const float* Vp = Kp + C * 32;
+    const float scale = 2.8284271247461903f;          // sqrt(8): attention.py:99 divides by sqrt(head size)
+    float sc[NS];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j0 = 0; j0 < NS; j0 += BS) {
+        if (j0 * P < L) {                             // warp-uniform
+            float kk[BS][8];
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) {
+                const int slot = (j0 + jj) * P + part;
+                ldg256(Kp + min(slot, L - 1) * 32, kk[jj]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) {
+                const int slot = (j0 + jj) * P + part;
+                float s0 = 0.f;
+#pragma unroll
+                for (int d = 0; d < 8; d++) s0 = fmaf(q[d], kk[jj][d], s0);
+                const float s1 = slot < L ? s0 / scale : -INFINITY;
+                sc[j0 + jj] = s1;
+                m = fmaxf(m, s1);
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) sc[j0 + jj] = -INFINITY;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < P; o <<= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXI; i++) {
-        sc[i] = (sg + 8 * i < L) ? expf(sc[i] - m) : 0.f;
-        sum += sc[i];
+    for (int j = 0; j < NS; j++) {
+        const float pj = (j * P + part < L) ? expf(sc[j] - m) : 0.f;
+        sc[j] = pj;
+        sum += pj;
     }
-    sum += __shfl_xor_sync(FULL, sum, 1);
-    sum += __shfl_xor_sync(FULL, sum, 2);
-    sum += __shfl_xor_sync(FULL, sum, 4);
-    float o[8];
 #pragma unroll
-    for (int d = 0; d < 8; d++) o[d] = 0.f;
+    for (int o = 1; o < P; o <<= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    const float rs = 1.0f / sum;
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < MAXI; i++) {
-        const int slot = sg + 8 * i;
-        if (slot < L) {
-            float vv[8];
-            ldg256(Vp + slot * 32 + hb, vv);
-            const float pw = sc[i] / sum;
+    for (int d = 0; d < 8; d++) acc[d] = 0.f;
 #pragma unroll
-            for (int d = 0; d < 8; d++) o[d] = fmaf(pw, vv[d], o[d]);
+    for (int j0 = 0; j0 < NS; j0 += BS) {
+        if (j0 * P < L) {
+            float vv[BS][8];
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) {
+                const int slot = (j0 + jj) * P + part;
+                ldg256(Vp + min(slot, L - 1) * 32, vv[jj]);       // clamped rows carry weight 0
+            }
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) {
+                const float pw = sc[j0 + jj] * rs;
+#pragma unroll
+                for (int d = 0; d < 8; d++) acc[d] = fmaf(pw, vv[jj][d], acc[d]);
+            }
         }
     }
-    // reduce-scatter across the 8 lanes of the head: lane sg keeps dimension sg
-    float t[4];
-    const bool b4 = sg & 4, b2 = sg & 2, b1 = sg & 1;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float send = b4 ? o[j] : o[j + 4];
-        const float keep = b4 ? o[j + 4] : o[j];
-        t[j] = keep + __shfl_xor_sync(FULL, send, 4);
-    }
-    float u[2];
+    for (int o = 1; o < P; o <<= 1)
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const float send = b2 ? t[j] : t[j + 2];
-        const float keep = b2 ? t[j + 2] : t[j];
-        u[j] = keep + __shfl_xor_sync(FULL, send, 2);
+        for (int d = 0; d < 8; d++) acc[d] += __shfl_xor_sync(FULL, acc[d], o);
+    if (part == 0) {
+#pragma unroll
+        for (int d = 0; d < 8; d++) outT[(hh * 8 + d) * G + g] = acc[d];
     }
-    const float send = b1 ? u[0] : u[1];
-    const float keep = b1 ? u[1] : u[0];
-    return keep + __shfl_xor_sync(FULL, send, 1);
 }
 
 template <int G, int MAXI, bool CACHE>
@@ -482,7 +502,6 @@ __global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
                 __syncwarp();
                 warp_ln_T<G>(scr, w + L.ln1w, w + L.ln1b, p.eps, lane);
                 __syncwarp();
-                float o[G];
                 if constexpr (CACHE) {
                     float qkv[3][G];
 #pragma unroll
@@ -497,25 +516,23 @@ __global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
                         kp[slot * 32 + lane] = qkv[1][g];
                         kp[C * 32 + slot * 32 + lane] = qkv[2][g];
                     }
-                    __syncwarp();
+                    __syncwarp();                 // LN tile fully consumed; ring stores visible to the warp
 #pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const float* kp = kvw + (size_t)g * kv_per_g + (size_t)(l * 2) * C * 32;
-                        o[g] = warp_attn_hd8<MAXI>(qkv[0][g], kp, kp + C * 32, Lk, lane);
-                    }
+                    for (int g = 0; g < G; g++) scr[g * 32 + lane] = qkv[0][g];
+                    __syncwarp();
+                    warp_attn_e32<G, 8 * MAXI>(scr, kvw + (size_t)(l * 2) * C * 32, kv_per_g, C, Lk, scr, lane);
+                    __syncwarp();
                 } else {
                     // window of one key: softmax == 1 exactly, so the head output is v itself
                     float vv[1][G];
 #pragma unroll
                     for (int g = 0; g < G; g++) vv[0][g] = w[L.bqkv + 64 + lane];
                     warp_gemv<G, 1>(scr, w + L.wqkv + 64, 32, 96, lane, vv);
-#pragma unroll
-                    for (int g = 0; g < G; g++) o[g] = vv[0][g];
+                    __syncwarp();
+                    store_T<G>(scr, lane, vv[0]);
+                    __syncwarp();
                 }
                 // ---- output projection + residual ----
-                __syncwarp();
-                store_T<G>(scr, lane, o);
-                __syncwarp();
                 {
                     float acc[1][G];
 #pragma unroll
@@ -918,10 +935,10 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
                       int S, int use_cache, float* presents, void* stream) {
     TRPX_REQUIRE(valid(h), "invalid handle");
     if (!h->loaded) return set_error(TRPX_E_STATE, "trpx_gpt2_rollout: weights not loaded");
-    TRPX_REQUIRE(x0 != nullptr && out != nullptr, "null tensor");
     TRPX_REQUIRE(B >= 0 && S >= 0, "negative size");
     TRPX_REQUIRE(presents == nullptr || use_cache, "presents requires use_cache");
     if (B == 0 || S == 0) return TRPX_OK;
+    TRPX_REQUIRE(x0 != nullptr && out != nullptr, "null tensor");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const Gpt2Layout& L = h->lay;
@@ -1001,11 +1018,11 @@ int trpx_gpt2_forward(trpx_gpt2_t h, const float* x, const float* const* past, i
                       float* const* presents, float* const* attn, int B, int T, void* stream) {
     TRPX_REQUIRE(valid(h), "invalid handle");
     if (!h->loaded) return set_error(TRPX_E_STATE, "trpx_gpt2_forward: weights not loaded");
-    TRPX_REQUIRE(x != nullptr && hidden != nullptr, "null tensor");
     TRPX_REQUIRE(B >= 0 && T >= 0 && Tp >= 0, "negative size");
     TRPX_REQUIRE((Tp == 0) == (past == nullptr), "past pointer / Tp mismatch");
     TRPX_REQUIRE(Tp + T <= h->cfg.n_ctx, "past (%d) + tokens (%d) exceeds n_ctx (%d)", Tp, T, h->cfg.n_ctx);
     if (B == 0 || T == 0) return TRPX_OK;
+    TRPX_REQUIRE(x != nullptr && hidden != nullptr, "null tensor");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const Gpt2Layout& L = h->lay;

@@ -12,4 +12,4 @@ from . import config, embedding, transformer  # noqa: F401
 from .config import AutoPhysConfig, PhysConfig  # noqa: F401
 from .embedding import AutoEmbeddingModel  # noqa: F401
 from .transformer import AutoPhysTransformer, PhysformerGPT2, PhysformerTrain  # noqa: F401
-from .parallel import shard_bounds, ShardedRollout  # noqa: F401
+from .parallel import shard_bounds, ShardedRollout, average_flat_grad  # noqa: F401

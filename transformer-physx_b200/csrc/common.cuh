@@ -70,6 +70,12 @@ __device__ __forceinline__ void ldg256(const float* p, float (&a)[8]) {
                  : "memory");
 }
 
+// Fire-and-forget bulk prefetch of a contiguous global range into L2 (cp.async.bulk.prefetch, SASS: UBLKPF).
+// `bytes` must be a multiple of 16 and `p` 16-byte aligned.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- TMA bulk copy global -> shared with an mbarrier (cp.async.bulk, SASS: UBLKCP) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

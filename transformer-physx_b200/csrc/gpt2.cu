@@ -26,7 +26,7 @@ struct trpx_gpt2 {
     bool loaded = false;
     float* kv = nullptr;          // rollout workspace (KV windows of the groups in flight)
     size_t kv_bytes = 0;
-    int tune_variant = 0, tune_warps = 0, tune_g = 0, tune_max_ctas = 0;
+    int tune_variant = 0, tune_warps = 0, tune_g = 0, tune_max_ctas = 0, tune_prefetch = 1;
     int last_variant = 0, last_grid = 0, last_block = 0, last_smem = 0, last_group = 0;
 };
 
@@ -149,6 +149,7 @@ struct RolloutParams {
     float eps;
     Gpt2Layout lay;
     int use_tma;
+    int prefetch;
 };
 
 template <int G>
@@ -497,6 +498,17 @@ __global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
             const int slot = CACHE ? (s % C) : 0;
             for (int l = 0; l < NL; l++) {
                 const float* w = wsm + l * L.layer_stride;
+                if constexpr (CACHE) {
+                    // Pull this layer's window into L2 now: one bulk prefetch per trajectory for K and for V (no
+                    // registers, no wait).  The HBM latency then overlaps LN1 + the QKV GEMV instead of being
+                    // exposed inside the attention; the prefetched data only has to survive that short phase
+                    // (prefetching a whole layer ahead was measured to thrash L2 and was slower).
+                    if (p.prefetch && lane < G && Lk > 1) {
+                        const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
+                        prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
+                        prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+                    }
+                }
                 // ---- LN1 ----
                 store_T<G>(scr, lane, h);
                 __syncwarp();
@@ -910,11 +922,12 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0..3");
+    TRPX_REQUIRE(variant >= 0 && variant <= 4, "variant must be 0..4");
     TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 12, "warps_per_cta must be 0..12");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
                      traj_per_warp == 8, "traj_per_warp must be 0,1,2,4,8");
     h->tune_variant = variant;
+    h->tune_prefetch = (variant == 4) ? 0 : 1;
     h->tune_warps = warps_per_cta;
     h->tune_g = traj_per_warp;
     h->tune_max_ctas = max_ctas;
@@ -946,6 +959,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
     p.blob = h->blob; p.pe = h->pe; p.x0 = x0; p.x0_stride = x0_stride; p.out = out; p.out_stride = out_stride;
     p.presents = presents; p.B = B; p.S = S; p.use_cache = use_cache ? 1 : 0; p.eps = h->cfg.ln_eps; p.lay = L;
     p.use_tma = (h->tune_variant == 3) ? 0 : 1;
+    p.prefetch = h->tune_prefetch;
     const size_t kv_per_traj = (size_t)L.n_layer * 2 * L.n_ctx * L.E * sizeof(float);
 
     // ---- E = 32 / head size 8 warp kernel, if the whole model fits in shared memory ----
@@ -957,8 +971,10 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
         int G = h->tune_g;
         if (G == 0) {
-            // enough groups to give every SM at least ~4 warps of work, else shrink the group
-            G = 8;
+            // measured (profiles/r01_sweep_*): with the KV window 4 trajectories per warp (two lanes per
+            // (trajectory, head) pair, smaller in-flight window set) beat 8; without it 8 amortise the weights best.
+            // Shrink the group further when the batch is too small to give every SM ~4 warps.
+            G = use_cache ? 4 : 8;
             while (G > 1 && (long long)(B + G - 1) / G < (long long)sms * 4) G >>= 1;
         }
         const int ngroups = (B + G - 1) / G;
@@ -967,7 +983,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             use_e32 = false;
         } else {
             const int grid = std::min(sms, ngroups);
-            const int want = h->tune_warps > 0 ? h->tune_warps : 8;
+            const int want = h->tune_warps > 0 ? h->tune_warps : ((use_cache && L.n_ctx <= 32) ? 11 : 8);
             const int Wc = std::max(1, std::min(std::min(want, max_w), (ngroups + grid - 1) / grid));
             const size_t smem = wbytes + (size_t)Wc * 64 * G * sizeof(float);
             if (use_cache) {

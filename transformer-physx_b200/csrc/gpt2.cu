@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
                     // registers, no wait).  The HBM latency then overlaps LN1 + the QKV GEMV instead of being
                     // exposed inside the attention; the prefetched data only has to survive that short phase
                     // (prefetching a whole layer ahead was measured to thrash L2 and was slower).
-                    if (p.prefetch && lane < G && Lk > 1) {
+                    if (p.prefetch == 1 && lane < G && Lk > 1) {
                         const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
                         prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
                         prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
@@ -533,6 +533,18 @@ __global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
                     for (int g = 0; g < G; g++) scr[g * 32 + lane] = qkv[0][g];
                     __syncwarp();
                     warp_attn_e32<G, 8 * MAXI>(scr, kvw + (size_t)(l * 2) * C * 32, kv_per_g, C, Lk, scr, lane);
+                    if (p.prefetch == 2 && lane < G) {
+                        // mid-layer distance: the NEXT attention's window (next layer, or layer 0 of the next step)
+                        // is requested now and has the projection + MLP phase to arrive
+                        const bool wrap = (l + 1 == NL);
+                        const int ln = wrap ? 0 : l + 1;
+                        const int Ln = wrap ? min(s + 2, C) : Lk;
+                        if ((!wrap || s + 1 < p.S) && Ln > 1) {
+                            const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(ln * 2) * C * 32;
+                            prefetch_l2_bulk(kp, (uint32_t)Ln * 128u);
+                            prefetch_l2_bulk(kp + C * 32, (uint32_t)Ln * 128u);
+                        }
+                    }
                     __syncwarp();
                 } else {
                     // window of one key: softmax == 1 exactly, so the head output is v itself
@@ -613,6 +625,342 @@ __global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
                 if (b >= p.B) break;
                 for (int r = 0; r < NL * 2 * Tk; r++) {
                     const int t = r % Tk, lw = r / Tk;          // lw = l*2 + which
+                    const int which = lw & 1, l = lw >> 1;
+                    const int sl = (p.S - Tk + t) % C;
+                    p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                        kvw[(size_t)g * kv_per_g + ((size_t)lw * C + sl) * 32 + lane];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (E = 32, head size 8), second generation: 2-D lane tiling.
+// Measured on the first kernel (ncu, profiles/): its GEMV loop is bound by shared-memory RETURN bandwidth —
+// one 32-bit word per lane per cycle per SM — because every lane re-reads the G broadcast activations:
+// (G + C) words for G*C FFMAs, i.e. 0.9 (proj, MLP-out) to 2.7 (MLP-in) FFMA per word where >= 4 are needed.
+// Here one warp owns 16 trajectories and the 32 lanes form a 4 x 8 grid: lane (r, c) holds the register tile
+// [4 trajectories r*4..r*4+3] x [Cc columns], so a k-step costs (4 + Cc) words for 4*Cc FFMAs: 2.0 (Cc = 4),
+// 3.0 (QKV, Cc = 12), 3.2 (MLP-in, Cc = 16) — ~1.8x fewer words per FFMA overall.  The residual stream lives in
+// the same [4 x 4] tile layout (channels c*4..c*4+3), LayerNorm is done in registers (3 xor-shuffles over c),
+// all smem/global accesses of the tile are 128-bit, and each 128-bit weight load of the 8 lanes c covers one
+// contiguous 128-byte line (no bank conflicts).  MLP-in column 32*m + 4*c + j sits in lane c's slot (m, j), so
+// each quarter m of the hidden units is spread evenly over the lanes for the chunked MLP-out accumulation.
+// ------------------------------------------------------------------------------------------------
+constexpr int V2G = 16;
+
+// attention of ONE (trajectory, head) pair held entirely by the calling lane; q in registers
+template <int NCTX>
+__device__ __forceinline__ void lane_attention(const float (&q)[8], const float* Kp, const float* Vp, int L,
+                                               float (&acc)[8]) {
+    constexpr int BS = NCTX >= 64 ? 4 : 8;
+    const float scale = 2.8284271247461903f;
+    float sc[NCTX];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j0 = 0; j0 < NCTX; j0 += BS) {
+        if (j0 < L) {
+            float kk[BS][8];
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) ldg256(Kp + min(j0 + jj, L - 1) * 32, kk[jj]);
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) {
+                float s0 = 0.f;
+#pragma unroll
+                for (int d = 0; d < 8; d++) s0 = fmaf(q[d], kk[jj][d], s0);
+                const float s1 = (j0 + jj < L) ? s0 / scale : -INFINITY;
+                sc[j0 + jj] = s1;
+                m = fmaxf(m, s1);
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) sc[j0 + jj] = -INFINITY;
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCTX; j++) {
+        const float pj = (j < L) ? expf(sc[j] - m) : 0.f;
+        sc[j] = pj;
+        sum += pj;
+    }
+    const float rs = 1.0f / sum;
+#pragma unroll
+    for (int d = 0; d < 8; d++) acc[d] = 0.f;
+#pragma unroll
+    for (int j0 = 0; j0 < NCTX; j0 += BS) {
+        if (j0 < L) {
+            float vv[BS][8];
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) ldg256(Vp + min(j0 + jj, L - 1) * 32, vv[jj]);
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) {
+                const float pw = sc[j0 + jj] * rs;
+#pragma unroll
+                for (int d = 0; d < 8; d++) acc[d] = fmaf(pw, vv[jj][d], acc[d]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// acc[i][4*m + j] += sum_k aT[k*16 + r*4 + i] * W[k*ldw + MS*m + j]     (NQ float4 weight loads per k; the 8
+// lanes c of a row read 8 consecutive float4 = one conflict-free 128-byte line per load)
+template <int NQ, int MS = 4>
+__device__ __forceinline__ void tile_gemv(const float* aT, const float* W, int K, int ldw, int r,
+                                          float (&acc)[4][4 * NQ]) {
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        const float4 a = lds4(aT + k * V2G + r * 4);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int m = 0; m < NQ; m++) {
+            const float4 w = lds4(W + k * ldw + MS * m);
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][4 * m + j] = fmaf(av[i], wv[j], acc[i][4 * m + j]);
+        }
+    }
+}
+
+// LayerNorm of the [4 traj][4 ch] register tile over the 32 channels (spread over the 8 lanes c), written
+// transposed to aT[(c*4+j)*16 + r*4 + i]
+__device__ __forceinline__ void tile_ln_to_smem(const float (&h)[4][4], const float* lw, const float* lb, float eps,
+                                                float* aT, int r, int c) {
+    const float4 w4 = lds4(lw + c * 4), b4 = lds4(lb + c * 4);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float n[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float s = (h[i][0] + h[i][1]) + (h[i][2] + h[i][3]);
+        s += __shfl_xor_sync(FULL, s, 4);
+        s += __shfl_xor_sync(FULL, s, 8);
+        s += __shfl_xor_sync(FULL, s, 16);
+        const float mean = s * (1.0f / 32.0f);
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            n[i][j] = h[i][j] - mean;
+            v = fmaf(n[i][j], n[i][j], v);
+        }
+        v += __shfl_xor_sync(FULL, v, 4);
+        v += __shfl_xor_sync(FULL, v, 8);
+        v += __shfl_xor_sync(FULL, v, 16);
+        const float rstd = 1.0f / sqrtf(v * (1.0f / 32.0f) + eps);
+#pragma unroll
+        for (int j = 0; j < 4; j++) n[i][j] = n[i][j] * rstd * wv[j] + bv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        *reinterpret_cast<float4*>(aT + (c * 4 + j) * V2G + r * 4) = make_float4(n[0][j], n[1][j], n[2][j], n[3][j]);
+}
+
+template <int NCTX, bool CACHE>
+__global__ void __launch_bounds__(384, 1) rollout_e32v2_kernel(RolloutParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t bar;
+    const Gpt2Layout& L = p.lay;
+    const int C = L.n_ctx, NL = L.n_layer;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, W = blockDim.x >> 5;
+    const int r = lane & 3, c = lane >> 2;      // lane = r + 4*c: conflict-light transposed tile stores
+    float* wsm = sm;
+    float* scr = sm + L.total + warp * (32 * V2G);
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)L.total * 4u;
+        mbar_expect_tx(&bar, bytes);
+        const uint32_t CH = 32768u;
+        for (uint32_t off = 0; off < bytes; off += CH)
+            bulk_g2s(reinterpret_cast<char*>(wsm) + off, reinterpret_cast<const char*>(p.blob) + off,
+                     min(CH, bytes - off), &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const int ngroups = (p.B + V2G - 1) / V2G;
+    const size_t kv_per_g = (size_t)NL * 2 * C * 32;
+    float* kvw = CACHE ? p.kv + (size_t)(blockIdx.x * W + warp) * V2G * kv_per_g : nullptr;
+    const float* gw = wsm + L.lnfw;
+
+    for (int grp = blockIdx.x * W + warp; grp < ngroups; grp += gridDim.x * W) {
+        const int b0 = grp * V2G + r * 4;            // first trajectory of this lane's tile rows
+        float h[4][4];
+        {
+            const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pe + c * 4));
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b0 + i < p.B) x = *reinterpret_cast<const float4*>(p.x0 + (size_t)(b0 + i) * p.x0_stride + c * 4);
+                h[i][0] = x.x + pe.x; h[i][1] = x.y + pe.y; h[i][2] = x.z + pe.z; h[i][3] = x.w + pe.w;
+            }
+        }
+        for (int s = 0; s < p.S; s++) {
+            const int Lk = CACHE ? min(s + 1, C) : 1;
+            const int slot = CACHE ? (s % C) : 0;
+            for (int l = 0; l < NL; l++) {
+                const float* w = wsm + l * L.layer_stride;
+                if constexpr (CACHE) {
+                    if (p.prefetch && lane < V2G && Lk > 1) {
+                        const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
+                        prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
+                        prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+                    }
+                }
+                tile_ln_to_smem(h, w + L.ln1w, w + L.ln1b, p.eps, scr, r, c);
+                __syncwarp();
+                if constexpr (CACHE) {
+                    float qkv[3][4][4];
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        const float4 b = lds4(w + L.bqkv + 32 * t + c * 4);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { qkv[t][i][0] = b.x; qkv[t][i][1] = b.y; qkv[t][i][2] = b.z; qkv[t][i][3] = b.w; }
+                    }
+#pragma unroll 2
+                    for (int k = 0; k < 32; k++) {
+                        const float4 a = lds4(scr + k * V2G + r * 4);
+                        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int t = 0; t < 3; t++) {
+                            const float4 wq = lds4(w + L.wqkv + k * 96 + 32 * t + c * 4);
+                            const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+#pragma unroll
+                                for (int j = 0; j < 4; j++) qkv[t][i][j] = fmaf(av[i], wv[j], qkv[t][i][j]);
+                        }
+                    }
+                    // append k, v rows (16 bytes per lane, 128 B per trajectory row per instruction)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float* kp = kvw + (size_t)(r * 4 + i) * kv_per_g + (size_t)(l * 2) * C * 32 + slot * 32 + c * 4;
+                        *reinterpret_cast<float4*>(kp) = make_float4(qkv[1][i][0], qkv[1][i][1], qkv[1][i][2], qkv[1][i][3]);
+                        *reinterpret_cast<float4*>(kp + C * 32) = make_float4(qkv[2][i][0], qkv[2][i][1], qkv[2][i][2], qkv[2][i][3]);
+                    }
+                    __syncwarp();                 // LN tile consumed; ring rows visible to the warp
+#pragma unroll
+                    for (int i = 0; i < 4; i++)     // queries, row-major per trajectory: qs[g][32]
+                        *reinterpret_cast<float4*>(scr + (r * 4 + i) * 32 + c * 4) =
+                            make_float4(qkv[0][i][0], qkv[0][i][1], qkv[0][i][2], qkv[0][i][3]);
+                    __syncwarp();
+                    float o[2][8];
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++) {
+                        const int id = lane + 32 * pp, g = id >> 2, hh = id & 3;
+                        float q[8];
+                        const float4 qa = lds4(scr + g * 32 + hh * 8), qb = lds4(scr + g * 32 + hh * 8 + 4);
+                        q[0] = qa.x; q[1] = qa.y; q[2] = qa.z; q[3] = qa.w; q[4] = qb.x; q[5] = qb.y; q[6] = qb.z; q[7] = qb.w;
+                        const float* Kp = kvw + (size_t)g * kv_per_g + (size_t)(l * 2) * C * 32 + hh * 8;
+                        lane_attention<NCTX>(q, Kp, Kp + C * 32, Lk, o[pp]);
+                    }
+                    __syncwarp();                 // every lane has read its queries
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++) {
+                        const int id = lane + 32 * pp, g = id >> 2, hh = id & 3;
+#pragma unroll
+                        for (int d = 0; d < 8; d++) scr[(hh * 8 + d) * V2G + g] = o[pp][d];
+                    }
+                    __syncwarp();
+                } else {
+                    float vv[4][4];
+                    {
+                        const float4 b = lds4(w + L.bqkv + 64 + c * 4);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { vv[i][0] = b.x; vv[i][1] = b.y; vv[i][2] = b.z; vv[i][3] = b.w; }
+                    }
+                    tile_gemv<1>(scr, w + L.wqkv + 64 + c * 4, 32, 96, r, vv);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        *reinterpret_cast<float4*>(scr + (c * 4 + j) * V2G + r * 4) = make_float4(vv[0][j], vv[1][j], vv[2][j], vv[3][j]);
+                    __syncwarp();
+                }
+                {   // output projection + residual
+                    float acc[4][4];
+                    const float4 b = lds4(w + L.bproj + c * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { acc[i][0] = b.x; acc[i][1] = b.y; acc[i][2] = b.z; acc[i][3] = b.w; }
+                    tile_gemv<1>(scr, w + L.wproj + c * 4, 32, 32, r, acc);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) h[i][j] += acc[i][j];
+                }
+                __syncwarp();
+                tile_ln_to_smem(h, w + L.ln2w, w + L.ln2b, p.eps, scr, r, c);
+                __syncwarp();
+                float f[4][16];
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const float4 b = lds4(w + L.bfc + 32 * m + c * 4);      // unit 32*m + 4*c + j
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { f[i][4 * m] = b.x; f[i][4 * m + 1] = b.y; f[i][4 * m + 2] = b.z; f[i][4 * m + 3] = b.w; }
+                }
+                tile_gemv<4, 32>(scr, w + L.wfc + c * 4, 32, 128, r, f);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 16; j++) f[i][j] = gelu_new(f[i][j]);
+                float acc[4][4];
+                {
+                    const float4 b = lds4(w + L.bpr + c * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { acc[i][0] = b.x; acc[i][1] = b.y; acc[i][2] = b.z; acc[i][3] = b.w; }
+                }
+#pragma unroll
+                for (int qd = 0; qd < 4; qd++) {
+                    // hidden units 32*qd .. 32*qd+31: this lane holds units 32*qd + 4*c + i2 in f[.][4*qd + i2]
+                    __syncwarp();
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; i2++)
+                        *reinterpret_cast<float4*>(scr + (4 * c + i2) * V2G + r * 4) =
+                            make_float4(f[0][4 * qd + i2], f[1][4 * qd + i2], f[2][4 * qd + i2], f[3][4 * qd + i2]);
+                    __syncwarp();
+                    tile_gemv<1>(scr, w + L.wpr + (32 * qd) * 32 + c * 4, 32, 32, r, acc);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) h[i][j] += acc[i][j];
+                __syncwarp();
+            }
+            // final LayerNorm + linear head
+            tile_ln_to_smem(h, gw, gw + 32, p.eps, scr, r, c);
+            __syncwarp();
+            float y[4][4];
+            {
+                const float4 b = lds4(gw + 64 + 1024 + c * 4);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { y[i][0] = b.x; y[i][1] = b.y; y[i][2] = b.z; y[i][3] = b.w; }
+            }
+            tile_gemv<1>(scr, gw + 64 + c * 4, 32, 32, r, y);
+            const int pnext = CACHE ? min(s + 1, C - 1) : 0;
+            const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pe + pnext * 32 + c * 4));
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (b0 + i < p.B)
+                    *reinterpret_cast<float4*>(p.out + (size_t)(b0 + i) * p.out_stride + (size_t)s * 32 + c * 4) =
+                        make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+                h[i][0] = y[i][0] + pe.x; h[i][1] = y[i][1] + pe.y; h[i][2] = y[i][2] + pe.z; h[i][3] = y[i][3] + pe.w;
+            }
+            __syncwarp();
+        }
+        if (CACHE && p.presents != nullptr) {
+            const int Tk = min(p.S, C);
+            const int H = 4, hd = 8;
+            const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+            const int hh = lane >> 3, d = lane & 7;
+            for (int g = 0; g < V2G; g++) {
+                const int b = grp * V2G + g;
+                if (b >= p.B) break;
+                for (int rr = 0; rr < NL * 2 * Tk; rr++) {
+                    const int t = rr % Tk, lw = rr / Tk;
                     const int which = lw & 1, l = lw >> 1;
                     const int sl = (p.S - Tk + t) % C;
                     p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
@@ -812,6 +1160,23 @@ int launch_e32(const RolloutParams& p, int maxi, int grid, int block, size_t sme
     }
 }
 
+template <int NCTX, bool CACHE>
+int launch_v2_one(const RolloutParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    TRPX_CUDA(cudaFuncSetAttribute(rollout_e32v2_kernel<NCTX, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    rollout_e32v2_kernel<NCTX, CACHE><<<grid, block, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int launch_v2(const RolloutParams& p, int n_ctx, int grid, int block, size_t smem, cudaStream_t st) {
+    if (!p.use_cache) return launch_v2_one<8, false>(p, grid, block, smem, st);
+    if (n_ctx <= 8) return launch_v2_one<8, true>(p, grid, block, smem, st);
+    if (n_ctx <= 16) return launch_v2_one<16, true>(p, grid, block, smem, st);
+    if (n_ctx <= 32) return launch_v2_one<32, true>(p, grid, block, smem, st);
+    return launch_v2_one<64, true>(p, grid, block, smem, st);
+}
+
 int ensure_kv(trpx_gpt2_t h, size_t bytes) {
     if (bytes <= h->kv_bytes) return TRPX_OK;
     if (h->kv) {
@@ -922,7 +1287,7 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 4, "variant must be 0..4");
+    TRPX_REQUIRE(variant >= 0 && variant <= 5, "variant must be 0..5");
     TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 12, "warps_per_cta must be 0..12");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
                      traj_per_warp == 8, "traj_per_warp must be 0,1,2,4,8");
@@ -966,6 +1331,32 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
     const bool e32_shape = (L.E == 32 && L.n_head == 4 && L.n_ctx <= 64);
     const size_t wbytes = (size_t)L.total * sizeof(float);
     const int scr_per_warp_g1 = 64 * (int)sizeof(float);
+    // ---- second-generation kernel (16 trajectories per warp, 2-D lane tiling): large batches ----
+    {
+        const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
+        const int ngroups = (B + V2G - 1) / V2G;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                             (x0_stride % 4) == 0 && (out_stride % 4) == 0;
+        const size_t scr_w = (size_t)32 * V2G * sizeof(float);
+        const bool fits = wbytes + scr_w + 1024 <= (size_t)h->smem_optin;
+        // measured (profiles/r01_sweep_rollout_v2.jsonl): v2 wins without the KV window, v1 (G = 4) with it
+        const bool want = h->tune_variant == 5 ||
+                          (h->tune_variant == 0 && !use_cache && (long long)ngroups >= (long long)sms * 8);
+        if (e32_shape && aligned && fits && want) {
+            const int max_w = (int)std::min<size_t>(12, ((size_t)h->smem_optin - 1024 - wbytes) / scr_w);
+            const int grid = std::min(sms, ngroups);
+            const int wantw = h->tune_warps > 0 ? h->tune_warps : max_w;
+            const int Wc = std::max(1, std::min(std::min(wantw, max_w), (ngroups + grid - 1) / grid));
+            const size_t smem = wbytes + (size_t)Wc * scr_w;
+            if (use_cache) {
+                int rc = ensure_kv(h, (size_t)grid * Wc * V2G * kv_per_traj);
+                if (rc) return rc;
+            }
+            p.kv = h->kv;
+            h->last_variant = 5; h->last_grid = grid; h->last_block = Wc * 32; h->last_smem = (int)smem; h->last_group = V2G;
+            return launch_v2(p, L.n_ctx, grid, Wc * 32, smem, st);
+        }
+    }
     bool use_e32 = e32_shape && h->tune_variant != 1 && wbytes + (size_t)scr_per_warp_g1 + 1024 <= (size_t)h->smem_optin;
     if (use_e32) {
         const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;

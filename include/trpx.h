@@ -80,10 +80,11 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0_dev, long long x0_stride,
 
 /* Tuning knobs of the rollout kernel (0 = automatic).  `variant`: 0 auto, 1 generic kernel only, 2 E=32 warp
  * kernel, 3 = 2 without TMA weight staging, 4 = 2 without the L2 window prefetch (for A/B measurements),
- * 5 = second-generation E=32 kernel (16 trajectories per warp; chosen automatically for large batches). */
+ * 5 = E=32 kernel with 2-D lane tiling (16 trajectories per warp), 6 = E=32 tensor-core kernel (3xTF32
+ * mma.sync; chosen automatically for large batches without the KV window). */
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp,
                                  int max_ctas);
-/* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 e32 warp kernel, 5 e32 v2 kernel), grid, block,
+/* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 E=32 warp kernel, 5 E=32 2-D tiling, 6 E=32 tensor-core), grid, block,
  * dynamic smem bytes, trajectories per warp/CTA group. */
 int trpx_gpt2_last_launch(trpx_gpt2_t h, int* variant, int* grid, int* block, int* smem, int* group);
 

@@ -45,7 +45,7 @@ def main():
             for variant in [int(v) for v in args.variants.split(",")]:
                 for G in [int(g) for g in args.groups.split(",")]:
                     for W in [int(w) for w in args.warps.split(",")]:
-                        tr.set_rollout_tuning(variant=variant, warps_per_cta=W, traj_per_warp=0 if variant == 5 else G)
+                        tr.set_rollout_tuning(variant=variant, warps_per_cta=W, traj_per_warp=0 if variant in (5, 6) else G)
                         for uc in (True, False):
                             ms = time_rollout(tr, g0, S, uc)
                             fl = algorithmic_flops_per_traj_step(cfg, S, uc) * B * S

@@ -39,7 +39,7 @@ def make_cylinder(cfg_ns, seed, device=None):
 _prefix_cache = {}
 
 
-def stable_prefix(cfg_ns, weights_np, ctx, max_length, use_cache, thresh=3e-6):
+def stable_prefix(cfg_ns, weights_np, ctx, max_length, use_cache, thresh=2e-6):
     """Free rollouts with the stress weights can be chaotic: the reference's OWN float32 arithmetic then drifts
     from exact arithmetic exponentially, and no implementation can match it beyond that point.  Returns
     (n, out32): the number of leading tokens over which the oracle run in float32 stays within `thresh`

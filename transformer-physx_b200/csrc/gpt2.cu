@@ -22,6 +22,7 @@ struct trpx_gpt2 {
     int sm_count = 0;
     int smem_optin = 0;
     float* blob = nullptr;
+    float* blob_sw = nullptr;
     float* pe = nullptr;
     bool loaded = false;
     float* kv = nullptr;          // rollout workspace (KV windows of the groups in flight)
@@ -138,6 +139,7 @@ __device__ __forceinline__ void warp_attention(const float* q, int qs, const flo
 // ------------------------------------------------------------------------------------------------
 struct RolloutParams {
     const float* blob;
+    const float* blob_sw;    // XOR-swizzled weight image for the tensor-core kernel (E = 32 only)
     const float* pe;
     const float* x0;
     long long x0_stride;
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(384, 1) rollout_e32_kernel(RolloutParams p) {
 #pragma unroll
                 for (int c = 0; c < 4; c++)
 #pragma unroll
-                    for (int g = 0; g < G; g++) f[c][g] = gelu_new(f[c][g]);
+                    for (int g = 0; g < G; g++) f[c][g] = gelu_new_sig(f[c][g]);
                 float acc[1][G];
 #pragma unroll
                 for (int g = 0; g < G; g++) acc[0][g] = w[L.bpr + lane];
@@ -906,7 +908,7 @@ __global__ void __launch_bounds__(384, 1) rollout_e32v2_kernel(RolloutParams p) 
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < 16; j++) f[i][j] = gelu_new(f[i][j]);
+                    for (int j = 0; j < 16; j++) f[i][j] = gelu_new_sig(f[i][j]);
                 float acc[4][4];
                 {
                     const float4 b = lds4(w + L.bpr + c * 4);
@@ -969,6 +971,331 @@ __global__ void __launch_bounds__(384, 1) rollout_e32v2_kernel(RolloutParams p) 
             }
             __syncwarp();
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (E = 32, head size 8), tensor-core generation: 3xTF32 on mma.sync.m16n8k8 (SASS HMMA.1688.F32.TF32).
+// Why: ncu shows the SIMT GEMVs bound by shared-memory return bandwidth at ~40 % of the FP32 pipe; the tensor
+// path measured on this B200 (scripts/probes/mma_probe.cu) sustains 278 TFLOP/s TF32 with 4 warps per SM, i.e.
+// ~93 TFLOP/s for the error-compensated 3xTF32 product (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi, FP32 accumulate),
+// which keeps the FP32 parity bar (plain TF32 would not).  tcgen05 needs M >= 64 rows per CTA tile, TMEM
+// round trips and hi/lo weight planes (2 x 203 KB > shared memory); at 16 trajectories per warp the legacy
+// warp-level MMA keeps the warp-autonomous, weights-resident structure of the SIMT kernels.
+//   * one warp = one 16-trajectory M-tile; lane (g = lane>>2, q = lane&3) holds rows g and g+8;
+//   * the residual stream lives in C-fragment layout; a C fragment of n-tile t IS the A fragment of k-step t
+//     when the K order inside a k-step is taken as (8t+0, 8t+2, 8t+4, 8t+6 | 8t+1, 8t+3, 8t+5, 8t+7) — so
+//     activations go GEMV -> GEMV through registers only (LayerNorm: 2 xor-shuffles over q);
+//   * B fragments come from an XOR-swizzled FP32 weight image in shared memory (conflict-free), split into
+//     TF32 hi/lo on the fly (cvt.rna + subtract);
+//   * the MLP is fused per 8 hidden units: MLP-in tile -> gelu -> A fragment -> 4 MLP-out tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int V4G = 16;
+constexpr int V4QS = 36;          // row stride (floats) of the per-warp q / attention-output staging tile
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_hi(x);
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += A(16x8) * W(8x8) with error compensation; w0/w1 = the lane's two FP32 weights of the tile
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float w0,
+                                     float w1) {
+    uint32_t bh0, bl0, bh1, bl1;
+    split_tf32(w0, bh0, bl0);
+    split_tf32(w1, bh1, bl1);
+    mma_tf32(c, al, bh0, bh1);
+    mma_tf32(c, ah, bl0, bl1);
+    mma_tf32(c, ah, bh0, bh1);
+}
+// C-fragment values (row g: x0, x1 ; row g+8: x2, x3) -> A fragment (a0,a1,a2,a3) = (x0, x2, x1, x3), hi/lo
+__device__ __forceinline__ void frag_c2a(const float (&x)[4], uint32_t (&ah)[4], uint32_t (&al)[4]) {
+    split_tf32(x[0], ah[0], al[0]);
+    split_tf32(x[2], ah[1], al[1]);
+    split_tf32(x[1], ah[2], al[2]);
+    split_tf32(x[3], ah[3], al[3]);
+}
+// swizzled weight element (k, n) of a [K][N] matrix: k*N + (n ^ (((k >> 1) & 3) << 3)).  For the B fragment of
+// k-step s / n-tile t the lane reads rows 8s+2q and 8s+2q+1 at physical column 8*(t^q) + g.
+__device__ __forceinline__ void ldb(const float* W, int N, int s, int t, int g, int q, float& w0, float& w1) {
+    const float* p = W + (8 * s + 2 * q) * N + 8 * (t ^ q) + g;
+    w0 = p[0];
+    w1 = p[N];
+}
+// acc[t] (t < NT) += X * W[:, 8*(t0+t) .. +8) for X given as KS k-step fragments
+template <int KS, int NT>
+__device__ __forceinline__ void gemv_mma(float (&acc)[NT][4], const uint32_t (&ah)[KS][4], const uint32_t (&al)[KS][4],
+                                         const float* W, int N, int t0, int g, int q) {
+#pragma unroll
+    for (int s = 0; s < KS; s++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) {       // NT independent accumulator chains in flight
+            float w0, w1;
+            ldb(W, N, s, t0 + t, g, q, w0, w1);
+            mma3(acc[t], ah[s], al[s], w0, w1);
+        }
+}
+// LayerNorm over the 32 channels of rows g and g+8 (fragment layout), result as A fragments
+__device__ __forceinline__ void frag_ln(const float (&h)[4][4], const float* lw, const float* lb, float eps, int q,
+                                        uint32_t (&ah)[4][4], uint32_t (&al)[4][4]) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; t++) { s0 += h[t][0] + h[t][1]; s1 += h[t][2] + h[t][3]; }
+    s0 += __shfl_xor_sync(FULL, s0, 1); s0 += __shfl_xor_sync(FULL, s0, 2);
+    s1 += __shfl_xor_sync(FULL, s1, 1); s1 += __shfl_xor_sync(FULL, s1, 2);
+    const float m0 = s0 * (1.0f / 32.0f), m1 = s1 * (1.0f / 32.0f);
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const float a = h[t][0] - m0, b = h[t][1] - m0, c = h[t][2] - m1, d = h[t][3] - m1;
+        v0 = fmaf(a, a, v0); v0 = fmaf(b, b, v0);
+        v1 = fmaf(c, c, v1); v1 = fmaf(d, d, v1);
+    }
+    v0 += __shfl_xor_sync(FULL, v0, 1); v0 += __shfl_xor_sync(FULL, v0, 2);
+    v1 += __shfl_xor_sync(FULL, v1, 1); v1 += __shfl_xor_sync(FULL, v1, 2);
+    const float r0 = 1.0f / sqrtf(v0 * (1.0f / 32.0f) + eps), r1 = 1.0f / sqrtf(v1 * (1.0f / 32.0f) + eps);
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const float2 w2 = *reinterpret_cast<const float2*>(lw + 8 * t + 2 * q);
+        const float2 b2 = *reinterpret_cast<const float2*>(lb + 8 * t + 2 * q);
+        float x[4];
+        x[0] = (h[t][0] - m0) * r0 * w2.x + b2.x;
+        x[1] = (h[t][1] - m0) * r0 * w2.y + b2.y;
+        x[2] = (h[t][2] - m1) * r1 * w2.x + b2.x;
+        x[3] = (h[t][3] - m1) * r1 * w2.y + b2.y;
+        frag_c2a(x, ah[t], al[t]);
+    }
+}
+__device__ __forceinline__ void frag_bias(float (&c)[4], const float* b, int t, int q) {
+    const float2 b2 = *reinterpret_cast<const float2*>(b + 8 * t + 2 * q);
+    c[0] = b2.x; c[1] = b2.y; c[2] = b2.x; c[3] = b2.y;
+}
+
+template <int NCTX, bool CACHE>
+__global__ void __launch_bounds__(384, 1) rollout_e32v4_kernel(RolloutParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t bar;
+    const Gpt2Layout& L = p.lay;
+    const int C = L.n_ctx, NL = L.n_layer;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, W = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    float* wsm = sm;
+    float* scr = sm + L.total + warp * (V4G * V4QS);      // only used (and allocated) with the KV window
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)L.total * 4u;
+        mbar_expect_tx(&bar, bytes);
+        const uint32_t CH = 32768u;
+        for (uint32_t off = 0; off < bytes; off += CH)
+            bulk_g2s(reinterpret_cast<char*>(wsm) + off, reinterpret_cast<const char*>(p.blob_sw) + off,
+                     min(CH, bytes - off), &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const int ngroups = (p.B + V4G - 1) / V4G;
+    const size_t kv_per_g = (size_t)NL * 2 * C * 32;
+    float* kvw = CACHE ? p.kv + (size_t)(blockIdx.x * W + warp) * V4G * kv_per_g : nullptr;
+    const float* gw = wsm + L.lnfw;
+
+    for (int grp = blockIdx.x * W + warp; grp < ngroups; grp += gridDim.x * W) {
+        const int br[2] = {grp * V4G + g, grp * V4G + g + 8};     // the lane's two trajectories
+        float h[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const float2 pe = __ldg(reinterpret_cast<const float2*>(p.pe + 8 * t + 2 * q));
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                float2 x = make_float2(0.f, 0.f);
+                if (br[rr] < p.B) x = *reinterpret_cast<const float2*>(p.x0 + (size_t)br[rr] * p.x0_stride + 8 * t + 2 * q);
+                h[t][2 * rr] = x.x + pe.x;
+                h[t][2 * rr + 1] = x.y + pe.y;
+            }
+        }
+        for (int s = 0; s < p.S; s++) {
+            const int Lk = CACHE ? min(s + 1, C) : 1;
+            const int slot = CACHE ? (s % C) : 0;
+            for (int l = 0; l < NL; l++) {
+                const float* w = wsm + l * L.layer_stride;
+                if constexpr (CACHE) {
+                    if (p.prefetch && lane < V4G && Lk > 1) {
+                        const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
+                        prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
+                        prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+                    }
+                }
+                uint32_t ah[4][4], al[4][4];
+                frag_ln(h, w + L.ln1w, w + L.ln1b, p.eps, q, ah, al);
+                float o[4][4];                    // attention output, fragment layout
+                if constexpr (CACHE) {
+                    float qf[4][4], kf[4][4], vf[4][4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        frag_bias(qf[t], w + L.bqkv, t, q);
+                        frag_bias(kf[t], w + L.bqkv + 32, t, q);
+                        frag_bias(vf[t], w + L.bqkv + 64, t, q);
+                    }
+                    gemv_mma<4, 4>(qf, ah, al, w + L.wqkv, 96, 0, g, q);
+                    gemv_mma<4, 4>(kf, ah, al, w + L.wqkv, 96, 4, g, q);
+                    gemv_mma<4, 4>(vf, ah, al, w + L.wqkv, 96, 8, g, q);
+                    // append k, v rows of the two trajectories; stage q row-major for the per-pair attention
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++) {
+                        float* kp = kvw + (size_t)(g + 8 * rr) * kv_per_g + (size_t)(l * 2) * C * 32 + slot * 32 + 2 * q;
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            *reinterpret_cast<float2*>(kp + 8 * t) = make_float2(kf[t][2 * rr], kf[t][2 * rr + 1]);
+                            *reinterpret_cast<float2*>(kp + C * 32 + 8 * t) = make_float2(vf[t][2 * rr], vf[t][2 * rr + 1]);
+                            *reinterpret_cast<float2*>(scr + (g + 8 * rr) * V4QS + 8 * t + 2 * q) =
+                                make_float2(qf[t][2 * rr], qf[t][2 * rr + 1]);
+                        }
+                    }
+                    __syncwarp();
+                    float oo[2][8];
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++) {
+                        const int id = lane + 32 * pp, tg = id >> 2, hh = id & 3;
+                        float qq[8];
+                        const float4 qa = lds4(scr + tg * V4QS + hh * 8), qb = lds4(scr + tg * V4QS + hh * 8 + 4);
+                        qq[0] = qa.x; qq[1] = qa.y; qq[2] = qa.z; qq[3] = qa.w; qq[4] = qb.x; qq[5] = qb.y; qq[6] = qb.z; qq[7] = qb.w;
+                        const float* Kp = kvw + (size_t)tg * kv_per_g + (size_t)(l * 2) * C * 32 + hh * 8;
+                        lane_attention<NCTX>(qq, Kp, Kp + C * 32, Lk, oo[pp]);
+                    }
+                    __syncwarp();                 // all queries read: the tile is reused for the outputs
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++) {
+                        const int id = lane + 32 * pp, tg = id >> 2, hh = id & 3;
+                        *reinterpret_cast<float4*>(scr + tg * V4QS + hh * 8) = make_float4(oo[pp][0], oo[pp][1], oo[pp][2], oo[pp][3]);
+                        *reinterpret_cast<float4*>(scr + tg * V4QS + hh * 8 + 4) = make_float4(oo[pp][4], oo[pp][5], oo[pp][6], oo[pp][7]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++) {
+                            const float2 v2 = *reinterpret_cast<const float2*>(scr + (g + 8 * rr) * V4QS + 8 * t + 2 * q);
+                            o[t][2 * rr] = v2.x;
+                            o[t][2 * rr + 1] = v2.y;
+                        }
+                    __syncwarp();
+                } else {
+                    // window of one key: the head output is v itself
+#pragma unroll
+                    for (int t = 0; t < 4; t++) frag_bias(o[t], w + L.bqkv + 64, t, q);
+                    gemv_mma<4, 4>(o, ah, al, w + L.wqkv, 96, 8, g, q);
+                }
+                // ---- output projection + residual ----
+#pragma unroll
+                for (int t = 0; t < 4; t++) frag_c2a(o[t], ah[t], al[t]);
+                {
+                    float acc[4][4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) frag_bias(acc[t], w + L.bproj, t, q);
+                    gemv_mma<4, 4>(acc, ah, al, w + L.wproj, 32, 0, g, q);
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) h[t][i] += acc[t][i];
+                }
+                // ---- LN2 + MLP fused per 8 hidden units ----
+                frag_ln(h, w + L.ln2w, w + L.ln2b, p.eps, q, ah, al);
+                float pr[4][4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) frag_bias(pr[t], w + L.bpr, t, q);
+#pragma unroll 1
+                for (int tf0 = 0; tf0 < 16; tf0 += 4) {
+                    // four MLP-in tiles (32 hidden units) at a time: 4 independent MMA chains
+                    float fc[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) frag_bias(fc[j], w + L.bfc, tf0 + j, q);
+                    gemv_mma<4, 4>(fc, ah, al, w + L.wfc, 128, tf0, g, q);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) fc[j][i] = gelu_new_sig(fc[j][i]);
+                        uint32_t fh[4], fl[4];
+                        frag_c2a(fc[j], fh, fl);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            float w0, w1;
+                            ldb(w + L.wpr, 32, tf0 + j, u, g, q, w0, w1);
+                            mma3(pr[u], fh, fl, w0, w1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) h[t][i] += pr[t][i];
+            }
+            // ---- final LayerNorm + linear head ----
+            uint32_t ah[4][4], al[4][4];
+            frag_ln(h, gw, gw + 32, p.eps, q, ah, al);
+            float y[4][4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) frag_bias(y[t], gw + 64 + 1024, t, q);
+            gemv_mma<4, 4>(y, ah, al, gw + 64, 32, 0, g, q);
+            const int pnext = CACHE ? min(s + 1, C - 1) : 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float2 pe = __ldg(reinterpret_cast<const float2*>(p.pe + pnext * 32 + 8 * t + 2 * q));
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    if (br[rr] < p.B)
+                        *reinterpret_cast<float2*>(p.out + (size_t)br[rr] * p.out_stride + (size_t)s * 32 + 8 * t + 2 * q) =
+                            make_float2(y[t][2 * rr], y[t][2 * rr + 1]);
+                    h[t][2 * rr] = y[t][2 * rr] + pe.x;
+                    h[t][2 * rr + 1] = y[t][2 * rr + 1] + pe.y;
+                }
+            }
+        }
+        if (CACHE && p.presents != nullptr) {
+            __syncwarp();
+            const int Tk = min(p.S, C);
+            const int H = 4, hd = 8;
+            const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+            const int hh = lane >> 3, d = lane & 7;
+            for (int tg = 0; tg < V4G; tg++) {
+                const int b = grp * V4G + tg;
+                if (b >= p.B) break;
+                for (int rr = 0; rr < NL * 2 * Tk; rr++) {
+                    const int t = rr % Tk, lw = rr / Tk;
+                    const int which = lw & 1, l = lw >> 1;
+                    const int sl = (p.S - Tk + t) % C;
+                    p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                        kvw[(size_t)tg * kv_per_g + ((size_t)lw * C + sl) * 32 + lane];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// swizzled weight image for the tensor-core kernel: every [K][N] matrix element (k, n) moves to column
+// n ^ (((k >> 1) & 3) << 3) of its row; vectors (LN, biases) are copied unchanged.
+__global__ void swizzle_weights_kernel(const float* __restrict__ blob, float* __restrict__ out, Gpt2Layout L) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < L.total; idx += gridDim.x * blockDim.x) {
+        int base = -1, N = 0, rel = 0;
+        if (idx < L.n_layer * L.layer_stride) {
+            const int l = idx / L.layer_stride, o = idx - l * L.layer_stride;
+            if (o >= L.wqkv && o < L.bqkv) { base = l * L.layer_stride + L.wqkv; N = 96; rel = o - L.wqkv; }
+            else if (o >= L.wproj && o < L.bproj) { base = l * L.layer_stride + L.wproj; N = 32; rel = o - L.wproj; }
+            else if (o >= L.wfc && o < L.bfc) { base = l * L.layer_stride + L.wfc; N = 128; rel = o - L.wfc; }
+            else if (o >= L.wpr && o < L.bpr) { base = l * L.layer_stride + L.wpr; N = 32; rel = o - L.wpr; }
+        } else if (idx >= L.wf && idx < L.bf) { base = L.wf; N = 32; rel = idx - L.wf; }
+        if (base < 0) { out[idx] = blob[idx]; continue; }
+        const int k = rel / N, n = rel - k * N;
+        out[base + k * N + (n ^ (((k >> 1) & 3) << 3))] = blob[idx];
     }
 }
 
@@ -1177,6 +1504,23 @@ int launch_v2(const RolloutParams& p, int n_ctx, int grid, int block, size_t sme
     return launch_v2_one<64, true>(p, grid, block, smem, st);
 }
 
+template <int NCTX, bool CACHE>
+int launch_v4_one(const RolloutParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    TRPX_CUDA(cudaFuncSetAttribute(rollout_e32v4_kernel<NCTX, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    rollout_e32v4_kernel<NCTX, CACHE><<<grid, block, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int launch_v4(const RolloutParams& p, int n_ctx, int grid, int block, size_t smem, cudaStream_t st) {
+    if (!p.use_cache) return launch_v4_one<8, false>(p, grid, block, smem, st);
+    if (n_ctx <= 8) return launch_v4_one<8, true>(p, grid, block, smem, st);
+    if (n_ctx <= 16) return launch_v4_one<16, true>(p, grid, block, smem, st);
+    if (n_ctx <= 32) return launch_v4_one<32, true>(p, grid, block, smem, st);
+    return launch_v4_one<64, true>(p, grid, block, smem, st);
+}
+
 int ensure_kv(trpx_gpt2_t h, size_t bytes) {
     if (bytes <= h->kv_bytes) return TRPX_OK;
     if (h->kv) {
@@ -1216,8 +1560,10 @@ int trpx_gpt2_create(const trpx_gpt2_config* cfg, int device, trpx_gpt2_t* out) 
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (cudaMalloc(&h->blob, sizeof(float) * h->lay.total) != cudaSuccess ||
+        cudaMalloc(&h->blob_sw, sizeof(float) * h->lay.total) != cudaSuccess ||
         cudaMalloc(&h->pe, sizeof(float) * cfg->n_ctx * cfg->n_embd) != cudaSuccess) {
         cudaFree(h->blob);
+        cudaFree(h->blob_sw);
         delete h;
         return set_error(TRPX_E_CUDA, "cudaMalloc of the weight blob failed");
     }
@@ -1229,6 +1575,7 @@ int trpx_gpt2_destroy(trpx_gpt2_t h) {
     if (!valid(h)) return set_error(TRPX_E_STATE, "trpx_gpt2_destroy: invalid handle");
     DeviceGuard guard(h->device);
     cudaFree(h->blob);
+    cudaFree(h->blob_sw);
     cudaFree(h->pe);
     cudaFree(h->kv);
     h->magic = 0;
@@ -1264,6 +1611,10 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
     transpose_kernel<<<(E * E + 255) / 256, 256, 0, st>>>(g[2], h->blob + L.wf, E, E);   // [out][in] -> [in][out]
     TRPX_CUDA(cudaGetLastError());
     TRPX_CUDA(cp(L.bf, g[3], E));
+    if (E == 32) {
+        swizzle_weights_kernel<<<64, 256, 0, st>>>(h->blob, h->blob_sw, L);
+        TRPX_CUDA(cudaGetLastError());
+    }
     if (pe_dev != nullptr) {
         TRPX_CUDA(cudaMemcpyAsync(h->pe, pe_dev, sizeof(float) * L.n_ctx * E, cudaMemcpyDeviceToDevice, st));
     } else {
@@ -1287,7 +1638,7 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 5, "variant must be 0..5");
+    TRPX_REQUIRE(variant >= 0 && variant <= 6, "variant must be 0..6");
     TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 12, "warps_per_cta must be 0..12");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
                      traj_per_warp == 8, "traj_per_warp must be 0,1,2,4,8");
@@ -1321,7 +1672,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
     cudaStream_t st = (cudaStream_t)stream;
     const Gpt2Layout& L = h->lay;
     RolloutParams p{};
-    p.blob = h->blob; p.pe = h->pe; p.x0 = x0; p.x0_stride = x0_stride; p.out = out; p.out_stride = out_stride;
+    p.blob = h->blob; p.blob_sw = h->blob_sw; p.pe = h->pe; p.x0 = x0; p.x0_stride = x0_stride; p.out = out; p.out_stride = out_stride;
     p.presents = presents; p.B = B; p.S = S; p.use_cache = use_cache ? 1 : 0; p.eps = h->cfg.ln_eps; p.lay = L;
     p.use_tma = (h->tune_variant == 3) ? 0 : 1;
     p.prefetch = h->tune_prefetch;
@@ -1331,6 +1682,33 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
     const bool e32_shape = (L.E == 32 && L.n_head == 4 && L.n_ctx <= 64);
     const size_t wbytes = (size_t)L.total * sizeof(float);
     const int scr_per_warp_g1 = 64 * (int)sizeof(float);
+    // ---- tensor-core kernel (3xTF32 mma.sync, 16 trajectories per warp) ----
+    {
+        const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
+        const int ngroups = (B + V4G - 1) / V4G;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(out)) & 7) == 0 &&
+                             (x0_stride % 2) == 0 && (out_stride % 2) == 0;
+        const size_t scr_w = use_cache ? (size_t)V4G * V4QS * sizeof(float) : 0;
+        const bool fits = wbytes + scr_w + 1024 <= (size_t)h->smem_optin;
+        // measured (profiles/): without the KV window the tensor-core kernel is 1.7x the SIMT kernels; with it the
+        // 4-trajectories-per-warp SIMT kernel hides the window latency better (more warps per trajectory)
+        const bool want = h->tune_variant == 6 ||
+                          (h->tune_variant == 0 && !use_cache && (long long)ngroups >= (long long)sms * 8);
+        if (e32_shape && aligned && fits && want) {
+            const int max_w = scr_w ? (int)std::min<size_t>(12, ((size_t)h->smem_optin - 1024 - wbytes) / scr_w) : 12;
+            const int grid = std::min(sms, ngroups);
+            const int wantw = h->tune_warps > 0 ? h->tune_warps : 8;
+            const int Wc = std::max(1, std::min(std::min(wantw, max_w), (ngroups + grid - 1) / grid));
+            const size_t smem = wbytes + (size_t)Wc * scr_w;
+            if (use_cache) {
+                int rc = ensure_kv(h, (size_t)grid * Wc * V4G * kv_per_traj);
+                if (rc) return rc;
+            }
+            p.kv = h->kv;
+            h->last_variant = 6; h->last_grid = grid; h->last_block = Wc * 32; h->last_smem = (int)smem; h->last_group = V4G;
+            return launch_v4(p, L.n_ctx, grid, Wc * 32, smem, st);
+        }
+    }
     // ---- second-generation kernel (16 trajectories per warp, 2-D lane tiling): large batches ----
     {
         const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
@@ -1340,8 +1718,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         const size_t scr_w = (size_t)32 * V2G * sizeof(float);
         const bool fits = wbytes + scr_w + 1024 <= (size_t)h->smem_optin;
         // measured (profiles/r01_sweep_rollout_v2.jsonl): v2 wins without the KV window, v1 (G = 4) with it
-        const bool want = h->tune_variant == 5 ||
-                          (h->tune_variant == 0 && !use_cache && (long long)ngroups >= (long long)sms * 8);
+        const bool want = h->tune_variant == 5;
         if (e32_shape && aligned && fits && want) {
             const int max_w = (int)std::min<size_t>(12, ((size_t)h->smem_optin - 1024 - wbytes) / scr_w);
             const int grid = std::min(sms, ngroups);

@@ -57,6 +57,20 @@ def algorithmic_flops_per_traj_step(cfg, horizon, use_cache=True):
     return tot / horizon
 
 
+def window_bytes_per_traj(cfg, horizon):
+    """HBM traffic model of the cache-mode rollout for ONE trajectory over the horizon: every step reads the
+    KV window of every layer (L keys x 2 x E floats), appends one key/value row per layer and writes one token.
+    This is SURVEY.md section 8d's "if the window spills" figure: with >= 4 resident warps per SM needed to hide
+    latency, the in-flight windows (32-64 KiB per trajectory) exceed the on-chip storage by an order of magnitude
+    (DESIGN.md section 3), so the window stream IS the kernel's necessary traffic; ncu confirms it (profiles/)."""
+    E, nl, C = cfg.n_embd, cfg.n_layer, cfg.n_ctx
+    tot = 0
+    for s in range(horizon):
+        L = min(s + 1, C)
+        tot += nl * (2 * L * E * 4 + 2 * E * 4) + E * 4
+    return tot
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -267,6 +281,7 @@ def run_ours(args):
         b.record()
         torch.cuda.synchronize()
         nocache_ms = a.elapsed_time(b)
+        nocache_launch = tr.last_launch()
         # embed / recover alone (median of 5)
         em, rc = [], []
         for _ in range(5):
@@ -285,8 +300,9 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    fp32 = N.ctypes.c_float()
+    fp32, mma = N.ctypes.c_float(), N.ctypes.c_float()
     N.check(N.lib().trpx_probe_fp32_fma(local, N.ctypes.byref(fp32)))
+    N.check(N.lib().trpx_probe_tf32_mma(local, N.ctypes.byref(mma)))
     flops_step = algorithmic_flops_per_traj_step(cfg, S)
     k_flops = flops_step * B * S
     achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
@@ -295,7 +311,17 @@ def run_ours(args):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    out_bytes = B * S * E * 4                       # algorithmic HBM traffic of the rollout: the generated tokens
+    model_bytes = window_bytes_per_traj(cfg, S) * B
+    achieved_gbs = model_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None                                   # dram__bytes_read+write of the same launch from an ncu capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_rollout_traffic.json")
+    if os.path.exists(tpath):
+        for rec in json.load(open(tpath)):
+            if rec.get("kind") == kind and rec.get("B") == B and rec.get("S") == S:
+                traffic = rec["dram_bytes_per_launch"]
+    nc_flops = algorithmic_flops_per_traj_step(cfg, S, use_cache=False) * B * S
+    nc_tf = nc_flops / (nocache_ms * 1e-3) / 1e12
+    kname = {1: "rollout_generic_kernel", 2: "rollout_e32_kernel", 5: "rollout_e32v2_kernel", 6: "rollout_e32v4_kernel"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -307,14 +333,26 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * 3 * 4,
                 "d2h_bytes_per_step": B * (S + 1) * 3 * 4},
         "gpu_launches": 3 * args.steps,
-        "roofline": {"bound": "fp32", "kernel": "rollout_e32_kernel" if launch["variant"] == 2 else "rollout_generic_kernel",
-                     "achieved": achieved_tf, "peak": fp32.value, "unit": "TFLOP/s", "frac": achieved_tf / fp32.value,
-                     "peak_source": "FP32 FMA microbenchmark in this run (trpx_probe_fp32_fma); MEASURED_PEAKS.json has no FP32 entry",
-                     "traffic": None, "kernel_ms": k_ms, "flops_per_traj_step": flops_step,
+        "roofline": {"bound": "hbm", "kernel": kname.get(launch["variant"], "?"),
+                     "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                     "traffic": traffic, "kernel_ms": k_ms, "bytes_per_launch": model_bytes,
+                     "bytes_model": "KV-window stream: per step and layer 2*L*E*4 B read + 2*E*4 B appended, + E*4 B token "
+                                    "written (SURVEY 8d spill case; see bench.py window_bytes_per_traj and DESIGN.md 3)",
                      "kernel_traj_steps_per_s": B * S / (k_ms * 1e-3),
-                     "hbm_view": {"algorithmic_GBps": out_bytes / (k_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak,
-                                  "frac": out_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
-                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+                     "fp32_view": {"achieved": achieved_tf, "peak": fp32.value, "unit": "TFLOP/s",
+                                   "frac": achieved_tf / fp32.value, "flops_per_traj_step": flops_step,
+                                   "peak_source": "FP32 FMA microbenchmark in this run (trpx_probe_fp32_fma)"},
+                     "token_only_view": {"algorithmic_GBps": B * S * E * 4 / (k_ms * 1e-3) / 1e9,
+                                         "note": "tokens written only (window treated as on-chip): not reachable, see DESIGN.md"}},
+        "use_cache_false": {"note": "the reference's DEFAULT generate() mode (1-token forward at position 0, no window)",
+                            "kernel": kname.get(nocache_launch["variant"], "?"), "kernel_ms": nocache_ms,
+                            "traj_steps_per_s": B * S / (nocache_ms * 1e-3),
+                            "roofline": {"bound": "tensor", "achieved": nc_tf, "peak": mma.value / 3.0, "unit": "TFLOP/s",
+                                         "frac": nc_tf / (mma.value / 3.0),
+                                         "peak_source": "measured mma.sync TF32 rate in this run (trpx_probe_tf32_mma) / 3 "
+                                                        "for the error-compensated 3xTF32 product",
+                                         "vs_fp32_fma_peak": nc_tf / fp32.value}},
         "breakdown_ms": {"embed": embed_ms, "rollout": k_ms, "recover": recover_ms, "rollout_use_cache_false": nocache_ms},
     }
     if world == 1 and not args.no_cpu:

@@ -34,6 +34,9 @@ int         trpx_device_info(int device, int* sm_count, int* smem_optin_bytes);
 /* Measured FP32 FMA throughput of `device` in TFLOP/s (register-only FMA chains; the roofline denominator of
  * the FP32-bound kernels, which MEASURED_PEAKS.json does not carry).  Synchronous. */
 int         trpx_probe_fp32_fma(int device, float* tflops_out);
+/* Measured dense TF32 throughput of the warp-level mma.sync.m16n8k8 path (SASS HMMA.1688.F32.TF32) in TFLOP/s:
+ * the denominator (divided by 3 for the error-compensated 3xTF32 product) of the tensor-core rollout kernel. */
+int         trpx_probe_tf32_mma(int device, float* tflops_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Transformer decoder stack: PhysformerGPT2 (trphysx/transformer/phys_transformer_gpt2.py:120-269)
@@ -157,6 +160,10 @@ int trpx_cyl_destroy(trpx_cyl_t h);
 int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w_dev, int n_tensors, void* stream);
 /* Frames per encoder/decoder pass (default 64): intermediates of one pass stay L2-resident. */
 int trpx_cyl_set_chunk(trpx_cyl_t h, int frames);
+/* Decoder conv path of the three heavy upsample+conv layers: 1 = FP32 SIMT direct convolution (default),
+ * 0 = 3xTF32 tensor-core implicit GEMM on mma.sync (opt-in; measured at the same speed with ~8x the rounding
+ * error, profiles/README.md). */
+int trpx_cyl_set_conv_mode(trpx_cyl_t h, int mode);
 /* CylinderEmbedding.embed (:138-154): x[N,3,64,128], visc[N] -> g[N,128] */
 int trpx_cyl_embed(trpx_cyl_t h, const float* x_dev, const float* visc_dev, float* g_dev, int N, void* stream);
 /* CylinderEmbedding.recover (:156-170): g[N,128] -> x[N,3,64,128]; apply_mask=1 zeroes the cylinder

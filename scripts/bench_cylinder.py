@@ -28,11 +28,13 @@ def main():
     ap.add_argument("--horizon", type=int, default=400)
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--cpu", action="store_true", help="also time the oracle port on the host (B=4, short horizon)")
+    ap.add_argument("--conv-mode", type=int, default=1)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = synth.make_config("cylinder")
     emb = make_cylinder(cfg, 2030, dev)
     emb.set_chunk(args.chunk)
+    emb.set_conv_mode(args.conv_mode)
     tr = make_gpt2(cfg, 2031, False, dev)
     S = args.horizon
     for B in [int(b) for b in args.batches.split(",")]:
@@ -60,7 +62,7 @@ def main():
                 "recover_frames_per_s": round(frames / res["recover_ms"] * 1e3, 1),
                 "recover_tflops": round(frames * DEC_FLOPS / res["recover_ms"] / 1e9, 2),
                 "embed_tflops": round(B * ENC_FLOPS / res["embed_ms"] / 1e9, 3),
-                "rollout_launch": tr.last_launch()}
+                "conv_mode": args.conv_mode, "rollout_launch": tr.last_launch()}
         print(json.dumps(line), flush=True)
     if args.cpu:
         Bc, Sc = 4, 40

@@ -28,6 +28,7 @@ struct trpx_cyl {
     float* ws = nullptr;                 // activation workspace for one chunk of frames
     size_t ws_bytes = 0;
     int chunk = 64;                      // frames per decoder/encoder pass (intermediates stay in L2)
+    int conv_mode = 1;                   // 1 = FP32 SIMT direct conv (default), 0 = 3xTF32 mma.sync implicit GEMM (opt-in)
 };
 
 namespace {
@@ -269,6 +270,142 @@ __global__ void __launch_bounds__(CONV_THREADS) conv3x3_tiled_kernel(const float
     }
 }
 
+// ---- tensor-core implicit GEMM for the heavy decoder layers (bilinear x2 upsample + 3x3 conv + ReLU) ------
+// M = pixels, N = output channels, K = 9 taps x Cin, computed as 3xTF32 (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi,
+// FP32 accumulate) on mma.sync.m16n8k8 so the FP32 parity bar holds.  Per chunk of 8 input channels the CTA
+// builds the upsampled, replicate-padded patch ONCE, already split into TF32 hi / lo planes, plus the hi / lo
+// weight slice; a warp owns 2 output rows x 32 pixels (4 M-tiles) and NT*8 output channels.  Fragment loads are
+// bank-conflict free: the patch plane stride (18*36 = 648 = 8 mod 32) and the padded weight row (9*(COUT+8) = 8
+// or 24 mod 32) spread the four k-lanes q over disjoint bank groups.
+constexpr int MCC = 8;                       // input channels per chunk = one k-step per tap
+constexpr int MPLANE = (TH + 2) * PW;        // 648 floats
+
+__device__ __forceinline__ void cyl_split_tf32(float x, float& hi, float& lo) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    hi = __uint_as_float(u);
+    lo = x - hi;
+}
+__device__ __forceinline__ void cyl_mma(float (&c)[4], const float (&a)[4], float b0, float b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(CONV_THREADS) conv3x3_up_mma_kernel(const float* __restrict__ in,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ bias,
+                                                                      float* __restrict__ out, int Cin, int Hs, int Ws,
+                                                                      int Cout) {
+    constexpr int COT = NT * 8;              // output channels per CTA
+    constexpr int COP = COT + 8;             // padded weight row
+    extern __shared__ __align__(16) float smc[];
+    float* p_hi = smc;                       // [MCC][TH+2][PW]
+    float* p_lo = p_hi + MCC * MPLANE;
+    float* w_hi = p_lo + MCC * MPLANE;       // [MCC][9][COP]
+    float* w_lo = w_hi + MCC * 9 * COP;
+    __shared__ Lerp ylut[TH + 2], xlut[TW + 2];
+    const int H = 2 * Hs, W = 2 * Ws;
+    const int tiles_x = (W + TW - 1) / TW;
+    const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW;
+    const int co0 = blockIdx.y * COT;
+    const int n = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+
+    if (tid < TH + 2) {
+        const int yy = min(max(ty0 + tid - 1, 0), H - 1);
+        ylut[tid] = lerp_idx(yy, Hs, (float)(Hs - 1) / (float)(H - 1));
+    } else if (tid >= 64 && tid < 64 + TW + 2) {
+        const int t = tid - 64;
+        const int xx = min(max(tx0 + t - 1, 0), W - 1);
+        xlut[t] = lerp_idx(xx, Ws, (float)(Ws - 1) / (float)(W - 1));
+    }
+    // accumulators: M-tile m = (row 2*warp + m/2, x0 = 16*(m%2)); C fragment rows g, g+8 = pixels, cols = channels
+    float acc[4][NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        const int co = co0 + 8 * t + 2 * q;
+        const float b0 = co < Cout ? __ldg(bias + co) : 0.f, b1 = co + 1 < Cout ? __ldg(bias + co + 1) : 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; m++) { acc[m][t][0] = b0; acc[m][t][1] = b1; acc[m][t][2] = b0; acc[m][t][3] = b1; }
+    }
+    const float* ip = in + (size_t)n * Cin * Hs * Ws;
+    __syncthreads();
+
+    for (int c0 = 0; c0 < Cin; c0 += MCC) {
+        for (int i = tid; i < MCC * 9 * COT; i += CONV_THREADS) {
+            const int co = i % COT, r = i / COT;
+            const int tap = r % 9, ci = r / 9;
+            const int gco = co0 + co, gci = c0 + ci;
+            const float v = (gco < Cout && gci < Cin) ? __ldg(w + ((size_t)gco * Cin + gci) * 9 + tap) : 0.f;
+            float hi, lo;
+            cyl_split_tf32(v, hi, lo);
+            w_hi[(ci * 9 + tap) * COP + co] = hi;
+            w_lo[(ci * 9 + tap) * COP + co] = lo;
+        }
+        for (int i = tid; i < MCC * (TH + 2) * (TW + 2); i += CONV_THREADS) {
+            const int xx = i % (TW + 2), r = i / (TW + 2);
+            const int yy = r % (TH + 2), ci = r / (TH + 2);
+            float v = 0.f;
+            if (c0 + ci < Cin) {
+                const float* ic = ip + (size_t)(c0 + ci) * Hs * Ws;
+                const Lerp ly = ylut[yy], lx = xlut[xx];
+                const float v00 = __ldg(ic + ly.i0 * Ws + lx.i0), v01 = __ldg(ic + ly.i0 * Ws + lx.i1);
+                const float v10 = __ldg(ic + ly.i1 * Ws + lx.i0), v11 = __ldg(ic + ly.i1 * Ws + lx.i1);
+                v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+            }
+            float hi, lo;
+            cyl_split_tf32(v, hi, lo);
+            p_hi[ci * MPLANE + yy * PW + xx] = hi;
+            p_lo[ci * MPLANE + yy * PW + xx] = lo;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+                const int tap = dy * 3 + dx;
+                float bh[NT][2], bl[NT][2];
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const int o0 = (q * 9 + tap) * COP + 8 * t + g, o1 = ((q + 4) * 9 + tap) * COP + 8 * t + g;
+                    bh[t][0] = w_hi[o0]; bh[t][1] = w_hi[o1];
+                    bl[t][0] = w_lo[o0]; bl[t][1] = w_lo[o1];
+                }
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int py = 2 * warp + (m >> 1) + dy, px = 16 * (m & 1) + g + dx;
+                    const int a0 = q * MPLANE + py * PW + px, a2 = (q + 4) * MPLANE + py * PW + px;
+                    const float ah[4] = {p_hi[a0], p_hi[a0 + 8], p_hi[a2], p_hi[a2 + 8]};
+                    const float al[4] = {p_lo[a0], p_lo[a0 + 8], p_lo[a2], p_lo[a2 + 8]};
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        cyl_mma(acc[m][t], al, bh[t][0], bh[t][1]);
+                        cyl_mma(acc[m][t], ah, bl[t][0], bl[t][1]);
+                        cyl_mma(acc[m][t], ah, bh[t][0], bh[t][1]);
+                    }
+                }
+            }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int y = ty0 + 2 * warp + (m >> 1);
+        if (y >= H) continue;
+#pragma unroll
+        for (int t = 0; t < NT; t++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int co = co0 + 8 * t + 2 * q + (i & 1);
+                const int x = tx0 + 16 * (m & 1) + g + 8 * (i >> 1);
+                if (co < Cout && x < W) out[(((size_t)n * Cout + co) * H + y) * W + x] = fmaxf(acc[m][t][i], 0.f);
+            }
+    }
+}
+
 // ---- LayerNorm over the flattened encoder output (observableNetFC, embedding_cylinder.py:62-67) --------
 __global__ void cyl_ln_kernel(const float* __restrict__ z, const float* __restrict__ lw, const float* __restrict__ lb,
                               float* __restrict__ g, int N, int E, float eps) {
@@ -380,6 +517,18 @@ int launch_tiled(const float* in, const float* w, const float* b, float* out, in
     return TRPX_OK;
 }
 
+template <int NT>
+int launch_up_mma(const float* in, const float* w, const float* b, float* out, int N, int Cin, int Hs, int Ws, int Cout,
+                  cudaStream_t st) {
+    const int H = 2 * Hs, W = 2 * Ws;
+    const size_t smem = sizeof(float) * (2 * (size_t)MCC * MPLANE + 2 * (size_t)MCC * 9 * (NT * 8 + 8));
+    TRPX_CUDA(cudaFuncSetAttribute(conv3x3_up_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(((H + TH - 1) / TH) * ((W + TW - 1) / TW), (Cout + NT * 8 - 1) / (NT * 8), N);
+    conv3x3_up_mma_kernel<NT><<<grid, CONV_THREADS, smem, st>>>(in, w, b, out, Cin, Hs, Ws, Cout);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
 template <bool UP>
 int launch_naive(const float* in, const float* w, const float* b, float* out, int N, int Cin, int Hs, int Ws, int Cout,
                  int stride, int relu, cudaStream_t st) {
@@ -461,6 +610,13 @@ int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w, int n, void* stre
     return TRPX_OK;
 }
 
+int trpx_cyl_set_conv_mode(trpx_cyl_t h, int mode) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    TRPX_REQUIRE(mode == 0 || mode == 1, "conv mode must be 0 (3xTF32 tensor-core) or 1 (FP32 SIMT)");
+    h->conv_mode = mode;
+    return TRPX_OK;
+}
+
 int trpx_cyl_set_chunk(trpx_cyl_t h, int frames) {
     TRPX_REQUIRE(valid(h), "invalid handle");
     TRPX_REQUIRE(frames >= 1 && frames <= 65535, "chunk must be in [1, 65535]");
@@ -532,9 +688,15 @@ int trpx_cyl_recover(trpx_cyl_t h, const float* g, float* x, int N, int apply_ma
         float* p4 = p3 + a3 * chunk;
         // g.view(-1, 4, 4, 8) -> up x2 -> conv(4->128) -> relu        (embedding_cylinder.py:71-73)
         if ((rc = launch_naive<true>(g + (size_t)n0 * h->E, B + h->off[T_DEC + 0], B + h->off[T_DEC + 1], p1, nn, c4, 4, 8, 128, 1, 1, st))) return rc;
-        if ((rc = launch_tiled<8, true>(p1, B + h->off[T_DEC + 2], B + h->off[T_DEC + 3], p2, nn, 128, 8, 16, 64, relu, st))) return rc;
-        if ((rc = launch_tiled<8, true>(p2, B + h->off[T_DEC + 4], B + h->off[T_DEC + 5], p3, nn, 64, 16, 32, 32, relu, st))) return rc;
-        if ((rc = launch_tiled<8, true>(p3, B + h->off[T_DEC + 6], B + h->off[T_DEC + 7], p4, nn, 32, 32, 64, 16, relu, st))) return rc;
+        if (h->conv_mode == 1) {       // FP32 SIMT direct convolution (default)
+            if ((rc = launch_tiled<8, true>(p1, B + h->off[T_DEC + 2], B + h->off[T_DEC + 3], p2, nn, 128, 8, 16, 64, relu, st))) return rc;
+            if ((rc = launch_tiled<8, true>(p2, B + h->off[T_DEC + 4], B + h->off[T_DEC + 5], p3, nn, 64, 16, 32, 32, relu, st))) return rc;
+            if ((rc = launch_tiled<8, true>(p3, B + h->off[T_DEC + 6], B + h->off[T_DEC + 7], p4, nn, 32, 32, 64, 16, relu, st))) return rc;
+        } else {                       // 3xTF32 tensor-core implicit GEMM (opt-in: measured equal speed, 8x the error)
+            if ((rc = launch_up_mma<8>(p1, B + h->off[T_DEC + 2], B + h->off[T_DEC + 3], p2, nn, 128, 8, 16, 64, st))) return rc;
+            if ((rc = launch_up_mma<4>(p2, B + h->off[T_DEC + 4], B + h->off[T_DEC + 5], p3, nn, 64, 16, 32, 32, st))) return rc;
+            if ((rc = launch_up_mma<2>(p3, B + h->off[T_DEC + 6], B + h->off[T_DEC + 7], p4, nn, 32, 32, 64, 16, st))) return rc;
+        }
         if ((rc = launch_tiled<2, false>(p4, B + h->off[T_DEC + 8], B + h->off[T_DEC + 9], x + (size_t)n0 * 3 * HW, nn, 16, 64, 128, 3, fin, st))) return rc;
     }
     return TRPX_OK;

@@ -29,6 +29,7 @@ SIGNATURES = {
     "trpx_version": (c_int, []),
     "trpx_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int)]),
     "trpx_probe_fp32_fma": (c_int, [c_int, POINTER(c_float)]),
+    "trpx_probe_tf32_mma": (c_int, [c_int, POINTER(c_float)]),
     "trpx_gpt2_create": (c_int, [POINTER(Gpt2Config), c_int, POINTER(c_void_p)]),
     "trpx_gpt2_destroy": (c_int, [c_void_p]),
     "trpx_gpt2_num_weight_tensors": (c_int, [c_void_p]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "trpx_cyl_destroy": (c_int, [c_void_p]),
     "trpx_cyl_load_weights": (c_int, [c_void_p, PP, c_int, c_void_p]),
     "trpx_cyl_set_chunk": (c_int, [c_void_p, c_int]),
+    "trpx_cyl_set_conv_mode": (c_int, [c_void_p, c_int]),
     "trpx_cyl_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "trpx_cyl_recover": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trpx_cyl_koopman": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -72,6 +72,10 @@ class CylinderEmbedding(EmbeddingModel):
             N.check(lib.trpx_cyl_create(self.config.n_embd, self.config.layer_norm_epsilon, idx, ctypes.byref(h)))
             entry = (h, N.WeightTracker())
             self._handles[idx] = entry
+            if getattr(self, "_conv_mode", None) is not None:
+                N.check(lib.trpx_cyl_set_conv_mode(h, self._conv_mode))
+            if getattr(self, "_chunk", None) is not None:
+                N.check(lib.trpx_cyl_set_chunk(h, self._chunk))
         h, tracker = entry
         ws = self._weight_list()
         if tracker.changed(ws):
@@ -83,6 +87,12 @@ class CylinderEmbedding(EmbeddingModel):
             N.check(lib.trpx_cyl_load_weights(h, N.ptr_array(tensors), len(tensors), N.stream_ptr(device)))
             self._keepalive = tensors
         return h
+
+    def set_conv_mode(self, mode: int):
+        """1 = FP32 SIMT direct decoder convs (default), 0 = 3xTF32 tensor-core implicit GEMM (opt-in)."""
+        self._conv_mode = mode
+        for h, _ in self._handles.values():
+            N.check(N.lib().trpx_cyl_set_conv_mode(h, mode))
 
     def set_chunk(self, frames: int):
         self._chunk = frames

@@ -420,7 +420,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
                                               float* outT, int lane) {
     constexpr int P = 8 / G;
     constexpr int NS = NCTX / P;                      // slots per lane
-    constexpr int BS = NS >= 64 ? 4 : (NS < 8 ? NS : 8);   // rows in flight per lane
+    constexpr int BS = NS >= 64 ? 4 : (NS < 8 ? NS : 8);   // rows in flight per lane (16 measured no faster: spills)
     const int part = lane % P, gh = lane / P, hh = gh & 3, g = gh >> 2;
     float q[8];
     {

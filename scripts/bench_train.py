@@ -19,7 +19,7 @@ from tests.util import torch_sd  # noqa: E402
 def main():
     from trphysx_b200.config import LorenzConfig
     from trphysx_b200.embedding import LorenzEmbeddingTrainer
-    from trphysx_b200.optim import FusedClipAdam
+    from trphysx_b200.optim import FusedClipAdam, FusedKoopmanStep
     from trphysx_b200.parallel import average_flat_grad
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -43,6 +43,11 @@ def main():
         opt.step()
         opt.zero_grad()
         return loss
+
+    fused = FusedKoopmanStep(head, opt, world)
+    if os.environ.get("TRPX_TRAIN_FUSED", "1") == "1":
+        def step():                      # noqa: F811  (no autograd graph: 3 native calls per step)
+            return fused(states)[0]
 
     for _ in range(5):
         step()

@@ -161,3 +161,30 @@ def test_train_step_config3_vs_oracle(dev):
     assert abs(float(loss) - float(l_ref)) <= 2e-5 * abs(float(l_ref))
     assert abs(float(loss_rec) - float(lr_ref)) <= 2e-5 * abs(float(lr_ref))
     assert O.rel_l2(flat.cpu(), g_ref) < TOL
+
+
+def test_fused_koopman_step_equals_autograd_step(dev):
+    """FusedKoopmanStep (no autograd graph) gives the same parameters as head(states); backward(); opt.step()."""
+    from trphysx_b200.config import PhysConfig
+    from trphysx_b200.embedding import LorenzEmbeddingTrainer
+    from trphysx_b200.optim import FusedClipAdam, FusedKoopmanStep
+    cfg_ns = synth.make_config("lorenz")
+    states = torch.from_numpy(synth.lorenz_trajectories(64, 7, seed=9)).to(dev)
+    outs = []
+    for fused in (False, True):
+        head = LorenzEmbeddingTrainer(PhysConfig(**vars(cfg_ns)))
+        head.embedding_model.load_state_dict(torch_sd(synth.lorenz_embedding_weights(cfg_ns, 21)))
+        head.to(dev)
+        opt = FusedClipAdam(head.parameters(), lr=1e-3, weight_decay=1e-8, max_norm=0.1)
+        stepper = FusedKoopmanStep(head, opt)
+        for _ in range(3):
+            if fused:
+                loss = stepper(states)[0]
+            else:
+                loss, _ = head(states)
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+        outs.append((float(loss), torch.cat([p.detach().reshape(-1) for p in head.parameters()]).clone()))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[0][0])
+    assert torch.equal(outs[0][1], outs[1][1])

@@ -198,3 +198,38 @@ def test_full_size_properties(dev):
     nc = m.generate(x0[:4096], max_length=65, use_cache=False)[0]
     step = m.generate(nc[:, 10:11].contiguous(), max_length=2, use_cache=False)[0]
     assert torch.equal(step[:, 1], nc[:, 11])
+
+
+def test_forward_attentions_and_train_head(dev):
+    """The reference's own unit tests (test/transformer_gpt2_tests.py:33-54): output shapes, attention tuple,
+    softmax rows summing to one; plus attention values and PhysformerTrain.evaluate against the oracle."""
+    from trphysx_b200.transformer import PhysformerTrain
+    cfg = synth.make_config("lorenz", n_ctx=16, n_layer=2, n_head=2, initializer_range=0.1)
+    w_np = synth.gpt2_weights(cfg, 17, stress=True, stress_sigma=0.2)
+    m = make_gpt2(cfg, 17, True, dev)
+    m.load_state_dict(torch_sd(w_np))
+    m.to(dev)
+    B, T = 5, 11
+    x = torch.from_numpy(synth.normal_embeds((B, T, 32), 3))
+    out = m(x.to(dev), use_cache=False, output_attentions=True)
+    assert out[0].shape == (B, T, 32)
+    assert isinstance(out[1], tuple) and len(out[1]) == cfg.n_layer
+    hid_ref, _, att_ref = O.gpt2_forward(O.to_torch(w_np), cfg, x, use_cache=False, output_attentions=True)
+    assert O.rel_l2(out[0].cpu(), hid_ref) < TOL
+    for l in range(cfg.n_layer):
+        assert out[1][l].shape == (B, cfg.n_head, T, T)
+        assert float((1.0 - out[1][l].sum(-1)).abs().mean()) < 1e-6
+        assert float(out[1][l].triu(1).abs().max()) == 0.0                 # causal mask
+        assert O.rel_l2(out[1][l].cpu(), att_ref[l]) < TOL
+    both = m(x.to(dev), use_cache=True, output_attentions=True)
+    assert len(both) == 3 and both[1][0].shape == (2, B, cfg.n_head, T, 16)
+    head = PhysformerTrain(m.config, m)             # re-applies _init_weights like the reference
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    labels = torch.from_numpy(synth.normal_embeds((B, 20, 32), 4))
+    err, pred, lab = head.evaluate(x[:, :1].to(dev), labels.to(dev))[:3]
+    ref, _ = O.gpt2_generate(sd, cfg, x[:, :1], 20, use_cache=False)
+    assert pred.shape == (B, 20, 32) and O.rel_l2(pred.cpu(), ref) < TOL
+    assert abs(float(err) - float(torch.nn.functional.mse_loss(ref, labels))) < 1e-5 * float(err)
+    with torch.no_grad():
+        loss = head(x.to(dev), x.to(dev), use_cache=False)[0]
+    assert abs(float(loss) - float(torch.nn.functional.mse_loss(O.gpt2_forward(sd, cfg, x, use_cache=False)[0], x))) < 1e-5

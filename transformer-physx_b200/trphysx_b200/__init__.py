@@ -13,3 +13,6 @@ from .config import AutoPhysConfig, PhysConfig  # noqa: F401
 from .embedding import AutoEmbeddingModel  # noqa: F401
 from .transformer import AutoPhysTransformer, PhysformerGPT2, PhysformerTrain  # noqa: F401
 from .parallel import shard_bounds, ShardedRollout, average_flat_grad  # noqa: F401
+from ._native import bump_weight_epoch as invalidate_weights  # noqa: F401,E402
+"""`invalidate_weights()`: call after modifying parameters through `.data` (or any other way torch's version
+counters cannot see); optimizer steps, load_state_dict, .to() and attribute assignment are detected automatically."""

@@ -62,3 +62,39 @@ class FusedClipAdam:
         for p, sz in zip(self.params, self.sizes):
             p.grad = self.grad[off:off + sz].view(p.shape)
             off += sz
+
+
+class FusedKoopmanStep:
+    """One Koopman-embedding training step with minimal host work: the fused forward+backward writes the flat
+    gradient straight into the optimizer's buffer, then (data parallel) ONE all-reduce, then clip + Adam.
+    Equivalent to the step body of trphysx/embedding/training/enn_trainer.py:93-102
+    (`loss = model(states); loss.backward(); clip_grad_norm_(0.1); optimizer.step(); zero_grad()`), but without
+    building an autograd graph: 3 native calls, ~8 kernel launches."""
+
+    def __init__(self, head, optimizer: FusedClipAdam, world_size: int = 1):
+        self.head, self.opt, self.world = head, optimizer, world_size
+        dev = optimizer.flat.device
+        self.loss2 = torch.zeros(2, device=dev, dtype=torch.float32)
+
+    @torch.no_grad()
+    def __call__(self, states: torch.Tensor):
+        """states [B, T, 3] on the model's device.  Returns the device tensor [loss, loss_reconstruct]."""
+        m = self.head.embedding_model
+        states = N.require_cuda_f32(states, "states")
+        dev = states.device
+        h = m._handle(dev)
+        N.check(N.lib().trpx_mlpemb_train_fwd_bwd(
+            h, states.data_ptr(), states.size(0), states.size(1), self.head.W_RECON, self.head.W_DYN,
+            self.head.W_REG, 1.0, self.loss2.data_ptr(), self.opt.grad.data_ptr(), N.stream_ptr(dev)))
+        if self.world > 1:
+            from .parallel import average_flat_grad
+            average_flat_grad(self.opt.grad, self.world)
+        self.opt.step_count += 1
+        o = self.opt
+        N.check(N.lib().trpx_clip_adam(o.flat.data_ptr(), o.grad.data_ptr(), o.m.data_ptr(), o.v.data_ptr(),
+                                       o.flat.numel(), o.step_count, o.lr, o.betas[0], o.betas[1], o.eps,
+                                       o.weight_decay, o.max_norm, o.norm.data_ptr(),
+                                       dev.index if dev.index is not None else torch.cuda.current_device(),
+                                       N.stream_ptr(dev)))
+        N.bump_weight_epoch()
+        return self.loss2

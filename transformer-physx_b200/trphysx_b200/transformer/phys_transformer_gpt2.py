@@ -71,6 +71,8 @@ class PhysformerBase(nn.Module):
         self.config = config
 
     def _init_weights(self, module):
+        # `.data` writes do not bump torch's version counters, so tell the packed-weight caches explicitly
+        N.bump_weight_epoch()
         if isinstance(module, (nn.Linear, nn.Embedding, Conv1D)):
             module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
             if isinstance(module, (nn.Linear, Conv1D)) and module.bias is not None:

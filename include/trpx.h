@@ -160,9 +160,10 @@ int trpx_cyl_destroy(trpx_cyl_t h);
 int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w_dev, int n_tensors, void* stream);
 /* Frames per encoder/decoder pass (default 64): intermediates of one pass stay L2-resident. */
 int trpx_cyl_set_chunk(trpx_cyl_t h, int frames);
-/* Decoder conv path of the three heavy upsample+conv layers: 1 = FP32 SIMT direct convolution (default),
- * 0 = 3xTF32 tensor-core implicit GEMM on mma.sync (opt-in; measured at the same speed with ~8x the rounding
- * error, profiles/README.md). */
+/* Decoder conv path of the three heavy upsample+conv layers: 2 = pipelined 3xTF32 tensor-core path (default):
+ * one upsample/pad/TF32-split pass into an L2-resident scratch, then a cp.async double-buffered mma.sync
+ * implicit GEMM with per-chunk FP32 accumulation; 1 = FP32 SIMT direct convolution; 0 = 3xTF32 MMA with
+ * in-kernel patch build (kept for A/B: same speed as 1, larger rounding error).  See profiles/README.md. */
 int trpx_cyl_set_conv_mode(trpx_cyl_t h, int mode);
 /* CylinderEmbedding.embed (:138-154): x[N,3,64,128], visc[N] -> g[N,128] */
 int trpx_cyl_embed(trpx_cyl_t h, const float* x_dev, const float* visc_dev, float* g_dev, int N, void* stream);

@@ -26,14 +26,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", default="1,6,64,512")
     ap.add_argument("--horizon", type=int, default=400)
-    ap.add_argument("--chunk", type=int, default=64)
+    ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--cpu", action="store_true", help="also time the oracle port on the host (B=4, short horizon)")
-    ap.add_argument("--conv-mode", type=int, default=1)
+    ap.add_argument("--conv-mode", type=int, default=2)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     cfg = synth.make_config("cylinder")
     emb = make_cylinder(cfg, 2030, dev)
-    emb.set_chunk(args.chunk)
+    if args.chunk:
+        emb.set_chunk(args.chunk)
     emb.set_conv_mode(args.conv_mode)
     tr = make_gpt2(cfg, 2031, False, dev)
     S = args.horizon

@@ -28,7 +28,14 @@ struct trpx_cyl {
     float* ws = nullptr;                 // activation workspace for one chunk of frames
     size_t ws_bytes = 0;
     int chunk = 64;                      // frames per decoder/encoder pass (intermediates stay in L2)
-    int conv_mode = 1;                   // 1 = FP32 SIMT direct conv (default), 0 = 3xTF32 mma.sync implicit GEMM (opt-in)
+    int conv_mode = 2;                   // 2 = pipelined 3xTF32 (upsample/split pass + cp.async double-buffered MMA kernel;
+                                         // default), 1 = FP32 SIMT direct conv, 0 = 3xTF32 MMA with in-kernel patch build
+    int final_mma = 0;                   // route the last 16->3 conv through the pipeline as well (slower, kept for A/B)
+    bool chunk_user = false;
+    float* wimg = nullptr;               // pre-split weight images of the three heavy decoder layers (mode 2)
+    size_t wimg_off[4] = {0, 0, 0, 0};
+    float* U = nullptr;                  // upsampled / padded / split layer input for one chunk (mode 2)
+    size_t U_bytes = 0;
 };
 
 namespace {
@@ -406,6 +413,245 @@ __global__ void __launch_bounds__(CONV_THREADS) conv3x3_up_mma_kernel(const floa
     }
 }
 
+// ---- pipelined tensor-core decoder layer (conv mode 2) -----------------------------------------------------
+// Stage A (cyl_upsplit_kernel): bilinear x2 upsample + replicate pad + TF32 hi/lo split of a whole layer input,
+//   written ONCE to an L2-resident scratch U[plane][n][ci][H+2][W+4]  (plane 0 = hi, 1 = lo).
+// Stage B (conv3x3_pipe_mma_kernel): 3xTF32 implicit GEMM whose patch / weight tiles are plain sub-blocks of U
+//   and of a pre-arranged weight image, fetched with 16-byte cp.async (LDGSTS) into a DOUBLE-BUFFERED shared
+//   memory stage: no arithmetic and no exposed latency in the load phase.  Each 8-channel chunk is accumulated in
+//   a zeroed temporary (27 MMAs) and added to the FP32 master accumulator with a rounded FADD, which removes the
+//   truncation bias of long tensor-core accumulation chains (rel-L2 6e-6 -> ~1e-6).
+template <bool UP>
+__global__ void cyl_upsplit_kernel(const float* __restrict__ in, float* __restrict__ U, int NC, int Hs, int Ws,
+                                   size_t plane_stride) {
+    // one thread = 4 consecutive padded columns of one padded row: row interpolation set up once, 128-bit stores
+    const int H = UP ? 2 * Hs : Hs, W = UP ? 2 * Ws : Ws, HP = H + 2, WP = W + 4, WQ = WP >> 2;
+    const float sh = UP ? (float)(Hs - 1) / (float)(H - 1) : 0.f, sw = UP ? (float)(Ws - 1) / (float)(W - 1) : 0.f;
+    const size_t total = (size_t)NC * HP * WQ;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xq = (int)(i % WQ);
+        const size_t row = i / WQ;                       // nc * HP + yp
+        const int yp = (int)(row % HP);
+        const size_t nc = row / HP;
+        const int y = min(max(yp - 1, 0), H - 1);
+        Lerp ly;
+        if (UP) ly = lerp_idx(y, Hs, sh);
+        else { ly.i0 = y; ly.i1 = y; ly.l0 = 1.f; ly.l1 = 0.f; }
+        const float* r0 = in + nc * Hs * Ws + ly.i0 * Ws;
+        const float* r1 = in + nc * Hs * Ws + ly.i1 * Ws;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int x = min(max(4 * xq + j - 1, 0), W - 1);
+            float v;
+            if (UP) {
+                const Lerp lx = lerp_idx(x, Ws, sw);
+                v = ly.l0 * (lx.l0 * __ldg(r0 + lx.i0) + lx.l1 * __ldg(r0 + lx.i1)) +
+                    ly.l1 * (lx.l0 * __ldg(r1 + lx.i0) + lx.l1 * __ldg(r1 + lx.i1));
+            } else {
+                v = __ldg(r0 + x);
+            }
+            cyl_split_tf32(v, hi[j], lo[j]);
+        }
+        float* dst = U + row * WP + 4 * xq;
+        *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(dst + plane_stride) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// weight image for the pipelined kernel: [pass][chunk][plane][ci 8][tap 9][COP], COP = NT*8 + 8 (zero padded)
+__global__ void cyl_wimage_kernel(const float* __restrict__ w, float* __restrict__ img, int Cin, int Cout, int COT) {
+    const int COP = COT + 8, nchunk = Cin / MCC, npass = (Cout + COT - 1) / COT;
+    const int total = npass * nchunk * 2 * MCC * 9 * COP;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int r = i;
+        const int co = r % COP; r /= COP;
+        const int tap = r % 9; r /= 9;
+        const int ci = r % MCC; r /= MCC;
+        const int plane = r % 2; r /= 2;
+        const int chunk = r % nchunk; const int pass = r / nchunk;
+        const int gco = pass * COT + co, gci = chunk * MCC + ci;
+        float v = 0.f;
+        if (co < COT && gco < Cout) v = w[((size_t)gco * Cin + gci) * 9 + tap];
+        float hi, lo;
+        cyl_split_tf32(v, hi, lo);
+        img[i] = plane ? lo : hi;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NT>
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_pipe_mma_kernel(const float* __restrict__ U,
+                                                                           size_t plane_stride,
+                                                                           const float* __restrict__ wimg,
+                                                                           const float* __restrict__ bias,
+                                                                           float* __restrict__ out, int Cin, int H,
+                                                                           int W, int Cout, ConvEpilogue ep) {
+    constexpr int COT = NT * 8, COP = COT + 8;
+    constexpr int PATCH = MCC * MPLANE;                 // floats per plane per stage
+    constexpr int WSZ = MCC * 9 * COP;
+    constexpr int STAGE = 2 * PATCH + 2 * WSZ;          // hi patch | lo patch | hi weights | lo weights
+    extern __shared__ __align__(16) float smc[];
+    const int HP = H + 2, WP = W + 4;
+    const int tiles_x = W / TW;
+    const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW;
+    const int pass = blockIdx.y, co0 = pass * COT;
+    const int n = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int nchunk = Cin / MCC;
+
+    auto issue = [&](int chunk, int buf) {
+        float* st = smc + buf * STAGE;
+        // patch rows: MCC channels x (TH+2) rows x 2 planes, 9 x 16 B per row
+        for (int i = tid; i < 2 * MCC * (TH + 2) * 9; i += CONV_THREADS) {
+            const int j = i % 9;
+            int r = i / 9;
+            const int row = r % (TH + 2); r /= (TH + 2);
+            const int ci = r % MCC, plane = r / MCC;
+            const float* src = U + plane * plane_stride +
+                               (((size_t)n * Cin + chunk * MCC + ci) * HP + ty0 + row) * WP + tx0 + 4 * j;
+            cp_async16(st + plane * PATCH + ci * MPLANE + row * PW + 4 * j, src);
+        }
+        const float* wsrc = wimg + ((size_t)pass * nchunk + chunk) * 2 * WSZ;
+        for (int i = tid; i < 2 * WSZ / 4; i += CONV_THREADS) cp_async16(st + 2 * PATCH + 4 * i, wsrc + 4 * i);
+        cp_async_commit();
+    };
+
+    float acc[4][NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        const int co = co0 + 8 * t + 2 * q;
+        const float b0 = co < Cout ? __ldg(bias + co) : 0.f, b1 = co + 1 < Cout ? __ldg(bias + co + 1) : 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; m++) { acc[m][t][0] = b0; acc[m][t][1] = b1; acc[m][t][2] = b0; acc[m][t][3] = b1; }
+    }
+    issue(0, 0);
+    for (int c = 0; c < nchunk; c++) {
+        if (c + 1 < nchunk) {
+            issue(c + 1, (c + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* st = smc + (c & 1) * STAGE;
+        const float* p_hi = st;
+        const float* p_lo = st + PATCH;
+        const float* w_hi = st + 2 * PATCH;
+        const float* w_lo = w_hi + WSZ;
+        float tmp[4][NT][4];
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+            for (int t = 0; t < NT; t++) tmp[m][t][0] = tmp[m][t][1] = tmp[m][t][2] = tmp[m][t][3] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+                const int tap = dy * 3 + dx;
+                float bh[NT][2], bl[NT][2];
+#pragma unroll
+                for (int t = 0; t < NT; t++) {
+                    const int o0 = (q * 9 + tap) * COP + 8 * t + g, o1 = ((q + 4) * 9 + tap) * COP + 8 * t + g;
+                    bh[t][0] = w_hi[o0]; bh[t][1] = w_hi[o1];
+                    bl[t][0] = w_lo[o0]; bl[t][1] = w_lo[o1];
+                }
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int py = 2 * warp + (m >> 1) + dy, px = 16 * (m & 1) + g + dx;
+                    const int a0 = q * MPLANE + py * PW + px, a2 = (q + 4) * MPLANE + py * PW + px;
+                    const float ah[4] = {p_hi[a0], p_hi[a0 + 8], p_hi[a2], p_hi[a2 + 8]};
+                    const float al[4] = {p_lo[a0], p_lo[a0 + 8], p_lo[a2], p_lo[a2 + 8]};
+#pragma unroll
+                    for (int t = 0; t < NT; t++) {
+                        cyl_mma(tmp[m][t], al, bh[t][0], bh[t][1]);
+                        cyl_mma(tmp[m][t], ah, bl[t][0], bl[t][1]);
+                        cyl_mma(tmp[m][t], ah, bh[t][0], bh[t][1]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+            for (int t = 0; t < NT; t++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[m][t][i] += tmp[m][t][i];
+        __syncthreads();                               // stage (c & 1) may be refilled by the next issue
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int y = ty0 + 2 * warp + (m >> 1);
+#pragma unroll
+        for (int t = 0; t < NT; t++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int co = co0 + 8 * t + 2 * q + (i & 1);
+                const int x = tx0 + 16 * (m & 1) + g + 8 * (i >> 1);
+                if (co < Cout) {
+                    float v = acc[m][t][i];
+                    if (ep.relu) v = fmaxf(v, 0.f);
+                    if (ep.unnorm) v = __ldg(ep.sd + co) * v + __ldg(ep.mu + co);
+                    if (ep.mask && ep.mask[y * W + x]) v = 0.f;
+                    out[(((size_t)n * Cout + co) * H + y) * W + x] = v;
+                }
+            }
+    }
+}
+
+// ---- first decoder layer: g.view(4,4,8) -> bilinear x2 -> conv(4 -> 128) -> ReLU, one CTA per frame ---------
+// (1.2 MFLOP per frame: the generic direct kernel spent more time here than in a 75 MFLOP layer.)  Thread =
+// (pixel, half of the output channels): its 4x3x3 input window sits in 36 registers, weights are warp-uniform
+// LDS.128 broadcasts, stores are coalesced over pixels.
+__global__ void __launch_bounds__(256) cyl_dec0_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out) {
+    constexpr int CI = 4, CO = 128, HS = 4, WS = 8, H0 = 8, W0 = 16;
+    __shared__ float src[CI * HS * WS];
+    __shared__ __align__(16) float wsm0[CO * CI * 9];
+    __shared__ float up[CI][H0 + 2][W0 + 2];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < CI * HS * WS; i += 256) src[i] = g[(size_t)n * CI * HS * WS + i];
+    for (int i = tid; i < CO * CI * 9; i += 256) wsm0[i] = __ldg(w + i);
+    __syncthreads();
+    const float sh = (float)(HS - 1) / (float)(H0 - 1), sw = (float)(WS - 1) / (float)(W0 - 1);
+    for (int i = tid; i < CI * (H0 + 2) * (W0 + 2); i += 256) {
+        const int xx = i % (W0 + 2), yy = (i / (W0 + 2)) % (H0 + 2), ci = i / ((W0 + 2) * (H0 + 2));
+        const Lerp ly = lerp_idx(min(max(yy - 1, 0), H0 - 1), HS, sh), lx = lerp_idx(min(max(xx - 1, 0), W0 - 1), WS, sw);
+        const float* ic = src + ci * HS * WS;
+        up[ci][yy][xx] = ly.l0 * (lx.l0 * ic[ly.i0 * WS + lx.i0] + lx.l1 * ic[ly.i0 * WS + lx.i1]) +
+                         ly.l1 * (lx.l0 * ic[ly.i1 * WS + lx.i0] + lx.l1 * ic[ly.i1 * WS + lx.i1]);
+    }
+    __syncthreads();
+    const int px = tid & 127, half = tid >> 7;
+    const int y = px >> 4, x = px & 15;
+    float win[36];
+#pragma unroll
+    for (int ci = 0; ci < CI; ci++)
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) win[ci * 9 + dy * 3 + dx] = up[ci][y + dy][x + dx];
+    for (int co = half * 64; co < half * 64 + 64; co++) {
+        const float4* wr = reinterpret_cast<const float4*>(wsm0 + co * 36);
+        float acc = __ldg(bias + co);
+#pragma unroll
+        for (int q4 = 0; q4 < 9; q4++) {
+            const float4 wv = wr[q4];
+            acc = fmaf(win[4 * q4 + 0], wv.x, acc);
+            acc = fmaf(win[4 * q4 + 1], wv.y, acc);
+            acc = fmaf(win[4 * q4 + 2], wv.z, acc);
+            acc = fmaf(win[4 * q4 + 3], wv.w, acc);
+        }
+        out[((size_t)n * CO + co) * (H0 * W0) + px] = fmaxf(acc, 0.f);
+    }
+}
+
 // ---- LayerNorm over the flattened encoder output (observableNetFC, embedding_cylinder.py:62-67) --------
 __global__ void cyl_ln_kernel(const float* __restrict__ z, const float* __restrict__ lw, const float* __restrict__ lb,
                               float* __restrict__ g, int N, int E, float eps) {
@@ -529,6 +775,23 @@ int launch_up_mma(const float* in, const float* w, const float* b, float* out, i
     return TRPX_OK;
 }
 
+template <int NT, bool UP>
+int launch_pipe(trpx_cyl_t h, const float* in, const float* wimg, const float* b, float* out, int N, int Cin, int Hs,
+                int Ws, int Cout, ConvEpilogue ep, cudaStream_t st) {
+    const int H = UP ? 2 * Hs : Hs, W = UP ? 2 * Ws : Ws;
+    const size_t plane = (size_t)N * Cin * (H + 2) * (W + 4);
+    const int blocks = (int)std::min<size_t>((plane / 4 + 255) / 256, (size_t)148 * 16);
+    cyl_upsplit_kernel<UP><<<blocks, 256, 0, st>>>(in, h->U, N * Cin, Hs, Ws, plane);
+    TRPX_CUDA(cudaGetLastError());
+    constexpr int COT = NT * 8, COP = COT + 8;
+    const size_t smem = sizeof(float) * 2 * (2 * (size_t)MCC * MPLANE + 2 * (size_t)MCC * 9 * COP);
+    TRPX_CUDA(cudaFuncSetAttribute(conv3x3_pipe_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((H / TH) * (W / TW), (Cout + COT - 1) / COT, N);
+    conv3x3_pipe_mma_kernel<NT><<<grid, CONV_THREADS, smem, st>>>(h->U, plane, wimg, b, out, Cin, H, W, Cout, ep);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
 template <bool UP>
 int launch_naive(const float* in, const float* w, const float* b, float* out, int N, int Cin, int Hs, int Ws, int Cout,
                  int stride, int relu, cudaStream_t st) {
@@ -591,6 +854,8 @@ int trpx_cyl_destroy(trpx_cyl_t h) {
     cudaFree(h->blob);
     cudaFree(h->mask);
     cudaFree(h->ws);
+    cudaFree(h->wimg);
+    cudaFree(h->U);
     h->magic = 0;
     delete h;
     return TRPX_OK;
@@ -606,13 +871,27 @@ int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w, int n, void* stre
     for (int i = 0; i < 36; i++)
         TRPX_CUDA(cudaMemcpyAsync(h->blob + h->off[i], w[i], sz[i] * sizeof(float), cudaMemcpyDeviceToDevice,
                                   (cudaStream_t)stream));
+    {   // weight images of the three heavy decoder layers for the pipelined tensor-core path
+        const int cin[4] = {128, 64, 32, 16}, cout[4] = {64, 32, 16, 3}, cot[4] = {32, 32, 16, 8};
+        size_t tot = 0;
+        for (int i = 0; i < 4; i++) {
+            h->wimg_off[i] = tot;
+            tot += (size_t)((cout[i] + cot[i] - 1) / cot[i]) * (cin[i] / MCC) * 2 * MCC * 9 * (cot[i] + 8);
+        }
+        if (h->wimg == nullptr) TRPX_CUDA(cudaMalloc(&h->wimg, tot * sizeof(float)));
+        for (int i = 0; i < 4; i++) {
+            cyl_wimage_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(h->blob + h->off[T_DEC + 2 + 2 * i],
+                                                                  h->wimg + h->wimg_off[i], cin[i], cout[i], cot[i]);
+            TRPX_CUDA(cudaGetLastError());
+        }
+    }
     h->loaded = true;
     return TRPX_OK;
 }
 
 int trpx_cyl_set_conv_mode(trpx_cyl_t h, int mode) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(mode == 0 || mode == 1, "conv mode must be 0 (3xTF32 tensor-core) or 1 (FP32 SIMT)");
+    TRPX_REQUIRE(mode >= 0 && mode <= 2, "conv mode must be 0 (3xTF32 in-kernel build), 1 (FP32 SIMT) or 2 (pipelined 3xTF32)");
     h->conv_mode = mode;
     return TRPX_OK;
 }
@@ -621,6 +900,7 @@ int trpx_cyl_set_chunk(trpx_cyl_t h, int frames) {
     TRPX_REQUIRE(valid(h), "invalid handle");
     TRPX_REQUIRE(frames >= 1 && frames <= 65535, "chunk must be in [1, 65535]");
     h->chunk = frames;
+    h->chunk_user = true;
     return TRPX_OK;
 }
 
@@ -674,9 +954,20 @@ int trpx_cyl_recover(trpx_cyl_t h, const float* g, float* x, int N, int apply_ma
     const int c4 = h->E / 32;
     const size_t a1 = 128 * 8 * 16, a2 = 64 * 16 * 32, a3 = 32 * 32 * 64, a4 = 16 * 64 * 128;
     const size_t per = a1 + a2 + a3 + a4;
-    const int chunk = std::min(N, h->chunk);
+    // frames per pass: 64 keeps one pass's intermediates L2-resident for the SIMT path; the pipelined path is
+    // tensor-bound and prefers fewer, larger launches (measured: 256)
+    const int chunk = std::min(N, (h->conv_mode == 2 && !h->chunk_user) ? 256 : h->chunk);
     int rc = ensure_ws(h, per * chunk * sizeof(float));
     if (rc) return rc;
+    if (h->conv_mode == 2) {
+        // largest layer input after upsampling: [32][66][132] floats per frame, two planes
+        const size_t need = (size_t)chunk * 2 * 32 * 66 * 132 * sizeof(float);
+        if (need > h->U_bytes) {
+            if (h->U) { TRPX_CUDA(cudaDeviceSynchronize()); TRPX_CUDA(cudaFree(h->U)); h->U = nullptr; h->U_bytes = 0; }
+            TRPX_CUDA(cudaMalloc(&h->U, need));
+            h->U_bytes = need;
+        }
+    }
     const float* B = h->blob;
     ConvEpilogue relu{1, 0, nullptr, nullptr, nullptr};
     ConvEpilogue fin{0, 1, B + h->off[T_MU], B + h->off[T_STD], apply_mask ? h->mask : nullptr};
@@ -686,6 +977,21 @@ int trpx_cyl_recover(trpx_cyl_t h, const float* g, float* x, int N, int apply_ma
         float* p2 = p1 + a1 * chunk;
         float* p3 = p2 + a2 * chunk;
         float* p4 = p3 + a3 * chunk;
+        if (h->conv_mode == 2) {       // pipelined 3xTF32 tensor-core path, all five layers
+            cyl_dec0_kernel<<<nn, 256, 0, st>>>(g + (size_t)n0 * h->E, B + h->off[T_DEC + 0], B + h->off[T_DEC + 1], p1);
+            TRPX_CUDA(cudaGetLastError());
+            if ((rc = launch_pipe<4, true>(h, p1, h->wimg + h->wimg_off[0], B + h->off[T_DEC + 3], p2, nn, 128, 8, 16, 64, relu, st))) return rc;
+            if ((rc = launch_pipe<4, true>(h, p2, h->wimg + h->wimg_off[1], B + h->off[T_DEC + 5], p3, nn, 64, 16, 32, 32, relu, st))) return rc;
+            if ((rc = launch_pipe<2, true>(h, p3, h->wimg + h->wimg_off[2], B + h->off[T_DEC + 7], p4, nn, 32, 32, 64, 16, relu, st))) return rc;
+            // final 16 -> 3 conv: the FP32 SIMT tile kernel is faster than the pipeline here (172 vs 216 us per 256
+            // frames: with 3 output channels the layer is bound by moving its input, not by math)
+            if (h->final_mma) {
+                if ((rc = launch_pipe<1, false>(h, p4, h->wimg + h->wimg_off[3], B + h->off[T_DEC + 9], x + (size_t)n0 * 3 * HW, nn, 16, 64, 128, 3, fin, st))) return rc;
+            } else {
+                if ((rc = launch_tiled<2, false>(p4, B + h->off[T_DEC + 8], B + h->off[T_DEC + 9], x + (size_t)n0 * 3 * HW, nn, 16, 64, 128, 3, fin, st))) return rc;
+            }
+            continue;
+        }
         // g.view(-1, 4, 4, 8) -> up x2 -> conv(4->128) -> relu        (embedding_cylinder.py:71-73)
         if ((rc = launch_naive<true>(g + (size_t)n0 * h->E, B + h->off[T_DEC + 0], B + h->off[T_DEC + 1], p1, nn, c4, 4, 8, 128, 1, 1, st))) return rc;
         if (h->conv_mode == 1) {       // FP32 SIMT direct convolution (default)

@@ -89,7 +89,8 @@ class CylinderEmbedding(EmbeddingModel):
         return h
 
     def set_conv_mode(self, mode: int):
-        """1 = FP32 SIMT direct decoder convs (default), 0 = 3xTF32 tensor-core implicit GEMM (opt-in)."""
+        """2 = pipelined 3xTF32 tensor-core decoder (default), 1 = FP32 SIMT direct convs, 0 = 3xTF32 MMA with
+        in-kernel patch build."""
         self._conv_mode = mode
         for h, _ in self._handles.values():
             N.check(N.lib().trpx_cyl_set_conv_mode(h, mode))

@@ -1130,7 +1130,7 @@ __device__ __forceinline__ void frag_bias(float (&c)[4], const float* b, int t, 
 }
 
 template <int NCTX, bool CACHE>
-__global__ void __launch_bounds__(384, 1) rollout_e32v4_kernel(RolloutParams p) {
+__global__ void __launch_bounds__(CACHE ? 256 : 384, 1) rollout_e32v4_kernel(RolloutParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(8) uint64_t bar;
     const Gpt2Layout& L = p.lay;
@@ -1744,7 +1744,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         const bool want = h->tune_variant == 6 ||
                           (h->tune_variant == 0 && !use_cache && (long long)ngroups >= (long long)sms * 8);
         if (e32_shape && aligned && fits && want) {
-            const int max_w = scr_w ? (int)std::min<size_t>(12, ((size_t)h->smem_optin - 1024 - wbytes) / scr_w) : 12;
+            const int max_w = scr_w ? (int)std::min<size_t>(8, ((size_t)h->smem_optin - 1024 - wbytes) / scr_w) : 12;
             const int grid = std::min(sms, ngroups);
             const int wantw = h->tune_warps > 0 ? h->tune_warps : 8;
             const int Wc = std::max(1, std::min(std::min(wantw, max_w), (ngroups + grid - 1) / grid));

@@ -84,10 +84,13 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0_dev, long long x0_stride,
 /* Tuning knobs of the rollout kernel (0 = automatic).  `variant`: 0 auto, 1 generic kernel only, 2 E=32 warp
  * kernel, 3 = 2 without TMA weight staging, 4 = 2 without the L2 window prefetch (for A/B measurements),
  * 5 = E=32 kernel with 2-D lane tiling (16 trajectories per warp), 6 = E=32 tensor-core kernel (3xTF32
- * mma.sync; chosen automatically for large batches without the KV window). */
+ * mma.sync; chosen automatically for large batches without the KV window), 7 = thread-block-cluster kernel
+ * (8 CTAs per trajectory group, column-split GEMVs, DSMEM exchange, TMA weight ring; chosen automatically for
+ * shapes other than E=32 when the batch fits about three waves of clusters). */
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp,
                                  int max_ctas);
-/* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 E=32 warp kernel, 5 E=32 2-D tiling, 6 E=32 tensor-core), grid, block,
+/* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 E=32 warp kernel, 5 E=32 2-D tiling, 6 E=32 tensor-core,
+ * 7 cluster kernel), grid, block,
  * dynamic smem bytes, trajectories per warp/CTA group. */
 int trpx_gpt2_last_launch(trpx_gpt2_t h, int* variant, int* grid, int* block, int* smem, int* group);
 

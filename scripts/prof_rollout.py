@@ -16,7 +16,13 @@ ap.add_argument("--nocache", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-cfg, emb, tr = build_modules(a.kind, dev)
+if a.kind == "cylinder":
+    from oracle import synth
+    from tests.util import make_gpt2
+    cfg = synth.make_config("cylinder")
+    tr = make_gpt2(cfg, 2025, False, dev)
+else:
+    cfg, emb, tr = build_modules(a.kind, dev)
 tr.set_rollout_tuning(variant=a.variant, warps_per_cta=a.warps, traj_per_warp=a.group)
 g0 = torch.nn.functional.layer_norm(torch.randn(a.batch, 1, cfg.n_embd, device=dev), (cfg.n_embd,))
 for _ in range(a.reps):

@@ -46,7 +46,7 @@ def test_forward_matches_reference(golden_dir, dev, name):
         assert torch.equal(only_hidden, hid)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 5, 6])   # auto, generic, E=32 w/o TMA staging, E=32 v2, E=32 3xTF32 MMA
+@pytest.mark.parametrize("variant", [0, 1, 3, 5, 6, 7])   # auto, generic, E=32 w/o TMA staging, E=32 v2, E=32 3xTF32 MMA, cluster
 @pytest.mark.parametrize("name", list(GPT2_CASES))
 def test_generate_matches_reference(golden_dir, dev, name, variant):
     """Free rollouts vs the reference's recorded outputs, over the horizon on which the reference's own float32
@@ -75,7 +75,12 @@ def test_generate_matches_reference(golden_dir, dev, name, variant):
     assert O.rel_l2(out0[0][:, :n0].cpu(), gold["gen_nocache"][:, :n0]) < TOL, f"stable horizon {n0}"
     info = m.last_launch()
     e32 = cfg.n_embd == 32 and cfg.n_head == 4 and cfg.n_ctx <= 64
-    assert info["variant"] == (1 if (variant == 1 or not e32) else (variant if variant in (5, 6) else 2))
+    if variant in (1, 7):
+        assert info["variant"] == variant
+    elif not e32:
+        assert info["variant"] == (7 if variant == 0 else 1)   # auto, small batch: the thread-block-cluster kernel
+    else:
+        assert info["variant"] == (variant if variant in (5, 6) else 2)
 
 
 @pytest.mark.parametrize("name", ["rossler_stress", "cylinder_stress", "lorenz_stress"])
@@ -113,6 +118,33 @@ def test_rollout_vs_oracle_all_group_sizes(dev, kind, B, S, G):
         assert O.rel_l2(got[:, :n], ref[:, :n]) < TOL, f"stable horizon {n}"
         per_step = (got - ref).flatten(2).norm(dim=2)[:, :n].max(0).values / ref.flatten(2).norm(dim=2)[:, :n].max(0).values
         assert float(per_step.max()) < 3 * TOL
+        if uc and n == S + 1:
+            _, ref_pres = O.gpt2_generate(O.to_torch(w_np), cfg, x0, S + 1, use_cache=True)
+            for l in range(cfg.n_layer):
+                assert O.rel_l2(out[1][l].cpu(), ref_pres[l]) < TOL
+
+
+@pytest.mark.parametrize("G", [0, 1, 2, 4, 8, 16])
+@pytest.mark.parametrize("B,S", [(1, 40), (7, 40), (70, 24), (300, 10)])
+def test_rollout_cluster_kernel_vs_oracle(dev, B, S, G):
+    """Thread-block-cluster kernel (variant 7) on the Cylinder-size transformer: ragged groups, several waves of
+    clusters (B=70 at G=1), both cache modes, presents, strided output."""
+    cfg = synth.make_config("cylinder")
+    w_np = synth.gpt2_weights(cfg, 905, stress=True, stress_sigma=0.08)
+    m = make_gpt2(cfg, 905, True, dev)
+    m.load_state_dict(torch_sd(w_np))
+    m.to(dev)
+    m.set_rollout_tuning(variant=7, traj_per_warp=G)
+    x0 = torch.from_numpy(synth.normal_embeds((B, 1, cfg.n_embd), 78))
+    for uc in (True, False):
+        n, ref = stable_prefix(cfg, w_np, x0, S + 1, uc)
+        out = m.generate(x0.to(dev), max_length=S + 1, use_cache=uc)
+        info = m.last_launch()
+        assert info["variant"] == 7 and info["grid"] % 8 == 0 and (G == 0 or info["group"] == G)
+        got = out[0].cpu()
+        print(f"cluster G={info['group']} B={B} use_cache={uc}: rel-L2 {O.rel_l2(got[:, :n], ref[:, :n]):.2e} over {n}")
+        assert n >= 5
+        assert O.rel_l2(got[:, :n], ref[:, :n]) < TOL, f"stable horizon {n}"
         if uc and n == S + 1:
             _, ref_pres = O.gpt2_generate(O.to_torch(w_np), cfg, x0, S + 1, use_cache=True)
             for l in range(cfg.n_layer):

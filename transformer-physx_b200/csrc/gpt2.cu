@@ -23,6 +23,7 @@ struct trpx_gpt2 {
     int smem_optin = 0;
     float* blob = nullptr;
     float* blob_sw = nullptr;
+    float* img_cl = nullptr;       // per-(image, rank) weight slices for the cluster kernel
     float* pe = nullptr;
     bool loaded = false;
     float* kv = nullptr;          // rollout workspace (KV windows of the groups in flight)
@@ -1349,6 +1350,394 @@ __global__ void swizzle_weights_kernel(const float* __restrict__ blob, float* __
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 (cluster): small batches of a wide model (Cylinder: E = 128, 6 layers, 4.6 MB of weights).
+// The generic kernel makes every CTA stream ALL weights from L2 every step (123 us per step, latency bound).
+// Here a thread-block CLUSTER of 8 CTAs owns one group of G trajectories:
+//   * CTA rank r owns the output-column slice [r*E/8, (r+1)*E/8) of every GEMV (q, k, v slices alike), so each
+//     CTA reads only 1/8 of the weights;
+//   * its per-(layer, rank) weight slice is a contiguous image, fetched by TMA bulk copies into a two-slot
+//     shared-memory ring (attention half / MLP half of a layer) half a layer AHEAD of use, completion on mbarriers;
+//   * after each GEMV the slice results are broadcast to all 8 CTAs with DSMEM stores (mapa + st.shared::cluster)
+//     and a cluster barrier (release/acquire) publishes them; every CTA keeps an identical copy of the residual;
+//   * (trajectory, head) attention pairs are dealt round-robin to the CTAs; the KV window ring stays in global
+//     memory (L2 resident: a few hundred KB).
+// ------------------------------------------------------------------------------------------------
+constexpr int CLS = 8;                 // CTAs per cluster
+constexpr int CL_THREADS = 256;
+
+struct ClusterLayout {                 // per-(image, rank) float offsets; image i < n_layer: layer i, image n_layer: head
+    int E, sl;                         // sl = E / CLS
+    // attention half
+    int ln1w, ln1b, bqkv, bproj, wqkv, wproj, att_size;
+    // MLP half
+    int ln2w, ln2b, bfc, bpr, wfc, wpr, mlp_size;
+    __host__ __device__ static ClusterLayout make(int E) {
+        ClusterLayout L;
+        L.E = E; L.sl = E / CLS;
+        int o = 0;
+        L.ln1w = o; o += E; L.ln1b = o; o += E; L.bqkv = o; o += 3 * L.sl; L.bproj = o; o += L.sl;
+        o = (o + 3) & ~3;
+        L.wqkv = o; o += E * 3 * L.sl; L.wproj = o; o += E * L.sl;
+        L.att_size = (o + 3) & ~3;
+        o = 0;
+        L.ln2w = o; o += E; L.ln2b = o; o += E; L.bfc = o; o += 4 * L.sl; L.bpr = o; o += L.sl;
+        o = (o + 3) & ~3;
+        L.wfc = o; o += E * 4 * L.sl; L.wpr = o; o += 4 * E * L.sl;
+        L.mlp_size = (o + 3) & ~3;
+        return L;
+    }
+    // the head image reuses the attention-half format: ln1w/ln1b = ln_f, bproj = bf slice, wproj = Wf^T slice
+};
+
+__device__ __forceinline__ int cluster_rank() {
+    int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v at the same shared-memory offset in every CTA of the cluster (including this one)
+__device__ __forceinline__ void dsmem_bcast(float* local, float v) {
+    const uint32_t l = smem_u32(local);
+#pragma unroll
+    for (int r = 0; r < CLS; r++) {
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(l), "r"(r));
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+    }
+}
+
+// slice GEMV with the weight slice in shared memory: y[g][n] = bias[n] + sum_k aT[k*G+g] * W[k*N + n], n < N (N % 4 == 0).
+// A thread owns (k-part, column quad, trajectory): 4 accumulators, one LDS.128 of weights + one LDS of the activation
+// per 4 FFMAs, so all NT threads are busy even for the 16-column slices.  K parts are reduced with shuffles when
+// several live in one warp, then across warps through `part` ([NT/32][N][G]) by 4 lanes per output.
+template <int G, int NT, class Epi>
+__device__ __forceinline__ void cta_gemv_smem(const float* W, const float* bias, int K, int N, const float* aT,
+                                              float* part, Epi epi) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int NQ = N >> 2;
+    int QL = 1;
+    while (QL < NQ) QL <<= 1;
+    const int UL = QL * G;                           // lanes per k-slice (power of two)
+    int unit, kp, kparts, np, pw;
+    if (UL >= 32) {
+        const int wpk = UL >> 5;                     // warps per k-slice
+        unit = (warp % wpk) * 32 + lane;
+        kp = warp / wpk;
+        kparts = NW / wpk;
+        np = kparts;
+        pw = kp;
+    } else {
+        const int nsub = 32 / UL;
+        unit = lane & (UL - 1);
+        kp = warp * nsub + lane / UL;
+        kparts = NW * nsub;
+        np = NW;
+        pw = warp;
+    }
+    const int g = unit % G, nq = unit / G;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (nq < NQ && kp < kparts) {
+        const float* wp = W + nq * 4;
+        const float* ap = aT + g;
+#pragma unroll 4
+        for (int k = kp; k < K; k += kparts) {
+            const float4 w = *reinterpret_cast<const float4*>(wp + k * N);
+            const float a = ap[k * G];
+            a0 = fmaf(a, w.x, a0);
+            a1 = fmaf(a, w.y, a1);
+            a2 = fmaf(a, w.z, a2);
+            a3 = fmaf(a, w.w, a3);
+        }
+    }
+    for (int o = UL; o < 32; o <<= 1) {
+        a0 += __shfl_xor_sync(FULL, a0, o);
+        a1 += __shfl_xor_sync(FULL, a1, o);
+        a2 += __shfl_xor_sync(FULL, a2, o);
+        a3 += __shfl_xor_sync(FULL, a3, o);
+    }
+    if (nq < NQ && pw < np && (UL >= 32 || lane < UL)) {
+        float* pp = part + ((size_t)pw * N + nq * 4) * G + g;
+        pp[0] = a0;
+        pp[G] = a1;
+        pp[2 * G] = a2;
+        pp[3 * G] = a3;
+    }
+    __syncthreads();
+    const int NG = N * G;
+    const int sub = tid & 3;
+    for (int base = 0; base < NG; base += NT / 4) {   // uniform trip count: the shuffles need whole warps
+        const int o = base + (tid >> 2);
+        float s2 = 0.f;
+        if (o < NG)
+            for (int j = sub; j < np; j += 4) s2 += part[(size_t)j * NG + o];
+        s2 += __shfl_xor_sync(FULL, s2, 1);
+        s2 += __shfl_xor_sync(FULL, s2, 2);
+        if (o < NG && sub == 0) {
+            const int nn = o / G;
+            epi(nn, o - nn * G, s2 + bias[nn]);
+        }
+    }
+}
+
+// attention of one (trajectory, head) pair by one warp, head size 32, window <= 16 slots: every global load of the
+// pass is issued up front (two L2 round trips in total), softmax in registers.  q: smem, stride qs; out[d]: lane d.
+__device__ __forceinline__ float cluster_attn_hd32(const float* q, int qs, const float* Kr, const float* Vr, int E, int L) {
+    const int lane = threadIdx.x & 31;
+    const int slot = lane >> 1, half = lane & 1;
+    float s = 0.f;
+    if (slot < L) {
+        const float4* kp4 = reinterpret_cast<const float4*>(Kr + (size_t)slot * E + half * 16);
+        const float4 k0 = __ldcg(kp4), k1 = __ldcg(kp4 + 1), k2 = __ldcg(kp4 + 2), k3 = __ldcg(kp4 + 3);
+        const float* qq = q + half * 16 * qs;
+        s = fmaf(qq[0], k0.x, s); s = fmaf(qq[qs], k0.y, s); s = fmaf(qq[2 * qs], k0.z, s); s = fmaf(qq[3 * qs], k0.w, s);
+        s = fmaf(qq[4 * qs], k1.x, s); s = fmaf(qq[5 * qs], k1.y, s); s = fmaf(qq[6 * qs], k1.z, s); s = fmaf(qq[7 * qs], k1.w, s);
+        s = fmaf(qq[8 * qs], k2.x, s); s = fmaf(qq[9 * qs], k2.y, s); s = fmaf(qq[10 * qs], k2.z, s); s = fmaf(qq[11 * qs], k2.w, s);
+        s = fmaf(qq[12 * qs], k3.x, s); s = fmaf(qq[13 * qs], k3.y, s); s = fmaf(qq[14 * qs], k3.z, s); s = fmaf(qq[15 * qs], k3.w, s);
+    }
+    // V rows: lane = channel; issue all loads before the softmax math
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = (j < L) ? __ldcg(Vr + (size_t)j * E + lane) : 0.f;
+    s += __shfl_xor_sync(FULL, s, 1);
+    s = (slot < L) ? s / sqrtf(32.0f) : -INFINITY;
+    const float m = warp_max(s);
+    float pexp = (slot < L && half == 0) ? expf(s - m) : 0.f;
+    const float sum = warp_sum(pexp);
+    pexp = pexp / sum;
+    float o = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) o = fmaf(__shfl_sync(FULL, pexp, 2 * j), v[j], o);
+    return o;
+}
+
+struct ClusterParams {
+    const float* img;          // [n_layer + 1][CLS][att_size + mlp_size]
+    const float* pe;
+    const float* x0;
+    long long x0_stride;
+    float* out;
+    long long out_stride;
+    float* kv;
+    float* presents;
+    int B, S, use_cache;
+    float eps;
+    Gpt2Layout lay;
+    ClusterLayout cl;
+};
+
+template <int G, int NT>
+__global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t full[2];
+    const Gpt2Layout& L = p.lay;
+    const ClusterLayout& CLy = p.cl;
+    const int E = L.E, H = L.n_head, hd = L.hd, C = L.n_ctx, NL = L.n_layer, sl = CLy.sl;
+    const int tid = threadIdx.x, warp = tid >> 5, nw = NT >> 5;
+    const int rank = cluster_rank();
+    const int grp = blockIdx.x / CLS;
+    const int b0 = grp * G;
+    float* slotA = sm;                               // attention-half weight slice
+    float* slotM = slotA + CLy.att_size;             // MLP-half weight slice
+    float* xT = slotM + CLy.mlp_size;                // [E][G] residual (identical in every CTA)
+    float* aT = xT + E * G;                          // [E][G] LN output / attention output
+    float* qT = aT + E * G;                          // [3E][G]
+    float* hT = qT + 3 * E * G;                      // [4E][G]
+    float* dT = hT + 4 * E * G;                      // [E][G] broadcast GEMV slice results (residual delta / token)
+    float* part = dT + E * G;                        // [NT/32][4*sl][G]
+    float* pbuf = part + (NT / 32) * 4 * sl * G;     // [nw][C]
+    const size_t img_stride = (size_t)CLy.att_size + CLy.mlp_size;
+    const size_t kv_per_g = (size_t)NL * 2 * C * E;
+    float* kvb = p.kv + (size_t)grp * G * kv_per_g;
+
+    auto img_of = [&](int image) { return p.img + ((size_t)image * CLS + rank) * img_stride; };
+    auto fetch = [&](int slot, int image) {           // thread 0 only
+        float* dst = slot ? slotM : slotA;
+        const float* src = img_of(image) + (slot ? CLy.att_size : 0);
+        const uint32_t bytes = (uint32_t)(slot ? CLy.mlp_size : CLy.att_size) * 4u;
+        mbar_expect_tx(&full[slot], bytes);
+        const uint32_t CH = 32768u;
+        for (uint32_t off = 0; off < bytes; off += CH)
+            bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src) + off, min(CH, bytes - off),
+                     &full[slot]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        fetch(0, 0);
+        fetch(1, 0);
+    }
+    uint32_t useA = 0, useM = 0;                      // completed uses of each slot -> wait parity
+
+    for (int i = tid; i < E * G; i += NT) {
+        const int c = i / G, g = i - c * G;
+        const int b = b0 + g;
+        xT[i] = ((b < p.B) ? p.x0[(size_t)b * p.x0_stride + c] : 0.f) + __ldg(p.pe + c);
+    }
+    cluster_sync_all();                               // all CTAs of the cluster are resident before any DSMEM store
+
+    auto ln_T = [&](const float* lw, const float* lb) {
+        const int lane = tid & 31;
+        for (int g = warp; g < G; g += nw) {
+            float s1 = 0.f;
+            for (int c = lane; c < E; c += 32) s1 += xT[c * G + g];
+            const float mean = warp_sum(s1) / (float)E;
+            float v = 0.f;
+            for (int c = lane; c < E; c += 32) {
+                const float d = xT[c * G + g] - mean;
+                v = fmaf(d, d, v);
+            }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + p.eps);
+            for (int c = lane; c < E; c += 32) aT[c * G + g] = (xT[c * G + g] - mean) * rstd * lw[c] + lb[c];
+        }
+    };
+
+    for (int s = 0; s < p.S; s++) {
+        const int Lk = p.use_cache ? min(s + 1, C) : 1;
+        const int slot = p.use_cache ? (s % C) : 0;
+        for (int l = 0; l <= NL; l++) {
+            // ================= attention half (or the final head when l == NL) =================
+            mbar_wait(&full[0], useA & 1);
+            useA++;
+            ln_T(slotA + CLy.ln1w, slotA + CLy.ln1b);
+            __syncthreads();
+            if (l == NL) {
+                // x' = LN_f(x) Wf^T + bf : this CTA's slice -> every CTA, and to the output
+                const int pnext = p.use_cache ? min(s + 1, C - 1) : 0;
+                cta_gemv_smem<G, NT>(slotA + CLy.wproj, slotA + CLy.bproj, E, sl, aT, part, [&](int n, int g, float v) {
+                    const int col = rank * sl + n, b = b0 + g;
+                    if (b < p.B) p.out[(size_t)b * p.out_stride + (size_t)s * E + col] = v;
+                    dsmem_bcast(dT + col * G + g, v + __ldg(p.pe + pnext * E + col));
+                });
+                cluster_sync_all();
+                for (int i = tid; i < E * G; i += NT) xT[i] = dT[i];
+                __syncthreads();
+                if (tid == 0 && s + 1 < p.S) fetch(0, 0);
+                break;
+            }
+            cta_gemv_smem<G, NT>(slotA + CLy.wqkv, slotA + CLy.bqkv, E, 3 * sl, aT, part, [&](int n, int g, float v) {
+                const int which = n / sl, col = rank * sl + (n - which * sl);       // q | k | v slices
+                dsmem_bcast(qT + (which * E + col) * G + g, v);
+                if (which) kvb[(size_t)g * kv_per_g + ((size_t)(l * 2 + which - 1) * C + slot) * E + col] = v;
+            });
+            cluster_sync_all();
+            // (trajectory, head) pairs dealt round-robin: pair p -> CTA p % CLS, warp (p / CLS) % nw
+            for (int pair = rank + CLS * warp; pair < G * H; pair += CLS * nw) {
+                const int g = pair / H, hh = pair - g * H;
+                const float* Kr = kvb + (size_t)g * kv_per_g + (size_t)(l * 2 + 0) * C * E + hh * hd;
+                const float* Vr = kvb + (size_t)g * kv_per_g + (size_t)(l * 2 + 1) * C * E + hh * hd;
+                if (hd == 32 && C <= 16) {
+                    const float o = cluster_attn_hd32(qT + (hh * hd) * G + g, G, Kr, Vr, E, Lk);
+                    dsmem_bcast(aT + (hh * hd + (tid & 31)) * G + g, o);
+                } else {
+                    float* ob = hT + (hh * hd) * G + g;     // local staging, then broadcast
+                    warp_attention(qT + (hh * hd) * G + g, G, Kr, Vr, E, hd, Lk, pbuf + warp * C, ob, G, nullptr);
+                    for (int d = (tid & 31); d < hd; d += 32) dsmem_bcast(aT + (hh * hd + d) * G + g, ob[d * G]);
+                }
+            }
+            cluster_sync_all();
+            cta_gemv_smem<G, NT>(slotA + CLy.wproj, slotA + CLy.bproj, E, sl, aT, part,
+                             [&](int n, int g, float v) { dsmem_bcast(dT + (rank * sl + n) * G + g, v); });
+            cluster_sync_all();                       // also: every thread of this CTA is done with slot A
+            if (tid == 0) fetch(0, (l + 1 <= NL) ? l + 1 : 0);
+            for (int i = tid; i < E * G; i += NT) xT[i] += dT[i];
+            __syncthreads();
+            // ================= MLP half =================
+            mbar_wait(&full[1], useM & 1);
+            useM++;
+            ln_T(slotM + CLy.ln2w, slotM + CLy.ln2b);
+            __syncthreads();
+            cta_gemv_smem<G, NT>(slotM + CLy.wfc, slotM + CLy.bfc, E, 4 * sl, aT, part, [&](int n, int g, float v) {
+                dsmem_bcast(hT + (rank * 4 * sl + n) * G + g, gelu_new(v));
+            });
+            cluster_sync_all();
+            cta_gemv_smem<G, NT>(slotM + CLy.wpr, slotM + CLy.bpr, 4 * E, sl, hT, part,
+                             [&](int n, int g, float v) { dsmem_bcast(dT + (rank * sl + n) * G + g, v); });
+            cluster_sync_all();
+            if (tid == 0 && !(s + 1 == p.S && l + 1 == NL)) fetch(1, (l + 1 < NL) ? l + 1 : 0);
+            for (int i = tid; i < E * G; i += NT) xT[i] += dT[i];
+            __syncthreads();
+        }
+    }
+    if (p.presents != nullptr && p.use_cache && rank == 0) {
+        const int Tk = min(p.S, C);
+        const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+        for (int g = 0; g < G; g++) {
+            const int b = b0 + g;
+            if (b >= p.B) break;
+            for (int i = tid; i < NL * 2 * Tk * E; i += NT) {
+                const int e = i % E;
+                int r = i / E;
+                const int t = r % Tk;
+                r /= Tk;
+                const int which = r & 1, l = r >> 1;
+                const int sl2 = (p.S - Tk + t) % C;
+                const int hh = e / hd, d = e - hh * hd;
+                p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                    kvb[(size_t)g * kv_per_g + ((size_t)(l * 2 + which) * C + sl2) * E + e];
+            }
+        }
+    }
+    cluster_sync_all();                               // no CTA may exit while peers can still store into its smem
+}
+
+// per-(image, rank) weight images for the cluster kernel
+__global__ void cluster_image_kernel(const float* __restrict__ blob, float* __restrict__ img, Gpt2Layout L, ClusterLayout C) {
+    const int E = L.E, sl = C.sl;
+    const size_t stride = (size_t)C.att_size + C.mlp_size;
+    const size_t total = (size_t)(L.n_layer + 1) * CLS * stride;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(i % stride);
+        const int rank = (int)((i / stride) % CLS), image = (int)(i / (stride * CLS));
+        float v = 0.f;
+        if (image < L.n_layer) {
+            const float* w = blob + (size_t)image * L.layer_stride;
+            if (o < C.att_size) {
+                if (o < C.ln1b) v = w[L.ln1w + o];
+                else if (o < C.bqkv) v = w[L.ln1b + o - C.ln1b];
+                else if (o < C.bproj) { const int n = o - C.bqkv, wh = n / sl; v = w[L.bqkv + wh * E + rank * sl + n % sl]; }
+                else if (o < C.bproj + sl) v = w[L.bproj + rank * sl + o - C.bproj];
+                else if (o >= C.wqkv && o < C.wproj) {
+                    const int r = o - C.wqkv, k = r / (3 * sl), n = r % (3 * sl), wh = n / sl;
+                    v = w[L.wqkv + k * 3 * E + wh * E + rank * sl + n % sl];
+                } else if (o >= C.wproj && o < C.wproj + E * sl) {
+                    const int r = o - C.wproj, k = r / sl, n = r % sl;
+                    v = w[L.wproj + k * E + rank * sl + n];
+                }
+            } else {
+                const int m = o - C.att_size;
+                if (m < C.ln2b) v = w[L.ln2w + m];
+                else if (m < C.bfc) v = w[L.ln2b + m - C.ln2b];
+                else if (m < C.bpr) v = w[L.bfc + rank * 4 * sl + m - C.bfc];
+                else if (m < C.bpr + sl) v = w[L.bpr + rank * sl + m - C.bpr];
+                else if (m >= C.wfc && m < C.wpr) {
+                    const int r = m - C.wfc, k = r / (4 * sl), n = r % (4 * sl);
+                    v = w[L.wfc + k * 4 * E + rank * 4 * sl + n];
+                } else if (m >= C.wpr && m < C.wpr + 4 * E * sl) {
+                    const int r = m - C.wpr, k = r / sl, n = r % sl;
+                    v = w[L.wpr + k * E + rank * sl + n];
+                }
+            }
+        } else if (o < C.att_size) {                   // head image in the attention-half format
+            if (o < C.ln1b) v = blob[L.lnfw + o];
+            else if (o < C.bqkv) v = blob[L.lnfb + o - C.ln1b];
+            else if (o >= C.bproj && o < C.bproj + sl) v = blob[L.bf + rank * sl + o - C.bproj];
+            else if (o >= C.wproj && o < C.wproj + E * sl) {
+                const int r = o - C.wproj, k = r / sl, n = r % sl;
+                v = blob[L.wf + k * E + rank * sl + n];
+            }
+        }
+        img[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: teacher-forced forward of T tokens (optional past of Tp keys), one CTA per batch element.
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_FWD_LAYERS = 32;
@@ -1625,6 +2014,7 @@ int trpx_gpt2_destroy(trpx_gpt2_t h) {
     DeviceGuard guard(h->device);
     cudaFree(h->blob);
     cudaFree(h->blob_sw);
+    cudaFree(h->img_cl);
     cudaFree(h->pe);
     cudaFree(h->kv);
     h->magic = 0;
@@ -1664,6 +2054,13 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
         swizzle_weights_kernel<<<64, 256, 0, st>>>(h->blob, h->blob_sw, L);
         TRPX_CUDA(cudaGetLastError());
     }
+    if (E % (CLS * 4) == 0) {
+        const ClusterLayout cl = ClusterLayout::make(E);
+        const size_t n = (size_t)(L.n_layer + 1) * CLS * ((size_t)cl.att_size + cl.mlp_size);
+        if (h->img_cl == nullptr) TRPX_CUDA(cudaMalloc(&h->img_cl, n * sizeof(float)));
+        cluster_image_kernel<<<256, 256, 0, st>>>(h->blob, h->img_cl, L, cl);
+        TRPX_CUDA(cudaGetLastError());
+    }
     if (pe_dev != nullptr) {
         TRPX_CUDA(cudaMemcpyAsync(h->pe, pe_dev, sizeof(float) * L.n_ctx * E, cudaMemcpyDeviceToDevice, st));
     } else {
@@ -1687,10 +2084,11 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 6, "variant must be 0..6");
-    TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 12, "warps_per_cta must be 0..12");
+    TRPX_REQUIRE(variant >= 0 && variant <= 7, "variant must be 0..7");
+    TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 32, "warps_per_cta must be 0..32");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
-                     traj_per_warp == 8, "traj_per_warp must be 0,1,2,4,8");
+                     traj_per_warp == 8 || (traj_per_warp == 16 && variant == 7),
+                 "traj_per_warp must be 0,1,2,4,8 (16 with variant 7)");
     h->tune_variant = variant;
     h->tune_prefetch = (variant == 4) ? 0 : 1;
     h->tune_warps = warps_per_cta;
@@ -1783,7 +2181,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             return launch_v2(p, L.n_ctx, grid, Wc * 32, smem, st);
         }
     }
-    bool use_e32 = e32_shape && h->tune_variant != 1 && wbytes + (size_t)scr_per_warp_g1 + 1024 <= (size_t)h->smem_optin;
+    bool use_e32 = e32_shape && h->tune_variant != 1 && h->tune_variant != 7 && wbytes + (size_t)scr_per_warp_g1 + 1024 <= (size_t)h->smem_optin;
     if (use_e32) {
         const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
         int G = h->tune_g;
@@ -1821,6 +2219,67 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         }
     }
 
+    // ---- cluster kernel: wide model, few trajectories ----
+    if (h->img_cl != nullptr && h->tune_variant != 1 && (!e32_shape || h->tune_variant == 7)) {
+        const ClusterLayout cl = ClusterLayout::make(L.E);
+        const int NTc = (h->tune_warps == 16) ? 512 : 256;
+        auto smem_of = [&](int G) {
+            return sizeof(float) * ((size_t)cl.att_size + cl.mlp_size + (size_t)L.E * G * (1 + 1 + 3 + 4 + 1) +
+                                    (size_t)(NTc / 32) * 4 * cl.sl * G + (size_t)(NTc / 32) * L.n_ctx);
+        };
+        auto kernel_of = [&](int G) -> void (*)(ClusterParams) {
+#define TRPX_CLK(NT_)                                                                                         \
+    (G == 16 ? rollout_cluster_kernel<16, NT_>                                                                \
+             : G == 8 ? rollout_cluster_kernel<8, NT_>                                                        \
+                      : G == 4 ? rollout_cluster_kernel<4, NT_>                                               \
+                               : G == 2 ? rollout_cluster_kernel<2, NT_> : rollout_cluster_kernel<1, NT_>)
+            return NTc == 512 ? TRPX_CLK(512) : TRPX_CLK(256);
+#undef TRPX_CLK
+        };
+        int ql = 1;
+        while (ql < cl.sl) ql <<= 1;                 // the FC slice has 4*sl columns = sl quads
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CLS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        // smallest group size whose clusters are all co-resident (one wave): a step costs about the same for
+        // any group size (it is a chain of exchanges), so waves are what to avoid
+        int G = 0, max_clusters = 0;
+        for (int g = 1; g <= 16; g <<= 1) {
+            if (h->tune_g && g != h->tune_g) continue;
+            if (smem_of(g) + 1024 > (size_t)h->smem_optin || ql * g > NTc) break;
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(CLS); q.blockDim = dim3(NTc); q.dynamicSmemBytes = smem_of(g);
+            q.attrs = attr; q.numAttrs = 1;
+            TRPX_CUDA(cudaFuncSetAttribute(kernel_of(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(g)));
+            int nc = 0;
+            TRPX_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel_of(g), &q));
+            G = g; max_clusters = nc;
+            if ((B + g - 1) / g <= nc) break;
+        }
+        const int ngroups = G ? (B + G - 1) / G : 0;
+        // measured (profiles/README.md): one wave of single-trajectory clusters runs a step in 62 us against the
+        // generic kernel's 123 us; larger groups lengthen the exchange phases and lose to it from B = 64 on
+        const bool want = G && max_clusters > 0 &&
+                          (h->tune_variant == 7 || (h->tune_variant == 0 && G == 1 && ngroups <= max_clusters));
+        if (want) {
+            int rc = ensure_kv(h, (size_t)ngroups * G * kv_per_traj);
+            if (rc) return rc;
+            ClusterParams cp{};
+            cp.img = h->img_cl; cp.pe = h->pe; cp.x0 = x0; cp.x0_stride = x0_stride; cp.out = out; cp.out_stride = out_stride;
+            cp.kv = h->kv; cp.presents = presents; cp.B = B; cp.S = S; cp.use_cache = use_cache ? 1 : 0;
+            cp.eps = h->cfg.ln_eps; cp.lay = L; cp.cl = cl;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(ngroups * CLS);
+            cfg.blockDim = dim3(NTc);
+            cfg.dynamicSmemBytes = smem_of(G);
+            cfg.stream = st;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            h->last_variant = 7; h->last_grid = ngroups * CLS; h->last_block = NTc;
+            h->last_smem = (int)smem_of(G); h->last_group = G;
+            TRPX_CUDA(cudaLaunchKernelEx(&cfg, kernel_of(G), cp));
+            return TRPX_OK;
+        }
+    }
     // ---- generic kernel ----
     int G = h->tune_g;
     if (G == 0) {

@@ -37,6 +37,12 @@ int         trpx_probe_fp32_fma(int device, float* tflops_out);
 /* Measured dense TF32 throughput of the warp-level mma.sync.m16n8k8 path (SASS HMMA.1688.F32.TF32) in TFLOP/s:
  * the denominator (divided by 3 for the error-compensated 3xTF32 product) of the tensor-core rollout kernel. */
 int         trpx_probe_tf32_mma(int device, float* tflops_out);
+/* Measured rate (GB/s) of the KV-window access pattern of the cache-mode rollout with the arithmetic removed:
+ * 4 trajectories per warp, per (step, layer) two windows of n_ctx rows of 128 B read with 256-bit loads
+ * (`rows_in_flight` per lane: 4, 8 or 16) plus two rows appended; `prefetch` adds the bulk L2 prefetch the rollout
+ * issues.  It is the practical ceiling of the HBM-bound rollout kernel for this access pattern.  Synchronous. */
+int         trpx_probe_window_stream(int device, int n_traj, int n_ctx, int n_layer, int steps, int warps_per_cta,
+                                     int rows_in_flight, int prefetch, float* gbps_out, float* ms_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Transformer decoder stack: PhysformerGPT2 (trphysx/transformer/phys_transformer_gpt2.py:120-269)
@@ -86,7 +92,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0_dev, long long x0_stride,
  * 5 = E=32 kernel with 2-D lane tiling (16 trajectories per warp), 6 = E=32 tensor-core kernel (3xTF32
  * mma.sync; chosen automatically for large batches without the KV window), 7 = thread-block-cluster kernel
  * (8 CTAs per trajectory group, column-split GEMVs, DSMEM exchange, TMA weight ring; chosen automatically for
- * shapes other than E=32 when the batch fits about three waves of clusters). */
+ * shapes other than E=32 when one trajectory per cluster fits in a single wave). */
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp,
                                  int max_ctas);
 /* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 E=32 warp kernel, 5 E=32 2-D tiling, 6 E=32 tensor-core,

@@ -46,7 +46,7 @@ def test_forward_matches_reference(golden_dir, dev, name):
         assert torch.equal(only_hidden, hid)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 5, 6, 7])   # auto, generic, E=32 w/o TMA staging, E=32 v2, E=32 3xTF32 MMA, cluster
+@pytest.mark.parametrize("variant", [0, 1, 3, 5, 6, 7, 8])   # auto, generic, E=32 w/o TMA staging, E=32 v2, E=32 3xTF32 MMA, cluster, TMA-staged window
 @pytest.mark.parametrize("name", list(GPT2_CASES))
 def test_generate_matches_reference(golden_dir, dev, name, variant):
     """Free rollouts vs the reference's recorded outputs, over the horizon on which the reference's own float32
@@ -149,6 +149,33 @@ def test_rollout_cluster_kernel_vs_oracle(dev, B, S, G):
             _, ref_pres = O.gpt2_generate(O.to_torch(w_np), cfg, x0, S + 1, use_cache=True)
             for l in range(cfg.n_layer):
                 assert O.rel_l2(out[1][l].cpu(), ref_pres[l]) < TOL
+
+
+@pytest.mark.parametrize("kind,B,S,over", [("lorenz", 19, 150, {}), ("rossler", 37, 70, {}), ("rossler", 16, 3, {}),
+                                           ("rossler", 9, 40, {"n_ctx": 16}), ("rossler", 4700, 40, {})])
+def test_rollout_staged_window_kernel(dev, kind, B, S, over):
+    """TMA-staged window kernel with the per-layer weight ring (variant 8): same arithmetic order as the LDG kernel
+    (variant 2, 4 trajectories per warp) => bit-identical states and presents; and both within the FP32 bar of the
+    oracle.  Horizons beyond n_ctx exercise the ring wrap, B=4700 several groups per warp with a ragged last round
+    (warps that only keep the weight-ring protocol going)."""
+    cfg = synth.make_config(kind, **over)
+    w_np = synth.gpt2_weights(cfg, 903, stress=True, stress_sigma=0.2)
+    m = make_gpt2(cfg, 903, True, dev)
+    m.load_state_dict(torch_sd(w_np))
+    m.to(dev)
+    x0 = torch.from_numpy(synth.normal_embeds((B, 1, cfg.n_embd), 79))
+    m.set_rollout_tuning(variant=8)
+    out8 = m.generate(x0.to(dev), max_length=S + 1, use_cache=True)
+    assert m.last_launch()["variant"] == 8 and m.last_launch()["group"] == 4
+    m.set_rollout_tuning(variant=2, traj_per_warp=4)
+    out2 = m.generate(x0.to(dev), max_length=S + 1, use_cache=True)
+    assert m.last_launch()["variant"] == 2 and m.last_launch()["group"] == 4
+    assert torch.equal(out8[0], out2[0])
+    for l in range(cfg.n_layer):
+        assert torch.equal(out8[1][l], out2[1][l])
+    if B <= 64:
+        n, ref = stable_prefix(cfg, w_np, x0, S + 1, True)
+        assert O.rel_l2(out8[0].cpu()[:, :n], ref[:, :n]) < TOL, f"stable horizon {n}"
 
 
 @pytest.mark.parametrize("variant", [5, 6])

@@ -416,7 +416,8 @@ __device__ __forceinline__ void warp_gemv(const float* scr, const float* W, int 
 //   qs   : smem [G][32] queries (row per trajectory)
 //   kvl  : ring of this warp for this layer: trajectory g at kvl + g*kv_per_g, K rows [C][32] then V rows [C][32]
 //   outT : smem transposed tile [32][G] receiving the merged-head output (input of the projection GEMV)
-template <int G, int NCTX>
+// FULLW: the window is full (L == C == NCTX, every step from n_ctx-1 on): no row clamping, no validity selects.
+template <int G, int NCTX, bool FULLW>
 __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl, size_t kv_per_g, int C, int L,
                                               float* outT, int lane) {
     constexpr int P = 8 / G;
@@ -437,12 +438,12 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
     float m = -INFINITY;
 #pragma unroll
     for (int j0 = 0; j0 < NS; j0 += BS) {
-        if (j0 * P < L) {                             // warp-uniform
+        if (FULLW || j0 * P < L) {                    // warp-uniform
             float kk[BS][8];
 #pragma unroll
             for (int jj = 0; jj < BS; jj++) {
                 const int slot = (j0 + jj) * P + part;
-                ldg256(Kp + min(slot, L - 1) * 32, kk[jj]);
+                ldg256(Kp + (FULLW ? slot : min(slot, L - 1)) * 32, kk[jj]);
             }
 #pragma unroll
             for (int jj = 0; jj < BS; jj++) {
@@ -450,7 +451,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
                 float s0 = 0.f;
 #pragma unroll
                 for (int d = 0; d < 8; d++) s0 = fmaf(q[d], kk[jj][d], s0);
-                const float s1 = slot < L ? s0 / scale : -INFINITY;
+                const float s1 = (FULLW || slot < L) ? s0 / scale : -INFINITY;
                 sc[j0 + jj] = s1;
                 m = fmaxf(m, s1);
             }
@@ -464,7 +465,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < NS; j++) {
-        const float pj = (j * P + part < L) ? expf(sc[j] - m) : 0.f;
+        const float pj = (FULLW || j * P + part < L) ? expf(sc[j] - m) : 0.f;
         sc[j] = pj;
         sum += pj;
     }
@@ -476,12 +477,12 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
     for (int d = 0; d < 8; d++) acc[d] = 0.f;
 #pragma unroll
     for (int j0 = 0; j0 < NS; j0 += BS) {
-        if (j0 * P < L) {
+        if (FULLW || j0 * P < L) {
             float vv[BS][8];
 #pragma unroll
             for (int jj = 0; jj < BS; jj++) {
                 const int slot = (j0 + jj) * P + part;
-                ldg256(Vp + min(slot, L - 1) * 32, vv[jj]);       // clamped rows carry weight 0
+                ldg256(Vp + (FULLW ? slot : min(slot, L - 1)) * 32, vv[jj]);       // clamped rows carry weight 0
             }
 #pragma unroll
             for (int jj = 0; jj < BS; jj++) {
@@ -584,7 +585,10 @@ __global__ void __launch_bounds__((CACHE && G == 4) ? 256 : 384, 1) rollout_e32_
 #pragma unroll
                     for (int g = 0; g < G; g++) scr[g * 32 + lane] = qkv[0][g];
                     __syncwarp();
-                    warp_attn_e32<G, 8 * MAXI>(scr, kvw + (size_t)(l * 2) * C * 32, kv_per_g, C, Lk, scr, lane);
+                    if (Lk == 8 * MAXI)
+                        warp_attn_e32<G, 8 * MAXI, true>(scr, kvw + (size_t)(l * 2) * C * 32, kv_per_g, C, Lk, scr, lane);
+                    else
+                        warp_attn_e32<G, 8 * MAXI, false>(scr, kvw + (size_t)(l * 2) * C * 32, kv_per_g, C, Lk, scr, lane);
                     if (p.prefetch == 2 && lane < G) {
                         // mid-layer distance: the NEXT attention's window (next layer, or layer 0 of the next step)
                         // is requested now and has the projection + MLP phase to arrive
@@ -680,6 +684,358 @@ __global__ void __launch_bounds__((CACHE && G == 4) ? 256 : 384, 1) rollout_e32_
                     const int which = lw & 1, l = lw >> 1;
                     const int sl = (p.S - Tk + t) % C;
                     p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                        kvw[(size_t)g * kv_per_g + ((size_t)lw * C + sl) * 32 + lane];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (E = 32, KV window), TMA-staged attention + per-layer weight ring.
+// Measured on rollout_e32_kernel<4,...> (profiles/README.md): the bare window stream runs at the HBM peak
+// (trpx_probe_window_stream: 6.4 TB/s with the same 8 warps x 16 rows in flight) and the dense part alone takes
+// 56 ms, yet the kernel takes their SUM (130 ms): every warp is a latency chain that holds 128 registers of
+// in-flight window rows, so only 8 warps fit and nothing hides a warp's wait.  Here the window never touches the
+// LSU or the register file:
+//   * a warp owns 4 trajectories and a 16 KB shared-memory stage [4][BR = 32 rows][32 floats];
+//   * one elected lane issues 4 TMA bulk copies (cp.async.bulk, one contiguous window slice per trajectory) that
+//     complete on the warp's own mbarrier; the key stage of the NEXT layer is issued as soon as this layer's
+//     attention is done, so it lands during projection + MLP + LN + QKV; value rows (and key rows beyond the first
+//     stage, n_ctx = 64) are bulk-prefetched into L2 at the same moment and staged when the buffer frees up;
+//   * the row of the current token is patched into the stage from registers (its global copy may be stale);
+//   * lanes read the stage with LDS.128, the two lanes of a (trajectory, head) pair in opposite half order so
+//     that a quarter-warp phase never hits a bank twice;
+//   * to make room for the stages the weights are no longer resident as a whole (203 KB): a producer warp streams
+//     one layer (50.8 KB) at a time from L2 into a two-slot ring (full/empty mbarriers, TMA bulk copies), the
+//     consumer warps run at most one layer apart; the head (ln_f, mlp_f) stays resident;
+//   * arithmetic order is the one of rollout_e32_kernel (bit-identical results).
+// ------------------------------------------------------------------------------------------------
+constexpr int E32S_G = 4;
+constexpr int E32S_MAXW = 12;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NCTX>
+__global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel(RolloutParams p) {
+    constexpr int G = E32S_G, P = 2;
+    constexpr int BR = NCTX < 32 ? NCTX : 32;         // rows per stage
+    constexpr int NS = NCTX / P;                      // scores per lane
+    constexpr int JB = BR / P;                        // rows per lane per stage
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t hbar;            // head weights
+    __shared__ __align__(8) uint64_t full[2], empty[2];
+    __shared__ __align__(8) uint64_t tbar_all[E32S_MAXW];
+    const Gpt2Layout& L = p.lay;
+    const int C = L.n_ctx, NL = L.n_layer;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = (blockDim.x >> 5) - 1;              // consumer warps; warp W is the weight producer
+    const int LS = L.layer_stride;
+    const int head_floats = L.total - L.lnfw;         // ln_f w, b, mlp_f W^T, b: consecutive at the end of the blob
+    float* gw = sm;                                   // resident head
+    float* wring = sm + ((head_floats + 3) & ~3);     // [2][LS]
+    float* scr = wring + 2 * LS + warp * (64 * G + G * BR * 32);
+    float* buf = scr + 64 * G;
+    uint64_t* tbar = &tbar_all[warp < E32S_MAXW ? warp : 0];
+
+    const int ngroups = (p.B + G - 1) / G;
+    const int iters = (ngroups + gridDim.x * W - 1) / (gridDim.x * W);    // same for every warp of the CTA
+    const int total_layers = iters * p.S * NL;
+
+    if (tid == 0) {
+        mbar_init(&hbar, 1);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], W);
+        mbar_init(&empty[1], W);
+    }
+    if (lane == 0 && warp < W) mbar_init(tbar, 1);
+    __syncthreads();
+    if (warp == W) {
+        // ---------------- producer: head once, then layer after layer into the two-slot ring ----------------
+        if (lane == 0) {
+            mbar_expect_tx(&hbar, (uint32_t)head_floats * 4u);
+            bulk_g2s(gw, p.blob + L.lnfw, (uint32_t)head_floats * 4u, &hbar);
+            const uint32_t bytes = (uint32_t)LS * 4u;
+            for (int lc = 0; lc < total_layers; lc++) {
+                const int b = lc & 1, u = lc >> 1;
+                if (u > 0) mbar_wait_backoff(&empty[b], (u - 1) & 1, 256);
+                mbar_expect_tx(&full[b], bytes);
+                const char* src = reinterpret_cast<const char*>(p.blob + (size_t)(lc % NL) * LS);
+                char* dst = reinterpret_cast<char*>(wring + b * LS);
+                const uint32_t CH = 16384u;
+                for (uint32_t off = 0; off < bytes; off += CH) bulk_g2s(dst + off, src + off, min(CH, bytes - off), &full[b]);
+            }
+        }
+        return;
+    }
+    mbar_wait(&hbar, 0);
+
+    const size_t kv_per_g = (size_t)NL * 2 * C * 32;
+    float* kvw = p.kv + (size_t)(blockIdx.x * W + warp) * G * kv_per_g;
+    const int part = lane & 1, gh = lane >> 1, hh = gh & 3, ga = gh >> 2;      // attention role of the lane
+    const float scale = 2.8284271247461903f;          // sqrt(8): attention.py:99 divides by sqrt(head size)
+    uint32_t par = 0;                                 // parity of the next completion of tbar
+    int lc = 0;                                       // layers consumed so far (ring position)
+
+    // stage rows [stg*BR, min(Lk, (stg+1)*BR)) of the key (which = 0) / value (1) windows of layer l
+    auto issue = [&](int l, int which, int stg, int Lk) {
+        if (lane == 0) {
+            const int r0 = stg * BR;
+            const uint32_t nb = (uint32_t)min(Lk - r0, BR) * 128u;
+            mbar_expect_tx(tbar, nb * G);
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                bulk_g2s(buf + g * BR * 32, kvw + (size_t)g * kv_per_g + ((size_t)(l * 2 + which) * C + r0) * 32, nb, tbar);
+        }
+    };
+    // everything of layer l's window that is not in the first key stage goes to L2 now
+    auto prefetch_rest = [&](int l, int Lk) {
+        if (p.prefetch == 1 && lane < G) {
+            const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
+            if (Lk > BR) prefetch_l2_bulk(kp + BR * 32, (uint32_t)(Lk - BR) * 128u);
+            prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+        }
+    };
+    // the 8 floats of (trajectory ga, head hh) in stage row r; the two lanes of a pair read the halves in opposite order
+    auto lds_row = [&](int r, float (&x)[8]) {
+        const float4* rp = reinterpret_cast<const float4*>(buf + (ga * BR + r) * 32 + hh * 8);
+        const float4 a = rp[part], b = rp[part ^ 1];
+        const float4 lo = part ? b : a, hi = part ? a : b;
+        x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+    };
+
+    for (int it = 0; it < iters; it++) {
+        const int grp = (it * gridDim.x + blockIdx.x) * W + warp;
+        if (grp >= ngroups) {
+            // ragged tail: keep the ring protocol going without computing
+            for (int i = 0; i < p.S * NL; i++, lc++) {
+                mbar_wait(&full[lc & 1], (lc >> 1) & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[lc & 1]);
+            }
+            continue;
+        }
+        const int b0 = grp * G;
+        float h[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int b = b0 + g;
+            h[g] = (b < p.B ? p.x0[(size_t)b * p.x0_stride + lane] : 0.f) + __ldg(p.pe + lane);
+        }
+        bool staged = false;                          // first key stage of the upcoming attention already in flight?
+        for (int s = 0; s < p.S; s++) {
+            const int Lk = min(s + 1, C);
+            const int slot = s % C;
+            for (int l = 0; l < NL; l++, lc++) {
+                if (!staged && Lk > 1) {
+                    issue(l, 0, 0, Lk);
+                    prefetch_rest(l, Lk);
+                    staged = true;
+                }
+                mbar_wait(&full[lc & 1], (lc >> 1) & 1);
+                const float* w = wring + (lc & 1) * LS;
+                // ---- LN1 + QKV ----
+                store_T<G>(scr, lane, h);
+                __syncwarp();
+                warp_ln_T<G>(scr, w + L.ln1w, w + L.ln1b, p.eps, lane);
+                __syncwarp();
+                float qkv[3][G];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int g = 0; g < G; g++) qkv[c][g] = w[L.bqkv + lane + 32 * c];
+                warp_gemv<G, 3>(scr, w + L.wqkv, 32, 96, lane, qkv);
+                // ---- append (k, v) to the ring (for the following steps) ----
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    float* kp = kvw + (size_t)g * kv_per_g + (size_t)(l * 2) * C * 32;
+                    kp[slot * 32 + lane] = qkv[1][g];
+                    kp[C * 32 + slot * 32 + lane] = qkv[2][g];
+                }
+                asm volatile("fence.proxy.async.global;" ::: "memory");   // later TMA reads of these rows
+                __syncwarp();                         // LN tile fully consumed
+#pragma unroll
+                for (int g = 0; g < G; g++) scr[g * 32 + lane] = qkv[0][g];
+                __syncwarp();
+                float q[8];
+                {
+                    const float4* qp = reinterpret_cast<const float4*>(scr + ga * 32 + hh * 8);
+                    const float4 a = qp[0], b = qp[1];
+                    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+                }
+                // ---- scores, stage by stage ----
+                float sc[NS];
+                float m = -INFINITY;
+#pragma unroll
+                for (int stg = 0; stg < NCTX / BR; stg++) {
+                    if (stg * BR < Lk) {              // warp-uniform
+                        if (Lk > 1) {
+                            if (stg > 0) {
+                                __syncwarp();
+                                issue(l, 0, stg, Lk);
+                            }
+                            mbar_wait(tbar, par);
+                            par ^= 1;
+                        }
+                        const int ps = slot - stg * BR;
+                        if (ps >= 0 && ps < BR) {
+#pragma unroll
+                            for (int g = 0; g < G; g++) buf[(g * BR + ps) * 32 + lane] = qkv[1][g];
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int jj = 0; jj < JB; jj++) {
+                            const int row = jj * P + part;
+                            float kk[8];
+                            lds_row(min(row, min(Lk - stg * BR, BR) - 1), kk);
+                            float s0 = 0.f;
+#pragma unroll
+                            for (int d = 0; d < 8; d++) s0 = fmaf(q[d], kk[d], s0);
+                            const float s1 = (stg * BR + row < Lk) ? s0 / scale : -INFINITY;
+                            sc[stg * JB + jj] = s1;
+                            m = fmaxf(m, s1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < JB; jj++) sc[stg * JB + jj] = -INFINITY;
+                    }
+                }
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < NS; j++) {
+                    const int stg = j / JB, jj = j - stg * JB;
+                    const float pj = (stg * BR + jj * P + part < Lk) ? expf(sc[j] - m) : 0.f;
+                    sc[j] = pj;
+                    sum += pj;
+                }
+                sum += __shfl_xor_sync(FULL, sum, 1);
+                const float rs = 1.0f / sum;
+                float acc[8];
+#pragma unroll
+                for (int d = 0; d < 8; d++) acc[d] = 0.f;
+#pragma unroll
+                for (int stg = 0; stg < NCTX / BR; stg++) {
+                    if (stg * BR < Lk) {
+                        __syncwarp();                 // the stage is fully consumed
+                        if (Lk > 1) {
+                            issue(l, 1, stg, Lk);
+                            mbar_wait(tbar, par);
+                            par ^= 1;
+                        }
+                        const int ps = slot - stg * BR;
+                        if (ps >= 0 && ps < BR) {
+#pragma unroll
+                            for (int g = 0; g < G; g++) buf[(g * BR + ps) * 32 + lane] = qkv[2][g];
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int jj = 0; jj < JB; jj++) {
+                            const int row = jj * P + part;
+                            float vv[8];
+                            lds_row(min(row, min(Lk - stg * BR, BR) - 1), vv);      // clamped rows carry weight 0
+                            const float pw = sc[stg * JB + jj] * rs;
+#pragma unroll
+                            for (int d = 0; d < 8; d++) acc[d] = fmaf(pw, vv[d], acc[d]);
+                        }
+                    }
+                }
+                __syncwarp();                         // stage free again: start the next attention's key stage
+                {
+                    const bool wrap = (l + 1 == NL);
+                    const int ln = wrap ? 0 : l + 1;
+                    const int Ln = wrap ? min(s + 2, C) : Lk;
+                    staged = false;
+                    if ((!wrap || s + 1 < p.S) && Ln > 1) {
+                        issue(ln, 0, 0, Ln);
+                        prefetch_rest(ln, Ln);
+                        staged = true;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < 8; d++) acc[d] += __shfl_xor_sync(FULL, acc[d], 1);
+                if (part == 0) {
+#pragma unroll
+                    for (int d = 0; d < 8; d++) scr[(hh * 8 + d) * G + ga] = acc[d];
+                }
+                __syncwarp();
+                // ---- output projection + residual ----
+                {
+                    float pr[1][G];
+#pragma unroll
+                    for (int g = 0; g < G; g++) pr[0][g] = w[L.bproj + lane];
+                    warp_gemv<G, 1>(scr, w + L.wproj, 32, 32, lane, pr);
+#pragma unroll
+                    for (int g = 0; g < G; g++) h[g] += pr[0][g];
+                }
+                // ---- LN2 + MLP ----
+                __syncwarp();
+                store_T<G>(scr, lane, h);
+                __syncwarp();
+                warp_ln_T<G>(scr, w + L.ln2w, w + L.ln2b, p.eps, lane);
+                __syncwarp();
+                float f[4][G];
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int g = 0; g < G; g++) f[c][g] = w[L.bfc + lane + 32 * c];
+                warp_gemv<G, 4>(scr, w + L.wfc, 32, 128, lane, f);
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int g = 0; g < G; g++) f[c][g] = gelu_new_sig(f[c][g]);
+                float mo[1][G];
+#pragma unroll
+                for (int g = 0; g < G; g++) mo[0][g] = w[L.bpr + lane];
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    __syncwarp();
+                    store_T<G>(scr, lane, f[2 * half]);
+                    store_T<G>(scr, lane + 32, f[2 * half + 1]);
+                    __syncwarp();
+                    warp_gemv<G, 1>(scr, w + L.wpr + half * 64 * 32, 64, 32, lane, mo);
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) h[g] += mo[0][g];
+                __syncwarp();                         // this warp is done with the layer's weights
+                if (lane == 0) mbar_arrive(&empty[lc & 1]);
+            }
+            // ---- final LN + linear head ----
+            store_T<G>(scr, lane, h);
+            __syncwarp();
+            warp_ln_T<G>(scr, gw, gw + 32, p.eps, lane);
+            __syncwarp();
+            float y[1][G];
+#pragma unroll
+            for (int g = 0; g < G; g++) y[0][g] = gw[64 + 1024 + lane];
+            warp_gemv<G, 1>(scr, gw + 64, 32, 32, lane, y);
+            const int pnext = min(s + 1, C - 1);
+            const float pe = __ldg(p.pe + pnext * 32 + lane);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int b = b0 + g;
+                if (b < p.B) p.out[(size_t)b * p.out_stride + (size_t)s * 32 + lane] = y[0][g];
+                h[g] = y[0][g] + pe;
+            }
+            __syncwarp();
+        }
+        if (p.presents != nullptr) {
+            const int Tk = min(p.S, C);
+            const int H = 4, hd = 8;
+            const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+            const int ph = lane >> 3, d = lane & 7;
+            for (int g = 0; g < G; g++) {
+                const int b = b0 + g;
+                if (b >= p.B) break;
+                for (int r = 0; r < NL * 2 * Tk; r++) {
+                    const int t = r % Tk, lw = r / Tk;          // lw = l*2 + which
+                    const int which = lw & 1, l = lw >> 1;
+                    const int sl = (p.S - Tk + t) % C;
+                    p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + ph) * Tk + t) * hd + d] =
                         kvw[(size_t)g * kv_per_g + ((size_t)lw * C + sl) * 32 + lane];
                 }
             }
@@ -1925,6 +2281,14 @@ int launch_e32(const RolloutParams& p, int maxi, int grid, int block, size_t sme
     }
 }
 
+template <int NCTX>
+int launch_e32s_one(const RolloutParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    TRPX_CUDA(cudaFuncSetAttribute(rollout_e32s_kernel<NCTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_e32s_kernel<NCTX><<<grid, block, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
 template <int NCTX, bool CACHE>
 int launch_v2_one(const RolloutParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     TRPX_CUDA(cudaFuncSetAttribute(rollout_e32v2_kernel<NCTX, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2084,7 +2448,7 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 7, "variant must be 0..7");
+    TRPX_REQUIRE(variant >= 0 && variant <= 8, "variant must be 0..8");
     TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 32, "warps_per_cta must be 0..32");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
                      traj_per_warp == 8 || (traj_per_warp == 16 && variant == 7),
@@ -2179,6 +2543,32 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             p.kv = h->kv;
             h->last_variant = 5; h->last_grid = grid; h->last_block = Wc * 32; h->last_smem = (int)smem; h->last_group = V2G;
             return launch_v2(p, L.n_ctx, grid, Wc * 32, smem, st);
+        }
+    }
+    // ---- E=32, KV window, TMA-staged attention + weight ring (variant 8) ----
+    if (e32_shape && use_cache && (h->tune_variant == 8) && (L.n_ctx == 8 || L.n_ctx == 16 || L.n_ctx % 32 == 0)) {
+        const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
+        const int nctx_t = L.n_ctx <= 8 ? 8 : (L.n_ctx <= 16 ? 16 : (L.n_ctx <= 32 ? 32 : 64));
+        const int br = std::min(nctx_t, 32);
+        const size_t per_warp = (size_t)(64 * E32S_G + E32S_G * br * 32) * sizeof(float);
+        const size_t fixed = ((size_t)((L.total - L.lnfw + 3) & ~3) + 2 * (size_t)L.layer_stride) * sizeof(float);
+        const int ngroups = (B + E32S_G - 1) / E32S_G;
+        const int max_w = (int)std::min<size_t>(nctx_t >= 32 ? 7 : E32S_MAXW, ((size_t)h->smem_optin - 1024 - fixed) / per_warp);
+        if (max_w >= 1) {
+            const int grid = std::min(sms, ngroups);
+            const int want = h->tune_warps > 0 ? h->tune_warps : max_w;
+            const int Wc = std::max(1, std::min(std::min(want, max_w), (ngroups + grid - 1) / grid));
+            const size_t smem = fixed + (size_t)Wc * per_warp;
+            int rc = ensure_kv(h, (size_t)grid * Wc * E32S_G * kv_per_traj);
+            if (rc) return rc;
+            p.kv = h->kv;
+            h->last_variant = 8; h->last_grid = grid; h->last_block = (Wc + 1) * 32; h->last_smem = (int)smem; h->last_group = E32S_G;
+            switch (nctx_t) {
+                case 8: return launch_e32s_one<8>(p, grid, (Wc + 1) * 32, smem, st);
+                case 16: return launch_e32s_one<16>(p, grid, (Wc + 1) * 32, smem, st);
+                case 32: return launch_e32s_one<32>(p, grid, (Wc + 1) * 32, smem, st);
+                default: return launch_e32s_one<64>(p, grid, (Wc + 1) * 32, smem, st);
+            }
         }
     }
     bool use_e32 = e32_shape && h->tune_variant != 1 && h->tune_variant != 7 && wbytes + (size_t)scr_per_warp_g1 + 1024 <= (size_t)h->smem_optin;

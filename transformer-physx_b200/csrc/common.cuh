@@ -78,6 +78,15 @@ __device__ __forceinline__ void ldg256(const float* p, float (&a)[8]) {
                  : "memory");
 }
 
+// Same with a compile-time byte offset folded into the instruction (no address register / LEA per row).
+template <int OFF>
+__device__ __forceinline__ void ldg256_off(const float* p, float (&a)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+%9];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
+                 : "l"(p), "n"(OFF)
+                 : "memory");
+}
+
 // Fire-and-forget bulk prefetch of a contiguous global range into L2 (cp.async.bulk.prefetch, SASS: UBLKPF).
 // `bytes` must be a multiple of 16 and `p` 16-byte aligned.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {

@@ -303,6 +303,14 @@ def run_ours(args):
     fp32, mma = N.ctypes.c_float(), N.ctypes.c_float()
     N.check(N.lib().trpx_probe_fp32_fma(local, N.ctypes.byref(fp32)))
     N.check(N.lib().trpx_probe_tf32_mma(local, N.ctypes.byref(mma)))
+    # the window access pattern alone (no arithmetic), same warps / rows in flight as the rollout: what the memory
+    # system delivers for this pattern on this box
+    probe_gbs = None
+    if cfg.n_embd == 32 and cfg.n_ctx % 32 == 0:
+        pg, pm = N.ctypes.c_float(), N.ctypes.c_float()
+        N.check(N.lib().trpx_probe_window_stream(local, min(B - B % 4, 65536), cfg.n_ctx, cfg.n_layer, 32, 8, 16, 0,
+                                                 N.ctypes.byref(pg), N.ctypes.byref(pm)))
+        probe_gbs = pg.value
     flops_step = algorithmic_flops_per_traj_step(cfg, S)
     k_flops = flops_step * B * S
     achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
@@ -321,7 +329,8 @@ def run_ours(args):
                 traffic = rec["dram_bytes_per_launch"]
     nc_flops = algorithmic_flops_per_traj_step(cfg, S, use_cache=False) * B * S
     nc_tf = nc_flops / (nocache_ms * 1e-3) / 1e12
-    kname = {1: "rollout_generic_kernel", 2: "rollout_e32_kernel", 5: "rollout_e32v2_kernel", 6: "rollout_e32v4_kernel"}
+    kname = {1: "rollout_generic_kernel", 2: "rollout_e32_kernel", 5: "rollout_e32v2_kernel", 6: "rollout_e32v4_kernel",
+             7: "rollout_cluster_kernel", 8: "rollout_e32s_kernel"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -340,6 +349,7 @@ def run_ours(args):
                      "bytes_model": "KV-window stream: per step and layer 2*L*E*4 B read + 2*E*4 B appended, + E*4 B token "
                                     "written (SURVEY 8d spill case; see bench.py window_bytes_per_traj and DESIGN.md 3)",
                      "kernel_traj_steps_per_s": B * S / (k_ms * 1e-3),
+                     "window_stream_probe_GBps": probe_gbs,
                      "fp32_view": {"achieved": achieved_tf, "peak": fp32.value, "unit": "TFLOP/s",
                                    "frac": achieved_tf / fp32.value, "flops_per_traj_step": flops_step,
                                    "peak_source": "FP32 FMA microbenchmark in this run (trpx_probe_fp32_fma)"},

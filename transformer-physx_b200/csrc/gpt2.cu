@@ -426,7 +426,9 @@ __device__ __forceinline__ void load_rows(const float* base, float (&r)[BS][8]) 
 }
 
 // FULLW: the window is full (L == C == NCTX, every step from n_ctx-1 on): no row clamping, no validity selects.
-template <int G, int NCTX, bool FULLW>
+// QS: row stride of the query tile; ORM > 0: write the output row-major [g][32] with row stride ORM instead of the
+// transposed tile.
+template <int G, int NCTX, bool FULLW, int QS = 32, int ORM = 0>
 __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl, size_t kv_per_g, int C, int L,
                                               float* outT, int lane) {
     constexpr int P = 8 / G;
@@ -435,7 +437,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
     const int part = lane % P, gh = lane / P, hh = gh & 3, g = gh >> 2;
     float q[8];
     {
-        const float4* qp = reinterpret_cast<const float4*>(qs + g * 32 + hh * 8);
+        const float4* qp = reinterpret_cast<const float4*>(qs + g * QS + hh * 8);
         const float4 a = qp[0], b = qp[1];
         q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
     }
@@ -514,8 +516,13 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
 #pragma unroll
         for (int d = 0; d < 8; d++) acc[d] += __shfl_xor_sync(FULL, acc[d], o);
     if (part == 0) {
+        if constexpr (ORM > 0) {
+            *reinterpret_cast<float4*>(outT + g * ORM + hh * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(outT + g * ORM + hh * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
 #pragma unroll
-        for (int d = 0; d < 8; d++) outT[(hh * 8 + d) * G + g] = acc[d];
+            for (int d = 0; d < 8; d++) outT[(hh * 8 + d) * G + g] = acc[d];
+        }
     }
 }
 
@@ -1551,7 +1558,7 @@ __global__ void __launch_bounds__(CACHE ? 256 : 384, 1) rollout_e32v4_kernel(Rol
             for (int l = 0; l < NL; l++) {
                 const float* w = wsm + l * L.layer_stride;
                 if constexpr (CACHE) {
-                    if (p.prefetch && lane < V4G && Lk > 1) {
+                    if (p.prefetch && lane < 4 && Lk > 1) {      // windows of the first attention pass
                         const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
                         prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
                         prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
@@ -1584,22 +1591,22 @@ __global__ void __launch_bounds__(CACHE ? 256 : 384, 1) rollout_e32v4_kernel(Rol
                         }
                     }
                     __syncwarp();
-                    float oo[2][8];
-#pragma unroll
-                    for (int pp = 0; pp < 2; pp++) {
-                        const int id = lane + 32 * pp, tg = id >> 2, hh = id & 3;
-                        float qq[8];
-                        const float4 qa = lds4(scr + tg * V4QS + hh * 8), qb = lds4(scr + tg * V4QS + hh * 8 + 4);
-                        qq[0] = qa.x; qq[1] = qa.y; qq[2] = qa.z; qq[3] = qa.w; qq[4] = qb.x; qq[5] = qb.y; qq[6] = qb.z; qq[7] = qb.w;
-                        const float* Kp = kvw + (size_t)tg * kv_per_g + (size_t)(l * 2) * C * 32 + hh * 8;
-                        lane_attention<NCTX>(qq, Kp, Kp + C * 32, Lk, oo[pp]);
-                    }
-                    __syncwarp();                 // all queries read: the tile is reused for the outputs
-#pragma unroll
-                    for (int pp = 0; pp < 2; pp++) {
-                        const int id = lane + 32 * pp, tg = id >> 2, hh = id & 3;
-                        *reinterpret_cast<float4*>(scr + tg * V4QS + hh * 8) = make_float4(oo[pp][0], oo[pp][1], oo[pp][2], oo[pp][3]);
-                        *reinterpret_cast<float4*>(scr + tg * V4QS + hh * 8 + 4) = make_float4(oo[pp][4], oo[pp][5], oo[pp][6], oo[pp][7]);
+                    // attention in 4 passes of 4 trajectories: two lanes per (trajectory, head) pair, 16 window rows in
+                    // flight per lane (the scheme of rollout_e32_kernel<4>); the windows of the NEXT pass are pulled
+                    // into L2 while this pass computes, so only ~32 KB per warp have to survive in L2
+#pragma unroll 1
+                    for (int t4 = 0; t4 < 4; t4++) {
+                        const float* kvl = kvw + (size_t)(4 * t4) * kv_per_g + (size_t)(l * 2) * C * 32;
+                        if (p.prefetch && t4 < 3 && lane < 4 && Lk > 1) {
+                            const float* kp = kvl + (size_t)(4 + lane) * kv_per_g;
+                            prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
+                            prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+                        }
+                        float* tile = scr + 4 * t4 * V4QS;
+                        if (Lk == NCTX)
+                            warp_attn_e32<4, NCTX, true, V4QS, V4QS>(tile, kvl, kv_per_g, C, Lk, tile, lane);
+                        else
+                            warp_attn_e32<4, NCTX, false, V4QS, V4QS>(tile, kvl, kv_per_g, C, Lk, tile, lane);
                     }
                     __syncwarp();
 #pragma unroll

@@ -402,9 +402,15 @@ __device__ __forceinline__ void warp_gemv(const float* scr, const float* W, int 
 #pragma unroll
         for (int c = 0; c < C; c++) w[c] = W[k * ldw + lane + 32 * c];
 #pragma unroll
-        for (int c = 0; c < C; c++)
+        for (int c = 0; c < C; c++) {
+            if constexpr (G % 2 == 0) {
 #pragma unroll
-            for (int g = 0; g < G; g++) acc[c][g] = fmaf(a[g], w[c], acc[c][g]);
+                for (int g = 0; g < G; g += 2) ffma2(acc[c][g], acc[c][g + 1], a[g], a[g + 1], w[c]);
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; g++) acc[c][g] = fmaf(a[g], w[c], acc[c][g]);
+            }
+        }
     }
 }
 
@@ -507,7 +513,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
             for (int jj = 0; jj < BS; jj++) {
                 const float pw = sc[j0 + jj] * rs;
 #pragma unroll
-                for (int d = 0; d < 8; d++) acc[d] = fmaf(pw, vv[jj][d], acc[d]);
+                for (int d = 0; d < 8; d += 2) ffma2(acc[d], acc[d + 1], vv[jj][d], vv[jj][d + 1], pw);
             }
         }
     }

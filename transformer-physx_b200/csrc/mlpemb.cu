@@ -93,12 +93,11 @@ __global__ void __launch_bounds__(EMB_THREADS) mlp_embed_kernel(const float* __r
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float4 w = sB[u * 8 + j];
+                // (acc[e], acc[e+1]) += (w[e], w[e+1]) * hid: one FFMA2 per weight pair (scalar-broadcast multiplier)
 #pragma unroll
                 for (int s = 0; s < SPT; s++) {
-                    acc[s][4 * j + 0] = fmaf(hid[s], w.x, acc[s][4 * j + 0]);
-                    acc[s][4 * j + 1] = fmaf(hid[s], w.y, acc[s][4 * j + 1]);
-                    acc[s][4 * j + 2] = fmaf(hid[s], w.z, acc[s][4 * j + 2]);
-                    acc[s][4 * j + 3] = fmaf(hid[s], w.w, acc[s][4 * j + 3]);
+                    ffma2(acc[s][4 * j + 0], acc[s][4 * j + 1], w.x, w.y, hid[s]);
+                    ffma2(acc[s][4 * j + 2], acc[s][4 * j + 3], w.z, w.w, hid[s]);
                 }
             }
         }
@@ -175,19 +174,18 @@ __global__ void __launch_bounds__(EMB_THREADS) mlp_recover_kernel(const float* _
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float4 w = sA[u * 8 + j];
+                // the (even, odd) partial sums of a sample advance together: one FFMA2 per weight pair, operands
+                // in the register order the 128-bit loads left them in
 #pragma unroll
                 for (int s = 0; s < SPT; s++) {
-                    p0[s] = fmaf(w.x, gi[s][4 * j + 0], p0[s]);
-                    p1[s] = fmaf(w.y, gi[s][4 * j + 1], p1[s]);
-                    p0[s] = fmaf(w.z, gi[s][4 * j + 2], p0[s]);
-                    p1[s] = fmaf(w.w, gi[s][4 * j + 3], p1[s]);
+                    ffma2v(p0[s], p1[s], gi[s][4 * j + 0], gi[s][4 * j + 1], w.x, w.y);
+                    ffma2v(p0[s], p1[s], gi[s][4 * j + 2], gi[s][4 * j + 3], w.z, w.w);
                 }
             }
 #pragma unroll
             for (int s = 0; s < SPT; s++) {
                 const float hid = fmaxf(p0[s] + p1[s], 0.f);
-                y[s][0] = fmaf(hid, b.x, y[s][0]);
-                y[s][1] = fmaf(hid, b.y, y[s][1]);
+                ffma2v(y[s][0], y[s][1], hid, hid, b.x, b.y);
                 y[s][2] = fmaf(hid, b.z, y[s][2]);
             }
         }

@@ -87,6 +87,18 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0_dev, long long x0_stride,
                       float* out_dev, long long out_stride, int B, int S, int use_cache,
                       float* presents_dev, void* stream);
 
+/* Teacher-forced training step (replaces PhysformerTrain.forward + loss.backward(),
+ * trphysx/transformer/phys_transformer_helpers.py:36-69 and utils/trainer.py:244-277):
+ *   hidden = forward(x)[0];  loss = mean((hidden - labels)^2) over B*T*n_embd
+ * x, labels: [B][T][n_embd], T <= n_ctx, positions 0..T-1, no past.  Writes the scalar loss, optionally the hidden
+ * states ([B][T][n_embd], may be NULL) and d loss / d weights as ONE blob of trpx_gpt2_blob_size() floats laid out
+ * like the packed weights: per layer ln_1.w, ln_1.b, c_attn.w [E][3E], c_attn.b, c_proj.w [E][E], c_proj.b, ln_2.w,
+ * ln_2.b, c_fc.w [E][4E], c_fc.b, mlp.c_proj.w [4E][E], mlp.c_proj.b; then ln_f.w, ln_f.b, mlp_f.weight TRANSPOSED
+ * ([in][out]), mlp_f.b.  Deterministic (per-sequence partials summed in a fixed order). */
+int trpx_gpt2_train_fwd_bwd(trpx_gpt2_t h, const float* x_dev, const float* labels_dev, int B, int T, float* loss_dev,
+                            float* hidden_dev, float* grad_blob_dev, void* stream);
+int trpx_gpt2_blob_size(trpx_gpt2_t h);
+
 /* Tuning knobs of the rollout kernel (0 = automatic).  `variant`: 0 auto, 1 generic kernel only, 2 E=32 warp
  * kernel, 3 = 2 without TMA weight staging, 4 = 2 without the L2 window prefetch (for A/B measurements),
  * 5 = E=32 kernel with 2-D lane tiling (16 trajectories per warp), 6 = E=32 tensor-core kernel (3xTF32

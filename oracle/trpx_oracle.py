@@ -159,6 +159,21 @@ def gpt2_generate(sd: SD, cfg, inputs_embeds: Tensor, max_length: int, use_cache
 # ==================================================================================================
 # Lorenz / Rossler embedding
 # ==================================================================================================
+def gpt2_train_grads(sd: SD, cfg, inputs_embeds: Tensor, labels_embeds: Tensor):
+    """PhysformerTrain.forward + loss.backward() (phys_transformer_helpers.py:36-69, utils/trainer.py:244-256):
+    loss = MSELoss()(transformer.forward(inputs_embeds)[0], labels_embeds).  Returns (loss, hidden, {name: grad})
+    for every tensor of `sd` that the forward uses (wpe, attn.bias and masked_bias get no gradient)."""
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.dtype.is_floating_point and not k.endswith("masked_bias")}      # buffers are not parameters
+    full = dict(sd)
+    full.update(leaves)
+    hidden, _, _ = gpt2_forward(full, cfg, inputs_embeds, use_cache=False)
+    loss = torch.nn.functional.mse_loss(hidden, labels_embeds)
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items() if v.grad is not None}
+    return loss.detach(), hidden.detach(), grads
+
+
 def lorenz_embed(sd: SD, cfg, x: Tensor) -> Tensor:
     # embedding_lorenz.py:94-105 ; observableNet :41-47
     x = (x - sd["mu"].unsqueeze(0)) / sd["std"].unsqueeze(0)

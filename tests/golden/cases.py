@@ -31,3 +31,14 @@ TRAIN_CASES = {
     "lorenz":  dict(kind="lorenz", seed=401, B=24, T=6, iters=2),
     "rossler": dict(kind="rossler", seed=402, B=16, T=4, iters=1),
 }
+
+# Teacher-forced transformer training step: PhysformerTrain.forward + loss.backward() of the reference
+# (phys_transformer_helpers.py:36-69).  Stored: loss, hidden states, every parameter gradient (state_dict names).
+GPT2_TRAIN_CASES = {
+    "lorenz_stress": dict(kind="lorenz", seed=501, stress=True, B=5, T=64),
+    "rossler_init": dict(kind="rossler", seed=502, stress=False, B=3, T=32),
+    "rossler_short": dict(kind="rossler", seed=503, stress=True, B=4, T=7),
+    "cylinder_stress": dict(kind="cylinder", seed=504, stress=True, B=2, T=16,
+                            keep=("h.0.ln_1.", "h.0.attn.c_attn.", "h.2.attn.c_proj.bias", "h.3.ln_2.", "h.5.mlp.c_fc.bias",
+                                  "h.5.mlp.c_proj.bias", "ln_f.", "mlp_f.")),
+}

@@ -14,7 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref_shim, synth  # noqa: E402
-from tests.golden.cases import GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES  # noqa: E402
+from tests.golden.cases import GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 torch.set_num_threads(1)          # deterministic reduction order for the fixtures
@@ -135,9 +135,37 @@ def train_cases(trphysx):
         print("train", name, {k: v.shape for k, v in out.items()})
 
 
+def gpt2_train_cases(trphysx):
+    from trphysx.transformer import PhysformerGPT2, PhysformerTrain
+    from trphysx.config.configuration_phys import PhysConfig
+    for name, c in GPT2_TRAIN_CASES.items():
+        cfg_ns = synth.make_config(c["kind"])
+        cfg = PhysConfig(**vars(cfg_ns))
+        head = PhysformerTrain(cfg, PhysformerGPT2(cfg, "golden"))
+        head.transformer.load_state_dict(_t(synth.gpt2_weights(cfg_ns, c["seed"], stress=c["stress"])), strict=True)
+        head.train()
+        B, T = c["B"], c["T"]
+        x = torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), c["seed"] + 1))
+        y = torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), c["seed"] + 2))
+        outputs = head(inputs_embeds=x, labels_embeds=y)          # the step body of utils/trainer.py:244-256
+        loss = outputs[0]
+        loss.backward()
+        out = {"loss": loss.detach().numpy(), "hidden": outputs[1].detach().numpy()}
+        keep = c.get("keep")                                       # wide models: a subset keeps the fixture small
+        for k, p_ in head.transformer.named_parameters():
+            if p_.grad is not None and (keep is None or any(k.startswith(pre) for pre in keep)):
+                out["grad." + k] = p_.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"gpt2train_{name}.npz"), **out)
+        print("gpt2train", name, float(loss), len(out))
+
+
 if __name__ == "__main__":
     t = ref_shim.load()
-    gpt2_cases(t)
-    lorenz_cases(t)
-    cyl_cases(t)
-    train_cases(t)
+    if len(sys.argv) > 1 and sys.argv[1] == "gpt2train":
+        gpt2_train_cases(t)                                        # added later: leaves the other fixtures untouched
+    else:
+        gpt2_cases(t)
+        lorenz_cases(t)
+        cyl_cases(t)
+        train_cases(t)
+        gpt2_train_cases(t)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import synth, trpx_oracle as O
-from tests.golden.cases import GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES
+from tests.golden.cases import GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES
 
 TOL = 2e-6          # both sides are torch-CPU fp32 executing the same aten ops; only threading differs
 
@@ -127,3 +127,23 @@ def test_lorenz_train_step_oracle(golden_dir, name):
         for k, t in zip(O.LORENZ_PARAM_ORDER, torch.split(flat, sizes)):
             sd[k] = t.view_as(sd[k]).clone()
     assert O.rel_l2(flat, gold["params_after"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", list(GPT2_TRAIN_CASES))
+def test_gpt2_train_step_oracle(golden_dir, name):
+    """Teacher-forced loss and parameter gradients against the reference's recorded backward()."""
+    c = GPT2_TRAIN_CASES[name]
+    gold = _load(golden_dir, f"gpt2train_{name}.npz")
+    cfg = synth.make_config(c["kind"])
+    sd = O.to_torch(synth.gpt2_weights(cfg, c["seed"], stress=c["stress"]))
+    x = torch.from_numpy(synth.normal_embeds((c["B"], c["T"], cfg.n_embd), c["seed"] + 1))
+    y = torch.from_numpy(synth.normal_embeds((c["B"], c["T"], cfg.n_embd), c["seed"] + 2))
+    loss, hidden, grads = O.gpt2_train_grads(sd, cfg, x, y)
+    assert abs(float(loss) - float(gold["loss"])) <= 2e-6 * abs(float(gold["loss"]))
+    assert O.rel_l2(hidden, gold["hidden"]) < TOL
+    keys = [k[5:] for k in gold.files if k.startswith("grad.")]
+    assert keys and all(k in grads for k in keys)
+    if c.get("keep") is None:
+        assert sorted(keys) == sorted(grads)              # same set of tensors receives a gradient
+    for k in keys:
+        assert O.rel_l2(grads[k], gold["grad." + k]) < 5 * TOL, k

@@ -8,29 +8,12 @@
 // attention: attention.py:75-119, 153-200.
 #include "common.cuh"
 #include "gpt2_layout.cuh"
+#include "gpt2_handle.cuh"
 #include <cmath>
 #include <vector>
 #include <algorithm>
 
 using namespace trpx;
-
-struct trpx_gpt2 {
-    uint32_t magic = 0x67707432u;
-    trpx_gpt2_config cfg{};
-    Gpt2Layout lay{};
-    int device = 0;
-    int sm_count = 0;
-    int smem_optin = 0;
-    float* blob = nullptr;
-    float* blob_sw = nullptr;
-    float* img_cl = nullptr;       // per-(image, rank) weight slices for the cluster kernel
-    float* pe = nullptr;
-    bool loaded = false;
-    float* kv = nullptr;          // rollout workspace (KV windows of the groups in flight)
-    size_t kv_bytes = 0;
-    int tune_variant = 0, tune_warps = 0, tune_g = 0, tune_max_ctas = 0, tune_prefetch = 1;
-    int last_variant = 0, last_grid = 0, last_block = 0, last_smem = 0, last_group = 0;
-};
 
 namespace {
 
@@ -2276,7 +2259,6 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
     }
 }
 
-bool valid(trpx_gpt2_t h) { return h != nullptr && h->magic == 0x67707432u; }
 
 size_t generic_rollout_smem(const Gpt2Layout& L, int G) {
     return sizeof(float) * ((size_t)(L.E * G) * (1 + 1 + 3 + 4) + (size_t)4 * ROLL_THREADS * G +
@@ -2411,6 +2393,7 @@ int trpx_gpt2_destroy(trpx_gpt2_t h) {
     cudaFree(h->img_cl);
     cudaFree(h->pe);
     cudaFree(h->kv);
+    cudaFree(h->train_ws);
     h->magic = 0;
     delete h;
     return TRPX_OK;

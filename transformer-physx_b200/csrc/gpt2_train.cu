@@ -1,0 +1,413 @@
+// K8: teacher-forced training step of the decoder stack.
+//
+// Replaces, for one mini-batch, PhysformerTrain.forward + loss.backward()
+// (trphysx/transformer/phys_transformer_helpers.py:36-69 ; utils/trainer.py:244-277):
+//     hidden = transformer.forward(inputs_embeds)[0];  loss = MSELoss()(hidden, labels_embeds)   (mean over B*T*E)
+// and the gradient of `loss` with respect to every parameter of the stack, in the packed blob layout
+// (gpt2_layout.cuh; mlp_f.weight transposed).  Forward arithmetic is the one of the forward kernel (K2).
+//
+// One CTA per sequence: forward keeps the residual stream in shared memory and saves, per layer, the tensors the
+// backward needs (LN inputs/outputs, q|k|v, attention output, MLP pre-activation) in a global workspace that stays
+// L2 resident (12*T*E floats per layer and sequence); attention probabilities are recomputed per head in the
+// backward.  Weight gradients are written as per-sequence partials and summed over the batch in a fixed order by
+// the finalize kernel (deterministic; no atomics), which also finishes the loss.
+#include "common.cuh"
+#include "gpt2_layout.cuh"
+#include "gpt2_handle.cuh"
+#include <algorithm>
+
+using namespace trpx;
+
+namespace {
+
+constexpr int TR_THREADS = 256;
+
+struct TrainParams {
+    const float* blob;
+    const float* pe;
+    const float* x;         // [B][T][E]
+    const float* labels;    // [B][T][E]
+    float* hidden;          // [B][T][E] or null
+    float* acts;            // [B][acts_per_seq]
+    float* gpart;           // [B][L.total]
+    float* loss_part;       // [B]
+    int B, T;
+    float eps;
+    float dscale;           // 2 / (B*T*E)
+    Gpt2Layout lay;
+};
+
+__device__ __forceinline__ float gelu_new_grad(float x) {
+    // d/dx [0.5 x (1 + tanh(u))], u = c (x + 0.044715 x^3)     (transformer/utils.py:57-60)
+    const float c = 0.7978845608028654f;
+    const float u = c * (x + 0.044715f * x * x * x);
+    const float t = tanhf(u);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * (1.0f + 3.0f * 0.044715f * x * x);
+}
+
+// Y[t][n] = bias[n] + sum_k X[t][k] * W[k*N + n]            X: smem [T][K], W: global [K][N]
+__device__ void mm_xw(float* Y, const float* X, const float* __restrict__ W, const float* __restrict__ bias, int T,
+                      int K, int N) {
+    for (int idx = threadIdx.x; idx < T * N; idx += blockDim.x) {
+        const int t = idx / N, n = idx - t * N;
+        float acc = bias ? __ldg(bias + n) : 0.f;
+        const float* xr = X + t * K;
+        for (int k = 0; k < K; k++) acc = fmaf(xr[k], __ldg(W + (size_t)k * N + n), acc);
+        Y[idx] = acc;
+    }
+}
+// dX[t][k] = sum_n dY[t][n] * W[k*N + n]                     dY: smem [T][N]
+__device__ void mm_xwT(float* dX, const float* dY, const float* __restrict__ W, int T, int K, int N) {
+    for (int idx = threadIdx.x; idx < T * K; idx += blockDim.x) {
+        const int t = idx / K, k = idx - t * K;
+        float acc = 0.f;
+        const float* dr = dY + t * N;
+        const float* wr = W + (size_t)k * N;
+        for (int n = 0; n < N; n++) acc = fmaf(dr[n], __ldg(wr + n), acc);
+        dX[idx] = acc;
+    }
+}
+// dW[k*N + n] = sum_t X[t][k] * dY[t][n] ; db[n] = sum_t dY[t][n]      (written, not accumulated)
+__device__ void mm_xTy(float* dW, float* db, const float* X, const float* dY, int T, int K, int N) {
+    for (int idx = threadIdx.x; idx < K * N; idx += blockDim.x) {
+        const int k = idx / N, n = idx - k * N;
+        float acc = 0.f;
+        for (int t = 0; t < T; t++) acc = fmaf(X[t * K + k], dY[t * N + n], acc);
+        dW[idx] = acc;
+    }
+    if (db != nullptr)
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            float acc = 0.f;
+            for (int t = 0; t < T; t++) acc += dY[t * N + n];
+            db[n] = acc;
+        }
+}
+// Y = LN(X) (biased variance)
+__device__ void ln_fwd(float* Y, const float* X, const float* __restrict__ w, const float* __restrict__ b, int T, int E,
+                       float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int t = warp; t < T; t += nw) {
+        float s = 0.f;
+        for (int c = lane; c < E; c += 32) s += X[t * E + c];
+        const float mean = warp_sum(s) / (float)E;
+        float v = 0.f;
+        for (int c = lane; c < E; c += 32) {
+            const float d = X[t * E + c] - mean;
+            v = fmaf(d, d, v);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + eps);
+        for (int c = lane; c < E; c += 32) Y[t * E + c] = (X[t * E + c] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+    }
+}
+// LayerNorm backward: X (in: LN input, out: xhat), dY unchanged; dH[t][c] (+)= dx ; dw, db written.
+// Caller synchronises before (X, dY complete) — this function synchronises internally between its two phases.
+__device__ void ln_bwd(float* dH, bool accumulate, float* X, const float* dY, const float* __restrict__ w, float* dw,
+                       float* db, int T, int E, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int t = warp; t < T; t += nw) {
+        float s = 0.f;
+        for (int c = lane; c < E; c += 32) s += X[t * E + c];
+        const float mean = warp_sum(s) / (float)E;
+        float v = 0.f;
+        for (int c = lane; c < E; c += 32) {
+            const float d = X[t * E + c] - mean;
+            v = fmaf(d, d, v);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + eps);
+        float m1 = 0.f, m2 = 0.f;
+        for (int c = lane; c < E; c += 32) {
+            const float xh = (X[t * E + c] - mean) * rstd;
+            const float dyw = dY[t * E + c] * __ldg(w + c);
+            X[t * E + c] = xh;
+            m1 += dyw;
+            m2 = fmaf(dyw, xh, m2);
+        }
+        m1 = warp_sum(m1) / (float)E;
+        m2 = warp_sum(m2) / (float)E;
+        for (int c = lane; c < E; c += 32) {
+            const float dyw = dY[t * E + c] * __ldg(w + c);
+            const float dx = rstd * (dyw - m1 - X[t * E + c] * m2);
+            dH[t * E + c] = accumulate ? dH[t * E + c] + dx : dx;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < E; c += blockDim.x) {
+        float a = 0.f, bsum = 0.f;
+        for (int t = 0; t < T; t++) {
+            a = fmaf(dY[t * E + c], X[t * E + c], a);
+            bsum += dY[t * E + c];
+        }
+        dw[c] = a;
+        db[c] = bsum;
+    }
+}
+__device__ void tile_load(float* dst, const float* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+__device__ void tile_store(float* __restrict__ dst, const float* src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// causal softmax row i of head hh:  P[i][j] = softmax_{j<=i}(q_i . k_j / sqrt(hd)), 0 for j > i
+// (attention.py:97-109: masked logits are -1e4, whose exp underflows to exactly 0 in FP32)
+__device__ __forceinline__ void attn_row(const float* qkv, int i, int hh, int T, int E, int hd, float* Prow, int lane) {
+    const float scale = sqrtf((float)hd);
+    const float* q = qkv + i * 3 * E + hh * hd;
+    float m = -INFINITY;
+    for (int j = lane; j <= i; j += 32) {
+        const float* k = qkv + j * 3 * E + E + hh * hd;
+        float s = 0.f;
+        for (int d = 0; d < hd; d++) s = fmaf(q[d], k[d], s);
+        s = s / scale;
+        Prow[j] = s;
+        m = fmaxf(m, s);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j <= i; j += 32) {
+        const float e = expf(Prow[j] - m);
+        Prow[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int j = lane; j < T; j += 32) Prow[j] = (j <= i) ? Prow[j] / sum : 0.f;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float red[TR_THREADS / 32];
+    const Gpt2Layout& L = p.lay;
+    const int E = L.E, H = L.n_head, hd = L.hd, T = p.T, NL = L.n_layer;
+    const int TE = T * E;
+    float* h = sm;                         // [T][E]   residual (forward) / its gradient (backward)
+    float* t0 = h + TE;                    // four [T][4E] work tiles
+    float* t1 = t0 + 4 * TE;
+    float* t2 = t1 + 4 * TE;
+    float* t3 = t2 + 4 * TE;
+    float* P = t3 + 4 * TE;                // [max(T, warps)][T]  (forward: one scratch row per warp)
+    float* dS = P + max(T, TR_THREADS / 32) * T;   // [T][T]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const int b = blockIdx.x;
+    const size_t per_layer = (size_t)12 * TE;
+    float* acts = p.acts + (size_t)b * (NL * per_layer + 2 * (size_t)TE);
+    float* gp = p.gpart + (size_t)b * L.total;
+    // saved per layer: x_in [TE] | a1 [TE] | qkv [3TE] | att [TE] | x_mid [TE] | a2 [TE] | fc_pre [4TE]
+    constexpr int O_XIN = 0, O_A1 = 1, O_QKV = 2, O_ATT = 5, O_XMID = 6, O_A2 = 7, O_FC = 8;
+
+    // ============================== forward ==============================
+    for (int i = tid; i < TE; i += blockDim.x) {
+        const int t = i / E, c = i - t * E;
+        h[i] = p.x[(size_t)b * TE + i] + __ldg(p.pe + t * E + c);      // position id = t (phys_transformer_gpt2.py:198)
+    }
+    __syncthreads();
+    for (int l = 0; l < NL; l++) {
+        const float* w = p.blob + (size_t)l * L.layer_stride;
+        float* sv = acts + l * per_layer;
+        tile_store(sv + O_XIN * TE, h, TE);
+        ln_fwd(t0, h, w + L.ln1w, w + L.ln1b, T, E, p.eps);
+        __syncthreads();
+        tile_store(sv + O_A1 * TE, t0, TE);
+        mm_xw(t1, t0, w + L.wqkv, w + L.bqkv, T, E, 3 * E);            // [T][3E] rows q|k|v
+        __syncthreads();
+        tile_store(sv + O_QKV * TE, t1, 3 * TE);
+        for (int pair = warp; pair < T * H; pair += nw) {
+            const int i = pair / H, hh = pair - i * H;
+            float* Prow = P + (size_t)warp * T;                         // per-warp scratch row (nw <= T rows used)
+            attn_row(t1, i, hh, T, E, hd, Prow, lane);
+            for (int d = lane; d < hd; d += 32) {
+                float acc = 0.f;
+                for (int j = 0; j <= i; j++) acc = fmaf(Prow[j], t1[j * 3 * E + 2 * E + hh * hd + d], acc);
+                t2[i * E + hh * hd + d] = acc;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        tile_store(sv + O_ATT * TE, t2, TE);
+        mm_xw(t0, t2, w + L.wproj, w + L.bproj, T, E, E);
+        __syncthreads();
+        for (int i = tid; i < TE; i += blockDim.x) h[i] += t0[i];
+        __syncthreads();
+        tile_store(sv + O_XMID * TE, h, TE);
+        ln_fwd(t0, h, w + L.ln2w, w + L.ln2b, T, E, p.eps);
+        __syncthreads();
+        tile_store(sv + O_A2 * TE, t0, TE);
+        mm_xw(t1, t0, w + L.wfc, w + L.bfc, T, E, 4 * E);
+        __syncthreads();
+        tile_store(sv + O_FC * TE, t1, 4 * TE);
+        for (int i = tid; i < 4 * TE; i += blockDim.x) t2[i] = gelu_new(t1[i]);
+        __syncthreads();
+        mm_xw(t0, t2, w + L.wpr, w + L.bpr, T, 4 * E, E);
+        __syncthreads();
+        for (int i = tid; i < TE; i += blockDim.x) h[i] += t0[i];
+        __syncthreads();
+    }
+    float* sv_f = acts + NL * per_layer;                                // h_L [TE] | a_f [TE]
+    tile_store(sv_f, h, TE);
+    ln_fwd(t0, h, p.blob + L.lnfw, p.blob + L.lnfb, T, E, p.eps);
+    __syncthreads();
+    mm_xw(t1, t0, p.blob + L.wf, p.blob + L.bf, T, E, E);              // blob wf is [in][out]
+    __syncthreads();
+    float lsum = 0.f;
+    for (int i = tid; i < TE; i += blockDim.x) {
+        const float y = t1[i];
+        if (p.hidden) p.hidden[(size_t)b * TE + i] = y;
+        const float d = y - p.labels[(size_t)b * TE + i];
+        lsum = fmaf(d, d, lsum);
+        t1[i] = d * p.dscale;                                           // dL/dy
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) red[warp] = lsum;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int i = 0; i < nw; i++) s += red[i];
+        p.loss_part[b] = s;
+    }
+
+    // ============================== backward ==============================
+    // head: y = a_f Wf + bf ; a_f = LN_f(h_L)
+    mm_xTy(gp + L.wf, gp + L.bf, t0, t1, T, E, E);
+    mm_xwT(t2, t1, p.blob + L.wf, T, E, E);                             // d a_f
+    tile_load(t3, sv_f, TE);                                            // h_L
+    __syncthreads();
+    ln_bwd(h, false, t3, t2, p.blob + L.lnfw, gp + L.lnfw, gp + L.lnfb, T, E, p.eps);
+    __syncthreads();
+    for (int l = NL - 1; l >= 0; l--) {
+        const float* w = p.blob + (size_t)l * L.layer_stride;
+        float* g = gp + (size_t)l * L.layer_stride;
+        const float* sv = acts + l * per_layer;
+        // ---- MLP: out = x_mid + gelu(fc_pre) Wpr + bpr ; fc_pre = a2 Wfc + bfc ; a2 = LN2(x_mid) ----
+        tile_load(t1, sv + O_FC * TE, 4 * TE);
+        __syncthreads();
+        for (int i = tid; i < 4 * TE; i += blockDim.x) t2[i] = gelu_new(t1[i]);
+        __syncthreads();
+        mm_xTy(g + L.wpr, g + L.bpr, t2, h, T, 4 * E, E);
+        mm_xwT(t0, h, w + L.wpr, T, 4 * E, E);                          // d gelu_out [T][4E]
+        __syncthreads();
+        for (int i = tid; i < 4 * TE; i += blockDim.x) t0[i] *= gelu_new_grad(t1[i]);     // d fc_pre
+        tile_load(t2, sv + O_A2 * TE, TE);
+        __syncthreads();
+        mm_xTy(g + L.wfc, g + L.bfc, t2, t0, T, E, 4 * E);
+        mm_xwT(t1, t0, w + L.wfc, T, E, 4 * E);                         // d a2 [T][E]
+        tile_load(t3, sv + O_XMID * TE, TE);
+        __syncthreads();
+        ln_bwd(h, true, t3, t1, w + L.ln2w, g + L.ln2w, g + L.ln2b, T, E, p.eps);
+        __syncthreads();
+        // ---- attention block: x_mid = x_in + att Wproj + bproj ----
+        tile_load(t0, sv + O_ATT * TE, TE);
+        tile_load(t2, sv + O_QKV * TE, 3 * TE);
+        __syncthreads();
+        mm_xTy(g + L.wproj, g + L.bproj, t0, h, T, E, E);
+        mm_xwT(t1, h, w + L.wproj, T, E, E);                            // d att [T][E]
+        __syncthreads();
+        // per head: P, dS in shared memory, then dq, dk, dv into t3 ([T][3E])
+        const float rscale = 1.0f / sqrtf((float)hd);
+        for (int hh = 0; hh < H; hh++) {
+            for (int i = warp; i < T; i += nw) {
+                float* Prow = P + (size_t)i * T;
+                attn_row(t2, i, hh, T, E, hd, Prow, lane);
+                // dP_ij = d_o_i . v_j ; rs_i = sum_j dP_ij P_ij ; dS_ij = P_ij (dP_ij - rs_i)
+                const float* doi = t1 + i * E + hh * hd;
+                float rs = 0.f;
+                for (int j = lane; j <= i; j += 32) {
+                    const float* v = t2 + j * 3 * E + 2 * E + hh * hd;
+                    float dp = 0.f;
+                    for (int d = 0; d < hd; d++) dp = fmaf(doi[d], v[d], dp);
+                    dS[i * T + j] = dp;
+                    rs = fmaf(dp, Prow[j], rs);
+                }
+                rs = warp_sum(rs);
+                for (int j = lane; j < T; j += 32) dS[i * T + j] = (j <= i) ? Prow[j] * (dS[i * T + j] - rs) : 0.f;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < T * hd; idx += blockDim.x) {
+                const int r = idx / hd, d = idx - r * hd;
+                // dq_r = sum_{j<=r} dS_rj k_j / sqrt(hd)
+                float dq = 0.f;
+                for (int j = 0; j <= r; j++) dq = fmaf(dS[r * T + j], t2[j * 3 * E + E + hh * hd + d], dq);
+                // dk_r = sum_{i>=r} dS_ir q_i / sqrt(hd) ; dv_r = sum_{i>=r} P_ir d_o_i
+                float dk = 0.f, dv = 0.f;
+                for (int i = r; i < T; i++) {
+                    dk = fmaf(dS[i * T + r], t2[i * 3 * E + hh * hd + d], dk);
+                    dv = fmaf(P[i * T + r], t1[i * E + hh * hd + d], dv);
+                }
+                t3[r * 3 * E + hh * hd + d] = dq * rscale;
+                t3[r * 3 * E + E + hh * hd + d] = dk * rscale;
+                t3[r * 3 * E + 2 * E + hh * hd + d] = dv;
+            }
+            __syncthreads();
+        }
+        tile_load(t0, sv + O_A1 * TE, TE);
+        __syncthreads();
+        mm_xTy(g + L.wqkv, g + L.bqkv, t0, t3, T, E, 3 * E);
+        mm_xwT(t1, t3, w + L.wqkv, T, E, 3 * E);                        // d a1 [T][E]
+        tile_load(t2, sv + O_XIN * TE, TE);
+        __syncthreads();
+        ln_bwd(h, true, t2, t1, w + L.ln1w, g + L.ln1w, g + L.ln1b, T, E, p.eps);
+        __syncthreads();
+    }
+}
+
+// grad[i] = sum_b gpart[b][i] (fixed order) ; loss = sum_b loss_part[b] / (B*T*E)
+__global__ void train_finalize_kernel(const float* __restrict__ gpart, const float* __restrict__ loss_part,
+                                      float* __restrict__ grad, float* __restrict__ loss, int B, int total, float inv_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        float s = 0.f;
+        for (int b = 0; b < B; b++) s += gpart[(size_t)b * total + i];
+        grad[i] = s;
+    }
+    if (i == 0) {
+        float s = 0.f;
+        for (int b = 0; b < B; b++) s += loss_part[b];
+        loss[0] = s * inv_count;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int trpx_gpt2_train_fwd_bwd(trpx_gpt2_t h, const float* x, const float* labels, int B, int T, float* loss_dev,
+                            float* hidden_dev, float* grad_blob_dev, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(B >= 1 && T >= 1, "bad batch / length");
+    TRPX_REQUIRE(T <= h->cfg.n_ctx, "sequence length %d exceeds n_ctx %d", T, h->cfg.n_ctx);
+    TRPX_REQUIRE(x != nullptr && labels != nullptr && loss_dev != nullptr && grad_blob_dev != nullptr, "null pointer");
+    DeviceGuard guard(h->device);
+    const Gpt2Layout& L = h->lay;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t TE = (size_t)T * L.E;
+    const size_t smem = sizeof(float) * (TE * 17 + ((size_t)std::max(T, TR_THREADS / 32) + T) * T);
+    TRPX_REQUIRE(smem + 1024 <= (size_t)h->smem_optin, "training step needs %zu B of shared memory per sequence", smem);
+    const size_t acts_per_seq = (size_t)L.n_layer * 12 * TE + 2 * TE;
+    const size_t need = sizeof(float) * ((size_t)B * (acts_per_seq + L.total + 1));
+    if (need > h->train_ws_bytes) {
+        if (h->train_ws) TRPX_CUDA(cudaFree(h->train_ws));
+        h->train_ws = nullptr;
+        h->train_ws_bytes = 0;
+        TRPX_CUDA(cudaMalloc(&h->train_ws, need));
+        h->train_ws_bytes = need;
+    }
+    TrainParams p{};
+    p.blob = h->blob; p.pe = h->pe; p.x = x; p.labels = labels; p.hidden = hidden_dev;
+    p.acts = h->train_ws;
+    p.gpart = h->train_ws + (size_t)B * acts_per_seq;
+    p.loss_part = p.gpart + (size_t)B * L.total;
+    p.B = B; p.T = T; p.eps = h->cfg.ln_eps;
+    p.dscale = 2.0f / ((float)B * (float)T * (float)L.E);
+    p.lay = L;
+    TRPX_CUDA(cudaFuncSetAttribute(train_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    train_fwd_bwd_kernel<<<B, TR_THREADS, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    train_finalize_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(p.gpart, p.loss_part, grad_blob_dev, loss_dev, B, L.total,
+                                                                  1.0f / ((float)B * (float)T * (float)L.E));
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int trpx_gpt2_blob_size(trpx_gpt2_t h) { return valid(h) ? h->lay.total : -1; }
+
+}  // extern "C"

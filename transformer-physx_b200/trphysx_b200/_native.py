@@ -30,6 +30,8 @@ SIGNATURES = {
     "trpx_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int)]),
     "trpx_probe_fp32_fma": (c_int, [c_int, POINTER(c_float)]),
     "trpx_probe_tf32_mma": (c_int, [c_int, POINTER(c_float)]),
+    "trpx_gpt2_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "trpx_gpt2_blob_size": (c_int, [c_void_p]),
     "trpx_probe_window_stream": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float),
                                          POINTER(c_float)]),
     "trpx_gpt2_create": (c_int, [POINTER(Gpt2Config), c_int, POINTER(c_void_p)]),

@@ -179,6 +179,44 @@ class PhysformerGPT2(PhysformerBase):
             self._keepalive = tensors
         return h
 
+    # ------------------------------------------------------------------ fused training step
+    def _blob_views(self, blob: Tensor) -> List[Tensor]:
+        """Views of a packed blob (csrc/gpt2_layout.cuh) in `_weight_list()` order and parameter shapes."""
+        E = self.config.n_embd
+        sizes = []
+        for _ in self.h:
+            sizes += [(E,), (E,), (E, 3 * E), (3 * E,), (E, E), (E,), (E,), (E,), (E, 4 * E), (4 * E,), (4 * E, E), (E,)]
+        sizes += [(E,), (E,), (E, E), (E,)]
+        views, o = [], 0
+        for shp in sizes:
+            n = 1
+            for d in shp:
+                n *= d
+            views.append(blob[o:o + n].view(*shp))
+            o += n
+        assert o == blob.numel()
+        views[-2] = views[-2].t()          # mlp_f.weight is stored transposed ([in][out]) in the blob
+        return views
+
+    def fused_loss_and_grads(self, inputs_embeds: Tensor, labels_embeds: Tensor):
+        """loss = MSE(forward(inputs_embeds), labels_embeds) and its gradient for every parameter of the stack in ONE
+        launch pair (csrc/gpt2_train.cu).  Returns (loss [scalar tensor], hidden [B,T,E], grads in `_weight_list()`
+        order)."""
+        self._check_supported()
+        x = N.require_cuda_f32(inputs_embeds, "inputs_embeds")
+        y = N.require_cuda_f32(labels_embeds, "labels_embeds")
+        if x.dim() != 3 or x.shape != y.shape or x.shape[-1] != self.config.n_embd:
+            raise ValueError("inputs_embeds and labels_embeds must both be [B, T, n_embd]")
+        B, T, E = x.shape
+        h = self._handle(x.device)
+        total = N.lib().trpx_gpt2_blob_size(h)
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        hidden = torch.empty_like(x)
+        gblob = torch.empty(total, device=x.device, dtype=torch.float32)
+        N.check(N.lib().trpx_gpt2_train_fwd_bwd(h, x.data_ptr(), y.data_ptr(), B, T, loss.data_ptr(), hidden.data_ptr(),
+                                                gblob.data_ptr(), N.stream_ptr(x.device)))
+        return loss, hidden, self._blob_views(gblob)
+
     def set_rollout_tuning(self, variant: int = 0, warps_per_cta: int = 0, traj_per_warp: int = 0, max_ctas: int = 0):
         """Kernel tuning knobs (0 = automatic); see trpx_gpt2_set_rollout_tuning in include/trpx.h."""
         self._tuning = (variant, warps_per_cta, traj_per_warp, max_ctas)

@@ -1,11 +1,27 @@
-"""`PhysformerTrain`: the evaluation head that drives generate() (reference:
+"""`PhysformerTrain`: the training / evaluation head (reference:
 trphysx/transformer/phys_transformer_helpers.py:22-122).  evaluate()/generate() are on the rollout hot path;
-the teacher-forced training forward() needs autograd through the decoder stack, which is a "next" row
- and raises until it is built."""
+the teacher-forced training forward() returns a loss whose backward() fills the `.grad` of every
+parameter of the stack from ONE fused forward+backward launch (csrc/gpt2_train.cu) — there is no autograd graph
+through the decoder blocks."""
 import torch
 from torch import nn
 
 from .phys_transformer_gpt2 import PhysformerBase
+
+
+class _FusedStackLoss(torch.autograd.Function):
+    """loss(params) with the gradient computed eagerly by the fused kernel; backward only scales it."""
+
+    @staticmethod
+    def forward(ctx, model, inputs_embeds, labels_embeds, *params):
+        loss, hidden, grads = model.fused_loss_and_grads(inputs_embeds, labels_embeds)
+        ctx.grads = grads
+        ctx.mark_non_differentiable(hidden)
+        return loss, hidden
+
+    @staticmethod
+    def backward(ctx, gloss, _ghidden):
+        return (None, None, None) + tuple(g * gloss for g in ctx.grads)
 
 
 class PhysformerTrain(PhysformerBase):
@@ -15,10 +31,15 @@ class PhysformerTrain(PhysformerBase):
         self.transformer.apply(self._init_weights)
 
     def forward(self, inputs_embeds, labels_embeds, **kwargs):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.transformer.parameters()):
-            raise NotImplementedError(
-                "teacher-forced training (autograd through the decoder stack) is not built yet; "
-                "call under torch.no_grad() for the loss value only")
+        params = self.transformer._weight_list()
+        if labels_embeds is not None and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            if any(kwargs.get(k) for k in ("past", "attention_mask", "head_mask", "prop_embeds", "position_ids",
+                                           "output_attentions")):
+                raise NotImplementedError("the fused training step takes inputs_embeds and labels_embeds only")
+            if inputs_embeds.requires_grad:
+                raise NotImplementedError("gradients with respect to inputs_embeds are not computed by the fused step")
+            loss, hidden = _FusedStackLoss.apply(self.transformer, inputs_embeds, labels_embeds, *params)
+            return (loss, hidden, labels_embeds)
         outputs = self.transformer.forward(inputs_embeds=inputs_embeds, **kwargs)
         if labels_embeds is not None:
             hidden = outputs[0]

@@ -98,6 +98,9 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0_dev, long long x0_stride,
 int trpx_gpt2_train_fwd_bwd(trpx_gpt2_t h, const float* x_dev, const float* labels_dev, int B, int T, float* loss_dev,
                             float* hidden_dev, float* grad_blob_dev, void* stream);
 int trpx_gpt2_blob_size(trpx_gpt2_t h);
+/* Replace the weights by a packed blob in the same layout (device pointer, trpx_gpt2_blob_size() floats): used by the
+ * fused optimizer, whose master parameters live in this layout, after every clip + Adam update. */
+int trpx_gpt2_load_blob(trpx_gpt2_t h, const float* blob_dev, void* stream);
 
 /* Tuning knobs of the rollout kernel (0 = automatic).  `variant`: 0 auto, 1 generic kernel only, 2 E=32 warp
  * kernel, 3 = 2 without TMA weight staging, 4 = 2 without the L2 window prefetch (for A/B measurements),

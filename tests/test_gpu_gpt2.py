@@ -366,3 +366,57 @@ def test_train_step_vs_oracle_and_sgd(dev):
     with torch.no_grad():                                   # the no-grad path still returns the reference tuple
         out = head(inputs_embeds=x, labels_embeds=y)
     assert len(out) >= 3 and float(out[0]) < losses[2]
+
+
+def test_fused_transformer_step_equals_reference_loop(dev):
+    """FusedTransformerStep (fused fwd+bwd -> clip + Adam on the packed master buffer -> load_blob) against the
+    reference's step body run by torch on the oracle graph: loss.backward(); clip_grad_norm_; Adam.step(), 3 steps.
+    Afterwards the module's parameters (views of the master buffer), its state_dict and generate() all see the
+    updated weights."""
+    from trphysx_b200.optim import FusedTransformerStep
+    cfg = synth.make_config("lorenz")
+    w_np = synth.gpt2_weights(cfg, 707, stress=True, stress_sigma=0.2)
+    m = make_gpt2(cfg, 707, True, dev)
+    m.load_state_dict(torch_sd(w_np))
+    m.to(dev).train()
+    B, T = 12, 40
+    xs = [torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), 710 + i)) for i in range(3)]
+    ys = [torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), 720 + i)) for i in range(3)]
+    # reference loop on CPU: leaves = the oracle's weight dict, torch.optim.Adam + clip_grad_norm_
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and not k.endswith("masked_bias") else v)
+          for k, v in O.to_torch(w_np).items()}
+    leaves = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-10)
+    ref_losses = []
+    for x, y in zip(xs, ys):
+        opt.zero_grad()
+        hidden, _, _ = O.gpt2_forward(sd, cfg, x, use_cache=False)
+        loss = torch.nn.functional.mse_loss(hidden, y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([v for v in leaves if v.grad is not None], 0.1)
+        opt.step()
+        ref_losses.append(float(loss))
+    step = FusedTransformerStep(m, lr=1e-3, weight_decay=1e-10, max_norm=0.1)
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        loss = step(x.to(dev), y.to(dev))
+        assert abs(float(loss) - ref_losses[i]) <= 2e-5 * abs(ref_losses[i]), (i, float(loss), ref_losses[i])
+    # Parameters after 3 Adam steps.  Adam divides by sqrt(v): where the true gradient is exactly zero (the key bias:
+    # softmax is invariant to a constant added to a row of scores) both sides step by +-lr on rounding noise, so
+    # those entries differ by O(lr) = 1e-3 absolute; everything else agrees to the FP32 bar.
+    got = m.state_dict()
+    E = cfg.n_embd
+    for k, v in sd.items():
+        if not v.requires_grad or k == "wpe.weight":
+            continue
+        a, b = got[k].cpu(), v.detach()
+        if k.endswith("attn.c_attn.bias"):
+            assert (a[E:2 * E] - b[E:2 * E]).abs().max() < 3 * 3 * 1e-3, k
+            a, b = torch.cat([a[:E], a[2 * E:]]), torch.cat([b[:E], b[2 * E:]])
+        assert O.rel_l2(a, b) < TOL, k
+    # the kernels use the updated weights: rollout through the same handle == oracle on the updated weights
+    m.eval()
+    x0 = torch.from_numpy(synth.normal_embeds((5, 1, cfg.n_embd), 730))
+    new_sd = {k: v.detach() for k, v in sd.items()}
+    ref, _ = O.gpt2_generate(new_sd, cfg, x0, 20, use_cache=True)
+    out = m.generate(x0.to(dev), max_length=20, use_cache=True)[0]
+    assert O.rel_l2(out.cpu(), ref) < TOL

@@ -2353,6 +2353,27 @@ int ensure_kv(trpx_gpt2_t h, size_t bytes) {
 // =================================================================================================
 // C ABI
 // =================================================================================================
+namespace {
+// images derived from the packed blob: XOR-swizzled copy for the tensor-core kernel, per-(layer, rank) slices for the
+// cluster kernel
+int derive_weight_images(trpx_gpt2_t h, cudaStream_t st) {
+    const Gpt2Layout& L = h->lay;
+    const int E = L.E;
+    if (E == 32) {
+        swizzle_weights_kernel<<<64, 256, 0, st>>>(h->blob, h->blob_sw, L);
+        TRPX_CUDA(cudaGetLastError());
+    }
+    if (E % (CLS * 4) == 0) {
+        const ClusterLayout cl = ClusterLayout::make(E);
+        const size_t n = (size_t)(L.n_layer + 1) * CLS * ((size_t)cl.att_size + cl.mlp_size);
+        if (h->img_cl == nullptr) TRPX_CUDA(cudaMalloc(&h->img_cl, n * sizeof(float)));
+        cluster_image_kernel<<<256, 256, 0, st>>>(h->blob, h->img_cl, L, cl);
+        TRPX_CUDA(cudaGetLastError());
+    }
+    return TRPX_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int trpx_gpt2_create(const trpx_gpt2_config* cfg, int device, trpx_gpt2_t* out) {
@@ -2399,6 +2420,18 @@ int trpx_gpt2_destroy(trpx_gpt2_t h) {
     return TRPX_OK;
 }
 
+/* Weights as ONE packed blob in the layout of gpt2_layout.cuh (what trpx_gpt2_train_fwd_bwd's gradient uses): the
+ * fused optimizer keeps its master copy in this layout and hands it over after every step. */
+int trpx_gpt2_load_blob(trpx_gpt2_t h, const float* blob_dev, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "load the weights once with trpx_gpt2_load_weights first");
+    TRPX_REQUIRE(blob_dev != nullptr, "null blob");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TRPX_CUDA(cudaMemcpyAsync(h->blob, blob_dev, sizeof(float) * h->lay.total, cudaMemcpyDeviceToDevice, st));
+    return derive_weight_images(h, st);
+}
+
 int trpx_gpt2_num_weight_tensors(trpx_gpt2_t h) { return valid(h) ? 12 * h->cfg.n_layer + 4 : -1; }
 
 int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const float* pe_dev, void* stream) {
@@ -2427,16 +2460,9 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
     transpose_kernel<<<(E * E + 255) / 256, 256, 0, st>>>(g[2], h->blob + L.wf, E, E);   // [out][in] -> [in][out]
     TRPX_CUDA(cudaGetLastError());
     TRPX_CUDA(cp(L.bf, g[3], E));
-    if (E == 32) {
-        swizzle_weights_kernel<<<64, 256, 0, st>>>(h->blob, h->blob_sw, L);
-        TRPX_CUDA(cudaGetLastError());
-    }
-    if (E % (CLS * 4) == 0) {
-        const ClusterLayout cl = ClusterLayout::make(E);
-        const size_t n = (size_t)(L.n_layer + 1) * CLS * ((size_t)cl.att_size + cl.mlp_size);
-        if (h->img_cl == nullptr) TRPX_CUDA(cudaMalloc(&h->img_cl, n * sizeof(float)));
-        cluster_image_kernel<<<256, 256, 0, st>>>(h->blob, h->img_cl, L, cl);
-        TRPX_CUDA(cudaGetLastError());
+    {
+        int rc = derive_weight_images(h, st);
+        if (rc) return rc;
     }
     if (pe_dev != nullptr) {
         TRPX_CUDA(cudaMemcpyAsync(h->pe, pe_dev, sizeof(float) * L.n_ctx * E, cudaMemcpyDeviceToDevice, st));

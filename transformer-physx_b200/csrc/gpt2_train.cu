@@ -20,7 +20,7 @@ using namespace trpx;
 
 namespace {
 
-constexpr int TR_THREADS = 256;
+constexpr int TR_THREADS = 1024;     // the step is a chain of small latency-bound tile operations: more threads = shorter chain
 
 struct TrainParams {
     const float* blob;
@@ -47,24 +47,54 @@ __device__ __forceinline__ float gelu_new_grad(float x) {
 
 // Y[t][n] = bias[n] + sum_k X[t][k] * W[k*N + n]            X: smem [T][K], W: global [K][N]
 __device__ void mm_xw(float* Y, const float* X, const float* __restrict__ W, const float* __restrict__ bias, int T,
-                      int K, int N) {
+                      int K, int N, int ldy = 0) {
+    if (ldy == 0) ldy = N;
     for (int idx = threadIdx.x; idx < T * N; idx += blockDim.x) {
         const int t = idx / N, n = idx - t * N;
         float acc = bias ? __ldg(bias + n) : 0.f;
         const float* xr = X + t * K;
+#pragma unroll 8
         for (int k = 0; k < K; k++) acc = fmaf(xr[k], __ldg(W + (size_t)k * N + n), acc);
-        Y[idx] = acc;
+        Y[t * ldy + n] = acc;
     }
 }
 // dX[t][k] = sum_n dY[t][n] * W[k*N + n]                     dY: smem [T][N]
-__device__ void mm_xwT(float* dX, const float* dY, const float* __restrict__ W, int T, int K, int N) {
-    for (int idx = threadIdx.x; idx < T * K; idx += blockDim.x) {
-        const int t = idx / K, k = idx - t * K;
-        float acc = 0.f;
-        const float* dr = dY + t * N;
-        const float* wr = W + (size_t)k * N;
-        for (int n = 0; n < N; n++) acc = fmaf(dr[n], __ldg(wr + n), acc);
-        dX[idx] = acc;
+// W rows are contiguous along n, the outputs want lanes along k: column chunks of W are staged TRANSPOSED in shared
+// memory (`stage`, STAGE_FLOATS floats, row stride K+1: conflict-free for both the transposing store and the read),
+// so every global read is coalesced.  A thread owns up to MAXO outputs (t, k) and keeps them in registers across
+// the chunks.  All threads must call; synchronises internally.
+constexpr int STAGE_FLOATS = 8192 + 512;
+template <int MAXO>
+__device__ void mm_xwT(float* dX, const float* dY, const float* __restrict__ W, int T, int K, int N, float* stage) {
+    const int NC = min(N, 8192 / K);                 // columns per chunk
+    float acc[MAXO];
+#pragma unroll
+    for (int o = 0; o < MAXO; o++) acc[o] = 0.f;
+    for (int n0 = 0; n0 < N; n0 += NC) {
+        const int nc = min(NC, N - n0);
+        __syncthreads();                              // previous chunk fully consumed
+        for (int i = threadIdx.x; i < K * nc; i += blockDim.x) {
+            const int k = i / nc, nn = i - k * nc;
+            stage[nn * (K + 1) + k] = __ldg(W + (size_t)k * N + n0 + nn);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < MAXO; o++) {
+            const int idx = threadIdx.x + o * blockDim.x;
+            if (idx < T * K) {
+                const int t = idx / K, k = idx - t * K;
+                const float* dr = dY + t * N + n0;
+                float a = acc[o];
+#pragma unroll 8
+                for (int nn = 0; nn < nc; nn++) a = fmaf(dr[nn], stage[nn * (K + 1) + k], a);
+                acc[o] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < MAXO; o++) {
+        const int idx = threadIdx.x + o * blockDim.x;
+        if (idx < T * K) dX[idx] = acc[o];
     }
 }
 // dW[k*N + n] = sum_t X[t][k] * dY[t][n] ; db[n] = sum_t dY[t][n]      (written, not accumulated)
@@ -72,6 +102,7 @@ __device__ void mm_xTy(float* dW, float* db, const float* X, const float* dY, in
     for (int idx = threadIdx.x; idx < K * N; idx += blockDim.x) {
         const int k = idx / N, n = idx - k * N;
         float acc = 0.f;
+#pragma unroll 8
         for (int t = 0; t < T; t++) acc = fmaf(X[t * K + k], dY[t * N + n], acc);
         dW[idx] = acc;
     }
@@ -148,14 +179,24 @@ __device__ void tile_store(float* __restrict__ dst, const float* src, int n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
-// causal softmax row i of head hh:  P[i][j] = softmax_{j<=i}(q_i . k_j / sqrt(hd)), 0 for j > i
+// [T][n] <-> [T][ld] (padded rows)
+__device__ void tile_load_ld(float* dst, int ld, const float* __restrict__ src, int T, int n) {
+    for (int i = threadIdx.x; i < T * n; i += blockDim.x) dst[(i / n) * ld + (i % n)] = src[i];
+}
+__device__ void tile_store_ld(float* __restrict__ dst, const float* src, int ld, int T, int n) {
+    for (int i = threadIdx.x; i < T * n; i += blockDim.x) dst[i] = src[(i / n) * ld + (i % n)];
+}
+
+// causal softmax row i of head hh (q|k|v tile with row stride LQ = 3E+1: lanes walk rows j, so an unpadded stride of
+// 3E = 0 mod 32 would put every lane on the same bank):  P[i][j] = softmax_{j<=i}(q_i . k_j / sqrt(hd)), 0 for j > i
 // (attention.py:97-109: masked logits are -1e4, whose exp underflows to exactly 0 in FP32)
 __device__ __forceinline__ void attn_row(const float* qkv, int i, int hh, int T, int E, int hd, float* Prow, int lane) {
     const float scale = sqrtf((float)hd);
-    const float* q = qkv + i * 3 * E + hh * hd;
+    const int LQ = 3 * E + 1;
+    const float* q = qkv + i * LQ + hh * hd;
     float m = -INFINITY;
     for (int j = lane; j <= i; j += 32) {
-        const float* k = qkv + j * 3 * E + E + hh * hd;
+        const float* k = qkv + j * LQ + E + hh * hd;
         float s = 0.f;
         for (int d = 0; d < hd; d++) s = fmaf(q[d], k[d], s);
         s = s / scale;
@@ -180,6 +221,7 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
     const Gpt2Layout& L = p.lay;
     const int E = L.E, H = L.n_head, hd = L.hd, T = p.T, NL = L.n_layer;
     const int TE = T * E;
+    const int LQ = 3 * E + 1;              // row stride of the q|k|v tile (see attn_row)
     float* h = sm;                         // [T][E]   residual (forward) / its gradient (backward)
     float* t0 = h + TE;                    // four [T][4E] work tiles
     float* t1 = t0 + 4 * TE;
@@ -187,6 +229,7 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
     float* t3 = t2 + 4 * TE;
     float* P = t3 + 4 * TE;                // [max(T, warps)][T]  (forward: one scratch row per warp)
     float* dS = P + max(T, TR_THREADS / 32) * T;   // [T][T]
+    float* stage = dS + T * T;             // [STAGE_FLOATS] transposed weight chunks (mm_xwT)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
     const int b = blockIdx.x;
     const size_t per_layer = (size_t)12 * TE;
@@ -208,16 +251,16 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
         ln_fwd(t0, h, w + L.ln1w, w + L.ln1b, T, E, p.eps);
         __syncthreads();
         tile_store(sv + O_A1 * TE, t0, TE);
-        mm_xw(t1, t0, w + L.wqkv, w + L.bqkv, T, E, 3 * E);            // [T][3E] rows q|k|v
+        mm_xw(t1, t0, w + L.wqkv, w + L.bqkv, T, E, 3 * E, LQ);        // [T][LQ] rows q|k|v (padded)
         __syncthreads();
-        tile_store(sv + O_QKV * TE, t1, 3 * TE);
+        tile_store_ld(sv + O_QKV * TE, t1, LQ, T, 3 * E);
         for (int pair = warp; pair < T * H; pair += nw) {
             const int i = pair / H, hh = pair - i * H;
             float* Prow = P + (size_t)warp * T;                         // per-warp scratch row (nw <= T rows used)
             attn_row(t1, i, hh, T, E, hd, Prow, lane);
             for (int d = lane; d < hd; d += 32) {
                 float acc = 0.f;
-                for (int j = 0; j <= i; j++) acc = fmaf(Prow[j], t1[j * 3 * E + 2 * E + hh * hd + d], acc);
+                for (int j = 0; j <= i; j++) acc = fmaf(Prow[j], t1[j * LQ + 2 * E + hh * hd + d], acc);
                 t2[i * E + hh * hd + d] = acc;
             }
             __syncwarp();
@@ -268,7 +311,7 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
     // ============================== backward ==============================
     // head: y = a_f Wf + bf ; a_f = LN_f(h_L)
     mm_xTy(gp + L.wf, gp + L.bf, t0, t1, T, E, E);
-    mm_xwT(t2, t1, p.blob + L.wf, T, E, E);                             // d a_f
+    mm_xwT<2>(t2, t1, p.blob + L.wf, T, E, E, stage);                   // d a_f
     tile_load(t3, sv_f, TE);                                            // h_L
     __syncthreads();
     ln_bwd(h, false, t3, t2, p.blob + L.lnfw, gp + L.lnfw, gp + L.lnfb, T, E, p.eps);
@@ -283,23 +326,23 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
         for (int i = tid; i < 4 * TE; i += blockDim.x) t2[i] = gelu_new(t1[i]);
         __syncthreads();
         mm_xTy(g + L.wpr, g + L.bpr, t2, h, T, 4 * E, E);
-        mm_xwT(t0, h, w + L.wpr, T, 4 * E, E);                          // d gelu_out [T][4E]
+        mm_xwT<8>(t0, h, w + L.wpr, T, 4 * E, E, stage);                // d gelu_out [T][4E]
         __syncthreads();
         for (int i = tid; i < 4 * TE; i += blockDim.x) t0[i] *= gelu_new_grad(t1[i]);     // d fc_pre
         tile_load(t2, sv + O_A2 * TE, TE);
         __syncthreads();
         mm_xTy(g + L.wfc, g + L.bfc, t2, t0, T, E, 4 * E);
-        mm_xwT(t1, t0, w + L.wfc, T, E, 4 * E);                         // d a2 [T][E]
+        mm_xwT<2>(t1, t0, w + L.wfc, T, E, 4 * E, stage);               // d a2 [T][E]
         tile_load(t3, sv + O_XMID * TE, TE);
         __syncthreads();
         ln_bwd(h, true, t3, t1, w + L.ln2w, g + L.ln2w, g + L.ln2b, T, E, p.eps);
         __syncthreads();
         // ---- attention block: x_mid = x_in + att Wproj + bproj ----
         tile_load(t0, sv + O_ATT * TE, TE);
-        tile_load(t2, sv + O_QKV * TE, 3 * TE);
+        tile_load_ld(t2, LQ, sv + O_QKV * TE, T, 3 * E);
         __syncthreads();
         mm_xTy(g + L.wproj, g + L.bproj, t0, h, T, E, E);
-        mm_xwT(t1, h, w + L.wproj, T, E, E);                            // d att [T][E]
+        mm_xwT<2>(t1, h, w + L.wproj, T, E, E, stage);                  // d att [T][E]
         __syncthreads();
         // per head: P, dS in shared memory, then dq, dk, dv into t3 ([T][3E])
         const float rscale = 1.0f / sqrtf((float)hd);
@@ -311,7 +354,7 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
                 const float* doi = t1 + i * E + hh * hd;
                 float rs = 0.f;
                 for (int j = lane; j <= i; j += 32) {
-                    const float* v = t2 + j * 3 * E + 2 * E + hh * hd;
+                    const float* v = t2 + j * LQ + 2 * E + hh * hd;
                     float dp = 0.f;
                     for (int d = 0; d < hd; d++) dp = fmaf(doi[d], v[d], dp);
                     dS[i * T + j] = dp;
@@ -325,11 +368,11 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
                 const int r = idx / hd, d = idx - r * hd;
                 // dq_r = sum_{j<=r} dS_rj k_j / sqrt(hd)
                 float dq = 0.f;
-                for (int j = 0; j <= r; j++) dq = fmaf(dS[r * T + j], t2[j * 3 * E + E + hh * hd + d], dq);
+                for (int j = 0; j <= r; j++) dq = fmaf(dS[r * T + j], t2[j * LQ + E + hh * hd + d], dq);
                 // dk_r = sum_{i>=r} dS_ir q_i / sqrt(hd) ; dv_r = sum_{i>=r} P_ir d_o_i
                 float dk = 0.f, dv = 0.f;
                 for (int i = r; i < T; i++) {
-                    dk = fmaf(dS[i * T + r], t2[i * 3 * E + hh * hd + d], dk);
+                    dk = fmaf(dS[i * T + r], t2[i * LQ + hh * hd + d], dk);
                     dv = fmaf(P[i * T + r], t1[i * E + hh * hd + d], dv);
                 }
                 t3[r * 3 * E + hh * hd + d] = dq * rscale;
@@ -341,7 +384,7 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
         tile_load(t0, sv + O_A1 * TE, TE);
         __syncthreads();
         mm_xTy(g + L.wqkv, g + L.bqkv, t0, t3, T, E, 3 * E);
-        mm_xwT(t1, t3, w + L.wqkv, T, E, 3 * E);                        // d a1 [T][E]
+        mm_xwT<2>(t1, t3, w + L.wqkv, T, E, 3 * E, stage);              // d a1 [T][E]
         tile_load(t2, sv + O_XIN * TE, TE);
         __syncthreads();
         ln_bwd(h, true, t2, t1, w + L.ln1w, g + L.ln1w, g + L.ln1b, T, E, p.eps);
@@ -380,7 +423,8 @@ int trpx_gpt2_train_fwd_bwd(trpx_gpt2_t h, const float* x, const float* labels, 
     const Gpt2Layout& L = h->lay;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t TE = (size_t)T * L.E;
-    const size_t smem = sizeof(float) * (TE * 17 + ((size_t)std::max(T, TR_THREADS / 32) + T) * T);
+    TRPX_REQUIRE(TE <= 2 * TR_THREADS, "training step supports T * n_embd <= %d", 2 * TR_THREADS);
+    const size_t smem = sizeof(float) * (TE * 17 + ((size_t)std::max(T, TR_THREADS / 32) + T) * T + STAGE_FLOATS);
     TRPX_REQUIRE(smem + 1024 <= (size_t)h->smem_optin, "training step needs %zu B of shared memory per sequence", smem);
     const size_t acts_per_seq = (size_t)L.n_layer * 12 * TE + 2 * TE;
     const size_t need = sizeof(float) * ((size_t)B * (acts_per_seq + L.total + 1));

@@ -32,6 +32,7 @@ SIGNATURES = {
     "trpx_probe_tf32_mma": (c_int, [c_int, POINTER(c_float)]),
     "trpx_gpt2_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trpx_gpt2_blob_size": (c_int, [c_void_p]),
+    "trpx_gpt2_load_blob": (c_int, [c_void_p, c_void_p, c_void_p]),
     "trpx_probe_window_stream": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float),
                                          POINTER(c_float)]),
     "trpx_gpt2_create": (c_int, [POINTER(Gpt2Config), c_int, POINTER(c_void_p)]),

@@ -98,3 +98,57 @@ class FusedKoopmanStep:
                                        N.stream_ptr(dev)))
         N.bump_weight_epoch()
         return self.loss2
+
+
+class FusedTransformerStep:
+    """One teacher-forced transformer training step with minimal host work.  Equivalent to the step
+    body of trphysx/utils/trainer.py:193-207,244-277 (`loss = model(**inputs)[0]; loss.backward();
+    clip_grad_norm_(max_grad_norm); optimizer.step(); zero_grad()` with torch.optim.Adam), but: the fused
+    forward+backward writes the gradient as one blob, (data parallel) ONE all-reduce averages it, clip + Adam update
+    the master parameters — kept in the same packed layout — in two launches, and the updated blob is handed to the
+    kernels with one device copy.  The module's parameters are views of the master buffer, so state_dict(), save_model()
+    and evaluate()/generate() see the current weights."""
+
+    def __init__(self, transformer, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0,
+                 world_size: int = 1):
+        self.model, self.world = transformer, world_size
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        params = transformer._weight_list()
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise NotImplementedError("FusedTransformerStep runs on CUDA devices only (no CPU fallback)")
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.loss = torch.zeros((), device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, view in zip(params, transformer._blob_views(self.flat)):
+                view.copy_(p.detach())
+                p.data = view                      # mlp_f.weight becomes a transposed view: same values, blob strides
+        self.step_count = 0
+        N.bump_weight_epoch()
+
+    @torch.no_grad()
+    def __call__(self, inputs_embeds: torch.Tensor, labels_embeds: torch.Tensor) -> torch.Tensor:
+        """inputs_embeds, labels_embeds: [B, T, n_embd] on the model's device.  Returns the loss (device scalar)."""
+        x = N.require_cuda_f32(inputs_embeds, "inputs_embeds")
+        y = N.require_cuda_f32(labels_embeds, "labels_embeds")
+        dev = x.device
+        lib = N.lib()
+        h = self.model._handle(dev)
+        N.check(lib.trpx_gpt2_train_fwd_bwd(h, x.data_ptr(), y.data_ptr(), x.size(0), x.size(1), self.loss.data_ptr(),
+                                            None, self.grad.data_ptr(), N.stream_ptr(dev)))
+        if self.world > 1:
+            from .parallel import average_flat_grad
+            average_flat_grad(self.grad, self.world)
+        self.step_count += 1
+        N.check(lib.trpx_clip_adam(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                   self.flat.numel(), self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
+                                   self.weight_decay, self.max_norm, self.norm.data_ptr(),
+                                   dev.index if dev.index is not None else torch.cuda.current_device(),
+                                   N.stream_ptr(dev)))
+        N.check(lib.trpx_gpt2_load_blob(h, self.flat.data_ptr(), N.stream_ptr(dev)))
+        return self.loss

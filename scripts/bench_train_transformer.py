@@ -16,7 +16,14 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--cpu", action="store_true", help="also time the oracle port (torch CPU autograd) at the first batch size")
 a = ap.parse_args()
 from trphysx_b200.transformer import PhysformerTrain
-dev = torch.device("cuda:0")
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+if world > 1:                                   # data parallel: one process per GPU, ONE all-reduce of the gradient blob
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dev = torch.device("cuda", local)
 cfg = synth.make_config(a.kind)
 T = cfg.n_ctx
 for B in [int(b) for b in a.batches.split(",")]:
@@ -39,12 +46,12 @@ for B in [int(b) for b in a.batches.split(",")]:
 
     from trphysx_b200.optim import FusedTransformerStep
     m2 = make_gpt2(cfg, 2025, False, dev)
-    fstep = FusedTransformerStep(m2.train(), lr=1e-3, weight_decay=1e-10, max_norm=0.1)
+    fstep = FusedTransformerStep(m2.train(), lr=1e-3, weight_decay=1e-10, max_norm=0.1, world_size=world)
 
     def fused_step():
         return fstep(x, y)
 
-    res = {"kind": a.kind, "B": B, "T": T}
+    res = {"kind": a.kind, "B_per_gpu": B, "T": T, "n_gpus": world}
     for name, fn in (("step_ms", step), ("fused_fwd_bwd_ms", fwd_bwd_only), ("fused_step_ms", fused_step)):
         for _ in range(3):
             fn()
@@ -56,7 +63,7 @@ for B in [int(b) for b in a.batches.split(",")]:
         e1.record()
         torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / a.iters
-    res["tokens_per_s"] = B * T / (res["fused_step_ms"] * 1e-3)
+    res["tokens_per_s"] = world * B * T / (res["fused_step_ms"] * 1e-3)
     res["loss_after"] = float(l)
     if a.cpu and B == int(a.batches.split(",")[0]):
         from oracle import trpx_oracle as O
@@ -69,4 +76,7 @@ for B in [int(b) for b in a.batches.split(",")]:
             O.gpt2_train_grads(sd, cfg, xc, yc)
         res["cpu_port_fwd_bwd_ms"] = (time.perf_counter() - t0) / 5 * 1e3
         res["cpu_threads"] = os.cpu_count()
-    print(json.dumps(res), flush=True)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+if world > 1:
+    dist.destroy_process_group()

@@ -241,10 +241,11 @@ def test_full_size_properties(dev):
     B, S = 8192, 256
     x0 = torch.from_numpy(synth.normal_embeds((B, 1, 32), 4242)).to(dev)
     full = m.generate(x0, max_length=S + 1, use_cache=True, return_presents=False)[0]
-    assert m.last_launch()["variant"] == 2 and m.last_launch()["group"] == 4
+    G = m.last_launch()["group"]
+    assert m.last_launch()["variant"] == 2 and G == 8        # n_ctx = 32 with the window: 8 trajectories per warp
     assert torch.isfinite(full).all()
     idx = torch.arange(0, B, 32, device=dev)
-    m.set_rollout_tuning(traj_per_warp=4)
+    m.set_rollout_tuning(traj_per_warp=G)
     same_group = m.generate(x0[idx], max_length=S + 1, use_cache=True, return_presents=False)[0]
     assert torch.equal(same_group, full[idx])
     m.set_rollout_tuning(traj_per_warp=2)

@@ -422,7 +422,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
                                               float* outT, int lane) {
     constexpr int P = 8 / G;
     constexpr int NS = NCTX / P;                      // slots per lane
-    constexpr int BS = (G == 4 && NS <= 32) ? (NS < 16 ? NS : 16) : (NS >= 64 ? 4 : (NS < 8 ? NS : 8));   // rows in flight per lane
+    constexpr int BS = (G >= 4 && NS <= 32) ? (NS < 16 ? NS : 16) : (NS >= 64 ? 4 : (NS < 8 ? NS : 8));   // rows in flight per lane
     const int part = lane % P, gh = lane / P, hh = gh & 3, g = gh >> 2;
     float q[8];
     {
@@ -516,7 +516,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
 }
 
 template <int G, int MAXI, bool CACHE>
-__global__ void __launch_bounds__((CACHE && G == 4) ? 256 : 384, 1) rollout_e32_kernel(RolloutParams p) {
+__global__ void __launch_bounds__((CACHE && G >= 4) ? 256 : 384, 1) rollout_e32_kernel(RolloutParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(8) uint64_t bar;
     const Gpt2Layout& L = p.lay;
@@ -2618,11 +2618,11 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             // measured (profiles/r01_sweep_*): with the KV window 4 trajectories per warp (two lanes per
             // (trajectory, head) pair, smaller in-flight window set) beat 8; without it 8 amortise the weights best.
             // Shrink the group further when the batch is too small to give every SM ~4 warps.
-            G = use_cache ? 4 : 8;
+            G = (use_cache && L.n_ctx > 32) ? 4 : 8;     // n_ctx <= 32: 8 with 16 rows in flight measured 3 % ahead of 4
             while (G > 1 && (long long)(B + G - 1) / G < (long long)sms * 4) G >>= 1;
         }
         const int ngroups = (B + G - 1) / G;
-        const int max_w = (int)std::min<size_t>((use_cache && G == 4) ? 8 : 12,
+        const int max_w = (int)std::min<size_t>((use_cache && G >= 4) ? 8 : 12,
                                                 ((size_t)h->smem_optin - 1024 - wbytes) / ((size_t)64 * G * sizeof(float)));
         if (max_w < 1) {
             use_e32 = false;

@@ -150,6 +150,11 @@ int trpx_mlpemb_load_weights(trpx_mlpemb_t h, const float* const* w_dev, int n_t
 int trpx_mlpemb_embed(trpx_mlpemb_t h, const float* x_dev, float* g_dev, long long N, void* stream);
 /* LorenzEmbedding.recover (:107-118): g[N,32] -> x[N,3] */
 int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g_dev, float* x_dev, long long N, void* stream);
+/* Fused `recover` + MSE of Trainer.eval_states (trphysx/utils/trainer.py:380-390):
+ * mse = mean((recover(g) - target)^2) over N*3 values, written to mse_dev (device scalar).  The recovered states
+ * are written only if states_or_null is given ([N][3]).  Deterministic (per-CTA sums added in a fixed order). */
+int trpx_mlpemb_recover_mse(trpx_mlpemb_t h, const float* g_dev, const float* target_dev, long long N,
+                            float* states_or_null, float* mse_dev, void* stream);
 /* LorenzEmbedding.koopmanOperation (:120-142) as a banded matvec: g[N,32] -> g'[N,32] */
 int trpx_mlpemb_koopman(trpx_mlpemb_t h, const float* g_dev, float* gnext_dev, long long N, void* stream);
 /* LorenzEmbedding.koopmanOperator (:144-157): dense K[32,32] */

@@ -188,3 +188,29 @@ def test_fused_koopman_step_equals_autograd_step(dev):
         outs.append((float(loss), torch.cat([p.detach().reshape(-1) for p in head.parameters()]).clone()))
     assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[0][0])
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("kind", ["lorenz", "rossler"])
+def test_eval_states_fused_recover_mse(dev, kind):
+    """Trainer.eval_states (utils/trainer.py:380-390): MSELoss()(recover(pred).view(B,T,3), states), here in one
+    launch without writing the states; against the oracle's recover + torch MSE, ragged N, and the optional states."""
+    from trphysx_b200.evaluation import eval_states, embed_series
+    cfg = synth.make_config(kind)
+    w = synth.lorenz_embedding_weights(cfg, 812)
+    emb = make_lorenz(cfg, 812, kind, dev)
+    B, T = 37, 29                                     # N = 1073: not a multiple of anything
+    g = torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), 813))
+    states = torch.from_numpy(synth.normal_embeds((B, T, 3), 814)) * 3.0
+    ref_states = O.lorenz_recover(O.to_torch(w), cfg, g.view(-1, cfg.n_embd)).view(B, T, 3)
+    ref = torch.nn.functional.mse_loss(ref_states, states)
+    err = eval_states(emb, g.to(dev), states.to(dev))
+    assert err.dim() == 0 and abs(float(err) - float(ref)) <= 2e-6 * float(ref)
+    err2, rec = eval_states(emb, g.to(dev), states.to(dev), return_states=True)
+    assert float(err2) == float(err) and rec.shape == (B, T, 3)
+    assert O.rel_l2(rec.cpu(), ref_states) < TOL
+    # bulk embedding of a whole series in one call (dataset_lorenz.py:22-47)
+    series = torch.from_numpy(synth.lorenz_trajectories(8, 40, seed=5) if kind == "lorenz"
+                              else synth.rossler_trajectories(8, 40, seed=5))
+    ge = embed_series(emb, series.to(dev))
+    assert ge.shape == (8, 41, cfg.n_embd)
+    assert O.rel_l2(ge.cpu().view(-1, cfg.n_embd), O.lorenz_embed(O.to_torch(w), cfg, series.view(-1, 3))) < TOL

@@ -135,9 +135,15 @@ __global__ void __launch_bounds__(EMB_THREADS) mlp_embed_kernel(const float* __r
 }
 
 // ---- K3b: recover  g[N,32] -> x[N,3] ------------------------------------------------------------------
+// With `target` != null the kernel is the fused `recover + MSE` of Trainer.eval_states (utils/trainer.py:380-390): the
+// recovered states are not written (x may be null); each CTA writes the sum of squared errors of its samples to
+// partial[blockIdx.x] (summed in a fixed order by sum_partials_kernel: deterministic).
 __global__ void __launch_bounds__(EMB_THREADS) mlp_recover_kernel(const float* __restrict__ blob, MlpLayout L,
                                                                   const float* __restrict__ g, float* __restrict__ x,
-                                                                  long long N) {
+                                                                  long long N, const float* __restrict__ target,
+                                                                  float* __restrict__ partial) {
+    __shared__ float red[EMB_THREADS / 32];
+    float sq = 0.f;
     extern __shared__ float4 sm4[];
     const int Hd = L.Hd;
     float4* sA = sm4;                 // [Hd][8]  V1 rows
@@ -193,9 +199,33 @@ __global__ void __launch_bounds__(EMB_THREADS) mlp_recover_kernel(const float* _
         for (int s = 0; s < SPT; s++) {
             if (base + s >= N) break;
 #pragma unroll
-            for (int c = 0; c < MS; c++)                     // _unnormalize, embedding_lorenz.py:162-163
-                x[(base + s) * MS + c] = __ldg(blob + L.sd + c) * y[s][c] + __ldg(blob + L.mu + c);
+            for (int c = 0; c < MS; c++) {                   // _unnormalize, embedding_lorenz.py:162-163
+                const float v = __ldg(blob + L.sd + c) * y[s][c] + __ldg(blob + L.mu + c);
+                if (x != nullptr) x[(base + s) * MS + c] = v;
+                if (target != nullptr) {
+                    const float d = v - target[(base + s) * MS + c];
+                    sq = fmaf(d, d, sq);
+                }
+            }
         }
+    }
+    if (partial != nullptr) {
+        sq = warp_sum(sq);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < EMB_THREADS / 32; i++) t += red[i];
+            partial[blockIdx.x] = t;
+        }
+    }
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < n; i++) t += partial[i];
+        out[0] = t * scale;
     }
 }
 
@@ -316,6 +346,7 @@ int trpx_mlpemb_destroy(trpx_mlpemb_t h) {
     DeviceGuard guard(h->device);
     cudaFree(h->blob);
     cudaFree(h->ws);
+    cudaFree(h->mse_partial);
     h->magic = 0;
     delete h;
     return TRPX_OK;
@@ -382,7 +413,32 @@ int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g, float* x, long long N, 
     const MlpLayout L = MlpLayout::make(h->cfg.hidden);
     const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
     TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_recover_kernel<<<emb_grid(h, N, 3), EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, g, x, N);
+    mlp_recover_kernel<<<emb_grid(h, N, 3), EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, g, x, N, nullptr,
+                                                                                        nullptr);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int trpx_mlpemb_recover_mse(trpx_mlpemb_t h, const float* g, const float* target, long long N, float* states_or_null,
+                            float* mse_dev, void* stream) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    if (!h->loaded) return set_error(TRPX_E_STATE, "weights not loaded");
+    TRPX_REQUIRE(N >= 1 && g != nullptr && target != nullptr && mse_dev != nullptr, "bad arguments");
+    DeviceGuard guard(h->device);
+    const MlpLayout L = MlpLayout::make(h->cfg.hidden);
+    const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
+    const int grid = emb_grid(h, N, 3);
+    if (h->mse_partial == nullptr || h->mse_partial_n < grid) {
+        if (h->mse_partial) TRPX_CUDA(cudaFree(h->mse_partial));
+        h->mse_partial = nullptr;
+        TRPX_CUDA(cudaMalloc(&h->mse_partial, sizeof(float) * grid));
+        h->mse_partial_n = grid;
+    }
+    TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_recover_kernel<<<grid, EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, g, states_or_null, N, target,
+                                                                           h->mse_partial);
+    TRPX_CUDA(cudaGetLastError());
+    sum_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->mse_partial, grid, 1.0f / ((float)N * (float)MS), mse_dev);
     TRPX_CUDA(cudaGetLastError());
     return TRPX_OK;
 }

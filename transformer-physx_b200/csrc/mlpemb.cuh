@@ -14,6 +14,8 @@ struct trpx_mlpemb {
     // training workspace (mlpemb_train.cu)
     float* ws = nullptr;
     size_t ws_bytes = 0;
+    float* mse_partial = nullptr; // per-CTA squared-error sums of the fused recover + MSE
+    int mse_partial_n = 0;
 };
 
 namespace trpx {

@@ -96,6 +96,21 @@ class LorenzEmbedding(EmbeddingModel):
                                             N.stream_ptr(g.device)))
         return x
 
+    def recover_mse(self, g: Tensor, states: Tensor, return_states: bool = False):
+        """MSELoss()(recover(g), states) in one launch without materialising the recovered states — the computation
+        of `Trainer.eval_states` (trphysx/utils/trainer.py:380-390).  g: [N, n_embd]; states: [N, 3] (any leading
+        shape with N*3 values).  Returns the MSE (device scalar) [and the recovered states [N, 3]]."""
+        self._inference_only("recover_mse")
+        g = N.require_cuda_f32(g, "g")
+        states = N.require_cuda_f32(states, "states")
+        assert g.dim() == 2 and g.size(1) == self.obsdim and states.numel() == g.size(0) * self.config.state_dims[0]
+        mse = torch.empty((), device=g.device, dtype=torch.float32)
+        out = torch.empty((g.size(0), self.config.state_dims[0]), device=g.device) if return_states else None
+        N.check(N.lib().trpx_mlpemb_recover_mse(self._handle(g.device), g.data_ptr(), states.data_ptr(), g.size(0),
+                                                out.data_ptr() if return_states else None, mse.data_ptr(),
+                                                N.stream_ptr(g.device)))
+        return (mse, out) if return_states else mse
+
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor]:
         """(g, xhat) = (embed(x), recover(embed(x)))  (embedding_lorenz.py:74-92)"""
         g = self.embed(x)

@@ -125,3 +125,37 @@ def test_shard_bounds_partition():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(4, 2, 2)
+
+
+def test_blob_views_cover_the_packed_layout():
+    """Gradient / master-parameter blob (csrc/gpt2_layout.cuh) <-> parameters in `_weight_list()` order: every view
+    has its parameter's shape, the views tile the blob exactly, and mlp_f.weight is the transposed one."""
+    for cfgc in (LorenzConfig, CylinderConfig):
+        m = PhysformerGPT2(cfgc(), "x")
+        params = m._weight_list()
+        total = sum(p.numel() for p in params)
+        E, nl = m.config.n_embd, m.config.n_layer
+        assert total == nl * (12 * E * E + 13 * E) + E * E + 3 * E
+        blob = torch.arange(total, dtype=torch.float32)
+        views = m._blob_views(blob)
+        assert len(views) == len(params)
+        for p, v in zip(params, views):
+            assert tuple(p.shape) == tuple(v.shape)
+        assert views[-2].stride() == (1, E) and views[-2][3, 5] == blob[total - E - E * E + 5 * E + 3]
+        assert all(v.is_contiguous() for v in views[:-2]) and views[-1].is_contiguous()
+
+
+def test_training_entry_points_refuse_cpu():
+    """The fused training step and the fused eval_states have no CPU path either."""
+    from trphysx_b200.evaluation import eval_states
+    from trphysx_b200.optim import FusedTransformerStep
+    m = PhysformerGPT2(RosslerConfig(), "rossler")
+    with pytest.raises(NotImplementedError):
+        FusedTransformerStep(m)
+    head = PhysformerTrain(RosslerConfig(), m).train()
+    x = torch.zeros(2, 4, 32)
+    with pytest.raises(NotImplementedError):
+        head(inputs_embeds=x, labels_embeds=x)
+    emb = RosslerEmbedding(RosslerConfig())
+    with pytest.raises(NotImplementedError):
+        eval_states(emb, x, torch.zeros(2, 4, 3))

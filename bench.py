@@ -114,7 +114,7 @@ class ClockSampler:
 
 
 def build_modules(kind, device):
-    from oracle import synth
+    from tests import synth
     from tests.util import make_gpt2, make_lorenz
     cfg = synth.make_config(kind)
     emb = make_lorenz(cfg, 2024, "lorenz" if kind == "lorenz" else "rossler", device)
@@ -123,7 +123,7 @@ def build_modules(kind, device):
 
 
 def initial_states(kind, n, seed):
-    from oracle import synth
+    from tests import synth
     gen = synth.lorenz_trajectories if kind == "lorenz" else synth.rossler_trajectories
     return torch.from_numpy(gen(n, 1, seed=seed)[:, 0].copy())
 
@@ -131,7 +131,8 @@ def initial_states(kind, n, seed):
 # ----------------------------------------------------------------------------------------------------------
 def cpu_reference_pass(kind, B, S, threads):
     """One pass of the CPU path (oracle port of the reference modules): embed -> generate(use_cache) -> recover."""
-    from oracle import synth, trpx_oracle as O
+    from tests import synth
+    from oracle import trpx_oracle as O
     cfg = synth.make_config(kind)
     sd_e = O.to_torch(synth.lorenz_embedding_weights(cfg, 2024))
     sd_t = O.to_torch(synth.gpt2_weights(cfg, 2025, stress=False))

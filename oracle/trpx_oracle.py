@@ -7,7 +7,7 @@ cpu_baseline / --impl reference legs may import this file.  The product package
 Parity status: PINNED.  The reference's own tests hold no golden vectors for this path
 (SURVEY.md §4, §8c), so the oracle is pinned against outputs of the reference itself: the fixtures in
 tests/golden/*.npz were produced by tests/golden/make_golden.py, which imports the unmodified reference
-from /root/reference, loads it with the oracle/synth.py weights and records its outputs.
+from /root/reference, loads it with the tests/synth.py weights and records its outputs.
 tests/test_oracle_golden.py checks every function below against those fixtures (and, where
 /root/reference is present, tests/test_oracle_vs_reference.py repeats the comparison live).
 
@@ -39,7 +39,7 @@ SD = Dict[str, Tensor]
 
 
 def to_torch(sd_np, dtype=torch.float32) -> SD:
-    """numpy state dict (oracle/synth.py) -> torch CPU tensors; float arrays are cast to `dtype`."""
+    """numpy state dict (tests/synth.py) -> torch CPU tensors; float arrays are cast to `dtype`."""
     out = {}
     for k, v in sd_np.items():
         t = torch.from_numpy(np.array(v))

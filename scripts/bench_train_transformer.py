@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "transformer-physx_b200")):
     sys.path.insert(0, p)
 import torch
-from oracle import synth
+from tests import synth
 from tests.util import make_gpt2
 
 ap = argparse.ArgumentParser()

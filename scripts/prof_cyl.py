@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "transformer-physx_b200")):
     sys.path.insert(0, p)
 import torch
-from oracle import synth
+from tests import synth
 from tests.util import make_cylinder
 dev = torch.device("cuda:0")
 mode, chunk, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])

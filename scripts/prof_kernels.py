@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "transformer-physx_b200")):
     sys.path.insert(0, p)
 import torch
-from oracle import synth
+from tests import synth
 from tests.util import make_cylinder, make_gpt2, make_lorenz, torch_sd
 dev = torch.device("cuda:0")
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2

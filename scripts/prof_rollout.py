@@ -17,7 +17,7 @@ ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 if a.kind == "cylinder":
-    from oracle import synth
+    from tests import synth
     from tests.util import make_gpt2
     cfg = synth.make_config("cylinder")
     tr = make_gpt2(cfg, 2025, False, dev)

@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference).
 
 Run here (CPU container, reference present):   python tests/golden/make_golden.py
-Weights and inputs come from oracle/synth.py (numpy default_rng, seeded) so only the reference's
+Weights and inputs come from tests/synth.py (numpy default_rng, seeded) so only the reference's
 outputs are stored.  Every case is listed in CASES below; tests/test_oracle_golden.py and the -m gpu
 parity tests iterate over the same table.
 """

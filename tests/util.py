@@ -1,4 +1,4 @@
-"""Helpers shared by the parity tests: build the B200 modules from the oracle/synth.py weights."""
+"""Helpers shared by the parity tests: build the B200 modules from the tests/synth.py weights."""
 import numpy as np
 import torch
 

@@ -42,3 +42,9 @@ GPT2_TRAIN_CASES = {
                             keep=("h.0.ln_1.", "h.0.attn.c_attn.", "h.2.attn.c_proj.bias", "h.3.ln_2.", "h.5.mlp.c_fc.bias",
                                   "h.5.mlp.c_proj.bias", "ln_f.", "mlp_f.")),
 }
+
+# Cylinder Koopman training loss (embedding_cylinder.py:236-281), value only: [B, T, 3, 64, 128] series built from
+# synth.cylinder_fields(B*T) frames, viscosity per sample.
+CYL_TRAIN_CASES = {
+    "cyl": dict(seed=601, B=2, T=3),
+}

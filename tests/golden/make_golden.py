@@ -14,7 +14,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref_shim, synth  # noqa: E402
-from tests.golden.cases import GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES  # noqa: E402
+from tests.golden.cases import (GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES,  # noqa: E402
+                                CYL_TRAIN_CASES)
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 torch.set_num_threads(1)          # deterministic reduction order for the fixtures
@@ -159,11 +160,31 @@ def gpt2_train_cases(trphysx):
         print("gpt2train", name, float(loss), len(out))
 
 
+def cyl_train_cases(trphysx):
+    from trphysx.embedding.embedding_cylinder import CylinderEmbeddingTrainer
+    from trphysx.config.configuration_phys import PhysConfig
+    for name, c in CYL_TRAIN_CASES.items():
+        cfg_ns = synth.make_config("cylinder")
+        head = CylinderEmbeddingTrainer(PhysConfig(**vars(cfg_ns)))
+        head.embedding_model.load_state_dict(_t(synth.cylinder_embedding_weights(cfg_ns, c["seed"])), strict=True)
+        B, T = c["B"], c["T"]
+        x, visc = synth.cylinder_fields(B * T, seed=c["seed"])
+        states = torch.from_numpy(x).view(B, T, 3, 64, 128)
+        visc = torch.from_numpy(visc).view(B, T, 1)[:, 0]
+        with torch.no_grad():
+            loss, loss_rec = head(states, visc)
+        np.savez_compressed(os.path.join(OUT, f"cyltrain_{name}.npz"), loss=loss.numpy(), loss_rec=loss_rec.numpy())
+        print("cyltrain", name, float(loss), float(loss_rec))
+
+
 if __name__ == "__main__":
     t = ref_shim.load()
     if len(sys.argv) > 1 and sys.argv[1] == "gpt2train":
         gpt2_train_cases(t)                                        # added later: leaves the other fixtures untouched
+    elif len(sys.argv) > 1 and sys.argv[1] == "cyltrain":
+        cyl_train_cases(t)
     else:
+        cyl_train_cases(t)
         gpt2_cases(t)
         lorenz_cases(t)
         cyl_cases(t)

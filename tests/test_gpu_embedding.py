@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import synth, trpx_oracle as O
-from tests.golden.cases import LORENZ_CASES, CYL_CASES, TRAIN_CASES
+from tests.golden.cases import LORENZ_CASES, CYL_CASES, TRAIN_CASES, CYL_TRAIN_CASES
 from tests.util import make_lorenz, make_cylinder, torch_sd
 
 pytestmark = pytest.mark.gpu
@@ -214,3 +214,26 @@ def test_eval_states_fused_recover_mse(dev, kind):
     ge = embed_series(emb, series.to(dev))
     assert ge.shape == (8, 41, cfg.n_embd)
     assert O.rel_l2(ge.cpu().view(-1, cfg.n_embd), O.lorenz_embed(O.to_torch(w), cfg, series.view(-1, 3))) < TOL
+
+
+@pytest.mark.parametrize("name", list(CYL_TRAIN_CASES))
+def test_cylinder_training_loss_value(golden_dir, dev, name):
+    """CylinderEmbeddingTrainer.forward under no_grad: the reference's recorded (loss, loss_reconstruct)
+    (embedding_cylinder.py:236-281); with gradients enabled it refuses (conv backward is a next row)."""
+    from trphysx_b200.embedding.embedding_cylinder import CylinderEmbeddingTrainer
+    c = CYL_TRAIN_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"cyltrain_{name}.npz"))
+    cfg = synth.make_config("cylinder")
+    head = CylinderEmbeddingTrainer(cfg)
+    head.embedding_model.load_state_dict(torch_sd(synth.cylinder_embedding_weights(cfg, c["seed"])))
+    head.to(dev)
+    B, T = c["B"], c["T"]
+    x, visc = synth.cylinder_fields(B * T, seed=c["seed"])
+    states = torch.from_numpy(x).view(B, T, 3, 64, 128).to(dev)
+    visc = torch.from_numpy(visc).view(B, T, 1)[:, 0].to(dev)
+    with torch.no_grad():
+        loss, loss_rec = head(states, visc)
+    assert abs(float(loss) - float(gold["loss"])) <= 1e-5 * float(gold["loss"])
+    assert abs(float(loss_rec) - float(gold["loss_rec"])) <= 1e-5 * float(gold["loss_rec"])
+    with pytest.raises(NotImplementedError):
+        head(states, visc)

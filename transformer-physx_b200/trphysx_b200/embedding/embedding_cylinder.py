@@ -176,7 +176,8 @@ class CylinderEmbedding(EmbeddingModel):
 
 
 class CylinderEmbeddingTrainer(EmbeddingTrainingHead):
-    """evaluate() is served by the kernels; the Cylinder Koopman TRAINING step (conv backward) is a "next" row
+    """evaluate() and the VALUE of the training loss (forward() under torch.no_grad(), e.g. for validation curves)
+    are served by the kernels; its gradient — the Cylinder Koopman TRAINING step, conv backward — is a "next" row
      and raises until it is built."""
 
     def __init__(self, config) -> None:
@@ -184,7 +185,33 @@ class CylinderEmbeddingTrainer(EmbeddingTrainingHead):
         self.embedding_model = CylinderEmbedding(config)
 
     def forward(self, states: Tensor, viscosity: Tensor):
-        raise NotImplementedError("Cylinder embedding training step (conv backward) is not built yet")
+        """(loss, loss_reconstruct) of embedding_cylinder.py:236-281: 1e1 MSE(x, recover(embed(x))) per step (decoder
+        without mask, as `forward()` of the reference) + 1e1 MSE(x_t, recover(K g_{t-1})) (with mask)
+        + 1e-2 sum(K^2) over the per-sample operators."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.embedding_model.parameters()):
+            raise NotImplementedError("Cylinder embedding training step (conv backward) is not built yet; "
+                                      "call under torch.no_grad() for the loss value")
+        assert states.size(0) == viscosity.size(0), \
+            "State variable and viscosity tensor should have the same batch dimensions."
+        m = self.embedding_model
+        device = m.devices[0]
+        mse = nn.functional.mse_loss
+        viscosity = viscosity.to(device)
+        xin0 = states[:, 0].to(device)
+        g0, xrec0 = m(xin0, viscosity)
+        loss = 1e1 * mse(xin0, xrec0)
+        loss_reconstruct = mse(xin0, xrec0)
+        g_old = g0
+        for t0 in range(1, states.shape[1]):
+            xin0 = states[:, t0].to(device)
+            _, xrec1 = m(xin0, viscosity)
+            g_pred = m.koopmanOperation(g_old, viscosity)
+            xgrec1 = m.recover(g_pred)
+            loss = loss + 1e1 * mse(xgrec1, xin0) + 1e1 * mse(xrec1, xin0) \
+                + 1e-2 * torch.sum(torch.pow(m.koopmanOperator, 2))
+            loss_reconstruct = loss_reconstruct + mse(xrec1, xin0)
+            g_old = g_pred
+        return loss, loss_reconstruct
 
     @torch.no_grad()
     def evaluate(self, states: Tensor, viscosity: Tensor):

@@ -1732,7 +1732,6 @@ __global__ void swizzle_weights_kernel(const float* __restrict__ blob, float* __
 //     memory (L2 resident: a few hundred KB).
 // ------------------------------------------------------------------------------------------------
 constexpr int CLS = 8;                 // CTAs per cluster
-constexpr int CL_THREADS = 256;
 
 struct ClusterLayout {                 // per-(image, rank) float offsets; image i < n_layer: layer i, image n_layer: head
     int E, sl;                         // sl = E / CLS
@@ -1915,7 +1914,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p)
     float* qT = aT + E * G;                          // [3E][G]
     float* hT = qT + 3 * E * G;                      // [4E][G]
     float* dT = hT + 4 * E * G;                      // [E][G] broadcast GEMV slice results (residual delta / token)
-    float* part = dT + E * G;                        // [NT/32][4*sl][G]
+    float* part = dT + 2 * E * G;                    // [NT/32][4*sl][G]   (dT is followed by the second residual buffer)
     float* pbuf = part + (NT / 32) * 4 * sl * G;     // [nw][C]
     const size_t img_stride = (size_t)CLy.att_size + CLy.mlp_size;
     const size_t kv_per_g = (size_t)NL * 2 * C * E;
@@ -1951,20 +1950,58 @@ __global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p)
     }
     cluster_sync_all();                               // all CTAs of the cluster are resident before any DSMEM store
 
-    auto ln_T = [&](const float* lw, const float* lb) {
+    // Residual update + LayerNorm.  pend: what still has to be applied to the residual from the last exchange
+    // (0 nothing, 1 x += dT, 2 x = dT).  Small groups (G <= 2): EVERY warp does the whole update and LayerNorm
+    // redundantly — same arithmetic, same values, so the concurrent identical writes are benign — into the other
+    // residual buffer (the update is then idempotent) and needs only a __syncwarp: no CTA barrier and no warps idling
+    // behind the one that normalises (that wait was 13 % of the step).  Larger groups: one warp per row + barriers.
+    float* xN = dT + E * G;                           // second residual buffer (allocated after dT; part follows)
+    int pend = 0;
+    auto advance_ln = [&](const float* lw, const float* lb) {
         const int lane = tid & 31;
-        for (int g = warp; g < G; g += nw) {
-            float s1 = 0.f;
-            for (int c = lane; c < E; c += 32) s1 += xT[c * G + g];
-            const float mean = warp_sum(s1) / (float)E;
-            float v = 0.f;
-            for (int c = lane; c < E; c += 32) {
-                const float d = xT[c * G + g] - mean;
-                v = fmaf(d, d, v);
+        if constexpr (G <= 2) {
+            float* xo = xT;
+            float* xn = pend ? xN : xT;
+            if (pend)
+                for (int i = lane; i < E * G; i += 32) xn[i] = (pend == 1) ? xo[i] + dT[i] : dT[i];
+            __syncwarp();
+            for (int g = 0; g < G; g++) {
+                float s1 = 0.f;
+                for (int c = lane; c < E; c += 32) s1 += xn[c * G + g];
+                const float mean = warp_sum(s1) / (float)E;
+                float v = 0.f;
+                for (int c = lane; c < E; c += 32) {
+                    const float d = xn[c * G + g] - mean;
+                    v = fmaf(d, d, v);
+                }
+                const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + p.eps);
+                for (int c = lane; c < E; c += 32) aT[c * G + g] = (xn[c * G + g] - mean) * rstd * lw[c] + lb[c];
             }
-            const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + p.eps);
-            for (int c = lane; c < E; c += 32) aT[c * G + g] = (xT[c * G + g] - mean) * rstd * lw[c] + lb[c];
+            __syncwarp();
+            if (pend) {                               // swap the residual buffers (uniform across the CTA)
+                xN = xo;
+                xT = xn;
+            }
+        } else {
+            if (pend) {
+                for (int i = tid; i < E * G; i += NT) xT[i] = (pend == 1) ? xT[i] + dT[i] : dT[i];
+                __syncthreads();
+            }
+            for (int g = warp; g < G; g += nw) {
+                float s1 = 0.f;
+                for (int c = lane; c < E; c += 32) s1 += xT[c * G + g];
+                const float mean = warp_sum(s1) / (float)E;
+                float v = 0.f;
+                for (int c = lane; c < E; c += 32) {
+                    const float d = xT[c * G + g] - mean;
+                    v = fmaf(d, d, v);
+                }
+                const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + p.eps);
+                for (int c = lane; c < E; c += 32) aT[c * G + g] = (xT[c * G + g] - mean) * rstd * lw[c] + lb[c];
+            }
+            __syncthreads();
         }
+        pend = 0;
     };
 
     for (int s = 0; s < p.S; s++) {
@@ -1974,8 +2011,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p)
             // ================= attention half (or the final head when l == NL) =================
             mbar_wait(&full[0], useA & 1);
             useA++;
-            ln_T(slotA + CLy.ln1w, slotA + CLy.ln1b);
-            __syncthreads();
+            advance_ln(slotA + CLy.ln1w, slotA + CLy.ln1b);
             if (l == NL) {
                 // x' = LN_f(x) Wf^T + bf : this CTA's slice -> every CTA, and to the output
                 const int pnext = p.use_cache ? min(s + 1, C - 1) : 0;
@@ -1985,8 +2021,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p)
                     dsmem_bcast(dT + col * G + g, v + __ldg(p.pe + pnext * E + col));
                 });
                 cluster_sync_all();
-                for (int i = tid; i < E * G; i += NT) xT[i] = dT[i];
-                __syncthreads();
+                pend = 2;                             // next step starts from x = dT
                 if (tid == 0 && s + 1 < p.S) fetch(0, 0);
                 break;
             }
@@ -2015,13 +2050,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p)
                              [&](int n, int g, float v) { dsmem_bcast(dT + (rank * sl + n) * G + g, v); });
             cluster_sync_all();                       // also: every thread of this CTA is done with slot A
             if (tid == 0) fetch(0, (l + 1 <= NL) ? l + 1 : 0);
-            for (int i = tid; i < E * G; i += NT) xT[i] += dT[i];
-            __syncthreads();
+            pend = 1;
             // ================= MLP half =================
             mbar_wait(&full[1], useM & 1);
             useM++;
-            ln_T(slotM + CLy.ln2w, slotM + CLy.ln2b);
-            __syncthreads();
+            advance_ln(slotM + CLy.ln2w, slotM + CLy.ln2b);
             cta_gemv_smem<G, NT>(slotM + CLy.wfc, slotM + CLy.bfc, E, 4 * sl, aT, part, [&](int n, int g, float v) {
                 dsmem_bcast(hT + (rank * 4 * sl + n) * G + g, gelu_new(v));
             });
@@ -2030,8 +2063,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p)
                              [&](int n, int g, float v) { dsmem_bcast(dT + (rank * sl + n) * G + g, v); });
             cluster_sync_all();
             if (tid == 0 && !(s + 1 == p.S && l + 1 == NL)) fetch(1, (l + 1 < NL) ? l + 1 : 0);
-            for (int i = tid; i < E * G; i += NT) xT[i] += dT[i];
-            __syncthreads();
+            pend = 1;
         }
     }
     if (p.presents != nullptr && p.use_cache && rank == 0) {
@@ -2653,7 +2685,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         const ClusterLayout cl = ClusterLayout::make(L.E);
         const int NTc = (h->tune_warps == 16) ? 512 : 256;
         auto smem_of = [&](int G) {
-            return sizeof(float) * ((size_t)cl.att_size + cl.mlp_size + (size_t)L.E * G * (1 + 1 + 3 + 4 + 1) +
+            return sizeof(float) * ((size_t)cl.att_size + cl.mlp_size + (size_t)L.E * G * (1 + 1 + 3 + 4 + 1 + 1) +
                                     (size_t)(NTc / 32) * 4 * cl.sl * G + (size_t)(NTc / 32) * L.n_ctx);
         };
         auto kernel_of = [&](int G) -> void (*)(ClusterParams) {

@@ -107,7 +107,8 @@ int trpx_gpt2_load_blob(trpx_gpt2_t h, const float* blob_dev, void* stream);
  * 5 = E=32 kernel with 2-D lane tiling (16 trajectories per warp), 6 = E=32 tensor-core kernel (3xTF32
  * mma.sync; chosen automatically for large batches without the KV window), 7 = thread-block-cluster kernel
  * (8 CTAs per trajectory group, column-split GEMVs, DSMEM exchange, TMA weight ring; chosen automatically for
- * shapes other than E=32 when one trajectory per cluster fits in a single wave). */
+ * shapes other than E=32 when one trajectory per cluster fits in a single wave; groups of 1-2 trajectories exchange
+ * with st.async + mbarrier complete_tx instead of cluster barriers), 9 = 7 with the cluster-barrier exchange (A/B). */
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp,
                                  int max_ctas);
 /* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 E=32 warp kernel, 5 E=32 2-D tiling, 6 E=32 tensor-core,

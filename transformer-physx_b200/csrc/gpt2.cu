@@ -2088,6 +2088,260 @@ __global__ void __launch_bounds__(NT, 1) rollout_cluster_kernel(ClusterParams p)
     cluster_sync_all();                               // no CTA may exit while peers can still store into its smem
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 (cluster, asynchronous exchange): the same decomposition as rollout_cluster_kernel for groups of 1-2
+// trajectories, but no cluster-wide barrier inside the step.  Measured on the barrier version: a step is 31 exchange
+// phases of ~2 us, of which ~0.5 us is barrier.cluster and ~0.3 us the release fence waiting for the remote stores.
+// Here every exchanged value travels as `st.async ... mbarrier::complete_tx::bytes` (a DSMEM store that credits its
+// 4 bytes to an mbarrier of the DESTINATION CTA); each CTA arms one of three rotating mbarriers with the byte count
+// the phase owes it and waits on that: point-to-point, no fence, a CTA proceeds as soon as ITS inputs are complete.
+// Buffers are reused only after an all-to-all phase in between (see the phase list in the body), the (trajectory,
+// head) owner CTA appends the k/v rows to the window itself (so the ring is written and read by one SM), and the
+// small groups use the per-warp redundant LayerNorm (no CTA barrier outside the GEMV reduction).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dsmem_bcast_async(float* local, float v, uint64_t* bar) {
+    const uint32_t l = smem_u32(local), b = smem_u32(bar);
+#pragma unroll
+    for (int r = 0; r < CLS; r++) {
+        uint32_t ra, rb;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(l), "r"(r));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(b), "r"(r));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra),
+                     "r"(__float_as_uint(v)), "r"(rb)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TRPX_WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TRPX_DONEC_%=;\n"
+        "bra TRPX_WAITC_%=;\n"
+        "TRPX_DONEC_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int G, int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) rollout_cluster_async_kernel(ClusterParams p) {
+    static_assert(G <= 2, "the asynchronous exchange kernel uses the per-warp redundant LayerNorm (small groups)");
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t full[2];         // weight ring
+    __shared__ __align__(8) uint64_t xb[3];           // exchange phases, rotating: phase ph uses xb[ph % 3]
+    const Gpt2Layout& L = p.lay;
+    const ClusterLayout& CLy = p.cl;
+    const int E = L.E, H = L.n_head, hd = L.hd, C = L.n_ctx, NL = L.n_layer, sl = CLy.sl;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+    const int rank = cluster_rank();
+    const int grp = blockIdx.x / CLS;
+    const int b0 = grp * G;
+    const int EG = E * G;
+    float* slotA = sm;
+    float* slotM = slotA + CLy.att_size;
+    float* xT = slotM + CLy.mlp_size;                // residual, two buffers
+    float* xN = xT + EG;
+    float* aT = xN + EG;                             // LN output (local)
+    float* qT = aT + EG;                             // [3E][G]  phase 1 (all -> all)
+    float* oT = qT + 3 * EG;                         // [E][G]   phase 2 (owners -> all)
+    float* dT = oT + EG;                             // [E][G]   phases 3 and 5
+    float* hT = dT + EG;                             // [4E][G]  phase 4
+    float* yT = hT + 4 * EG;                         // [E][G]   head
+    float* part = yT + EG;                           // [NT/32][4*sl][G]
+    float* pbuf = part + (NT / 32) * 4 * sl * G;     // [nw][C]
+    const size_t img_stride = (size_t)CLy.att_size + CLy.mlp_size;
+    const size_t kv_per_g = (size_t)NL * 2 * C * E;
+    float* kvb = p.kv + (size_t)grp * G * kv_per_g;
+
+    auto img_of = [&](int image) { return p.img + ((size_t)image * CLS + rank) * img_stride; };
+    auto fetch = [&](int slot, int image) {           // thread 0 only
+        float* dst = slot ? slotM : slotA;
+        const float* src = img_of(image) + (slot ? CLy.att_size : 0);
+        const uint32_t bytes = (uint32_t)(slot ? CLy.mlp_size : CLy.att_size) * 4u;
+        mbar_expect_tx(&full[slot], bytes);
+        const uint32_t CH = 32768u;
+        for (uint32_t off = 0; off < bytes; off += CH)
+            bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src) + off, min(CH, bytes - off),
+                     &full[slot]);
+    };
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&xb[0], 1);
+        mbar_init(&xb[1], 1);
+        mbar_init(&xb[2], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        fetch(0, 0);
+        fetch(1, 0);
+    }
+    uint32_t useA = 0, useM = 0;
+    // Exchange phase counter: barrier xb[ph % 3], parity (ph / 3) & 1.  Three barriers, not two: phase 2 is sent by
+    // the pair owners only, so a CTA that owns no pair could otherwise receive phase-3 bytes on the barrier it is
+    // still waiting on for phase 1; with a rotation of three a sender of phase ph+3 has always (transitively) seen
+    // this CTA's own send of phase ph+1 or ph+2, which it issues after its wait of phase ph.
+    uint32_t ph = 0;
+    for (int i = tid; i < EG; i += NT) {
+        const int c = i / G, g = i - c * G;
+        const int b = b0 + g;
+        xT[i] = ((b < p.B) ? p.x0[(size_t)b * p.x0_stride + c] : 0.f) + __ldg(p.pe + c);
+    }
+    cluster_sync_all();                               // barriers initialised and CTAs resident before any remote store
+
+    // arm the barrier of the phase that starts now with the bytes this CTA will receive in it
+    auto arm = [&](uint32_t bytes) {
+        if (tid == 0) mbar_expect_tx(&xb[ph % 3], bytes);
+    };
+    auto wait_phase = [&]() {
+        mbar_wait_cluster(&xb[ph % 3], (ph / 3) & 1);
+        ph++;
+    };
+    int pend = 0;                                     // 0 nothing, 1 x += dT, 2 x = yT
+    auto advance_ln = [&](const float* lw, const float* lb) {
+        float* xo = xT;
+        float* xn = pend ? xN : xT;
+        if (pend)
+            for (int i = lane; i < EG; i += 32) xn[i] = (pend == 1) ? xo[i] + dT[i] : yT[i];
+        __syncwarp();
+        for (int g = 0; g < G; g++) {
+            float s1 = 0.f;
+            for (int c = lane; c < E; c += 32) s1 += xn[c * G + g];
+            const float mean = warp_sum(s1) / (float)E;
+            float v = 0.f;
+            for (int c = lane; c < E; c += 32) {
+                const float d = xn[c * G + g] - mean;
+                v = fmaf(d, d, v);
+            }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)E + p.eps);
+            for (int c = lane; c < E; c += 32) aT[c * G + g] = (xn[c * G + g] - mean) * rstd * lw[c] + lb[c];
+        }
+        __syncwarp();
+        if (pend) {
+            xN = xo;
+            xT = xn;
+        }
+        pend = 0;
+    };
+
+    for (int s = 0; s < p.S; s++) {
+        const int Lk = p.use_cache ? min(s + 1, C) : 1;
+        const int slot = p.use_cache ? (s % C) : 0;
+        for (int l = 0; l <= NL; l++) {
+            mbar_wait(&full[0], useA & 1);
+            useA++;
+            if (l == NL) {
+                // ---- head: x' = LN_f(x) Wf^T + bf ----
+                arm((uint32_t)EG * 4u);
+                advance_ln(slotA + CLy.ln1w, slotA + CLy.ln1b);
+                const int pnext = p.use_cache ? min(s + 1, C - 1) : 0;
+                uint64_t* bar = &xb[ph % 3];
+                cta_gemv_smem<G, NT>(slotA + CLy.wproj, slotA + CLy.bproj, E, sl, aT, part, [&](int n, int g, float v) {
+                    const int col = rank * sl + n, b = b0 + g;
+                    if (b < p.B) p.out[(size_t)b * p.out_stride + (size_t)s * E + col] = v;
+                    dsmem_bcast_async(yT + col * G + g, v + __ldg(p.pe + pnext * E + col), bar);
+                });
+                wait_phase();
+                pend = 2;
+                __syncthreads();                      // every warp is done with slot A
+                if (tid == 0 && s + 1 < p.S) fetch(0, 0);
+                break;
+            }
+            // ---- phase 1: q | k | v slices, all -> all ----
+            arm((uint32_t)3 * EG * 4u);
+            advance_ln(slotA + CLy.ln1w, slotA + CLy.ln1b);
+            {
+                uint64_t* bar = &xb[ph % 3];
+                cta_gemv_smem<G, NT>(slotA + CLy.wqkv, slotA + CLy.bqkv, E, 3 * sl, aT, part, [&](int n, int g, float v) {
+                    const int which = n / sl, col = rank * sl + (n - which * sl);
+                    dsmem_bcast_async(qT + (which * E + col) * G + g, v, bar);
+                });
+            }
+            wait_phase();
+            // ---- phase 2: attention outputs, owners -> all ----
+            arm((uint32_t)EG * 4u);
+            {
+                uint64_t* bar = &xb[ph % 3];
+                for (int pair = rank + CLS * warp; pair < G * H; pair += CLS * nw) {
+                    const int g = pair / H, hh = pair - g * H;
+                    float* Kr = kvb + (size_t)g * kv_per_g + (size_t)(l * 2 + 0) * C * E + hh * hd;
+                    float* Vr = kvb + (size_t)g * kv_per_g + (size_t)(l * 2 + 1) * C * E + hh * hd;
+                    for (int d = lane; d < hd; d += 32) {   // the owner appends this pair's k / v row to the window
+                        Kr[(size_t)slot * E + d] = qT[(E + hh * hd + d) * G + g];
+                        Vr[(size_t)slot * E + d] = qT[(2 * E + hh * hd + d) * G + g];
+                    }
+                    __syncwarp();
+                    if (hd == 32 && C <= 16) {
+                        const float o = cluster_attn_hd32(qT + (hh * hd) * G + g, G, Kr, Vr, E, Lk);
+                        dsmem_bcast_async(oT + (hh * hd + lane) * G + g, o, bar);
+                    } else {
+                        float* ob = aT + (hh * hd) * G + g;   // LN output is consumed: local staging, then broadcast
+                        warp_attention(qT + (hh * hd) * G + g, G, Kr, Vr, E, hd, Lk, pbuf + warp * C, ob, G, nullptr);
+                        for (int d = lane; d < hd; d += 32) dsmem_bcast_async(oT + (hh * hd + d) * G + g, ob[d * G], bar);
+                    }
+                }
+            }
+            wait_phase();
+            // ---- phase 3: projection slices ----
+            arm((uint32_t)EG * 4u);
+            {
+                uint64_t* bar = &xb[ph % 3];
+                cta_gemv_smem<G, NT>(slotA + CLy.wproj, slotA + CLy.bproj, E, sl, oT, part,
+                                     [&](int n, int g, float v) { dsmem_bcast_async(dT + (rank * sl + n) * G + g, v, bar); });
+            }
+            wait_phase();
+            __syncthreads();                          // every warp is done with slot A
+            if (tid == 0) fetch(0, l + 1);
+            pend = 1;
+            // ---- phase 4: MLP hidden slices ----
+            mbar_wait(&full[1], useM & 1);
+            useM++;
+            arm((uint32_t)4 * EG * 4u);
+            advance_ln(slotM + CLy.ln2w, slotM + CLy.ln2b);
+            {
+                uint64_t* bar = &xb[ph % 3];
+                cta_gemv_smem<G, NT>(slotM + CLy.wfc, slotM + CLy.bfc, E, 4 * sl, aT, part, [&](int n, int g, float v) {
+                    dsmem_bcast_async(hT + (rank * 4 * sl + n) * G + g, gelu_new(v), bar);
+                });
+            }
+            wait_phase();
+            // ---- phase 5: MLP output slices ----
+            arm((uint32_t)EG * 4u);
+            {
+                uint64_t* bar = &xb[ph % 3];
+                cta_gemv_smem<G, NT>(slotM + CLy.wpr, slotM + CLy.bpr, 4 * E, sl, hT, part,
+                                     [&](int n, int g, float v) { dsmem_bcast_async(dT + (rank * sl + n) * G + g, v, bar); });
+            }
+            wait_phase();
+            __syncthreads();                          // every warp is done with slot M
+            if (tid == 0 && !(s + 1 == p.S && l + 1 == NL)) fetch(1, (l + 1 < NL) ? l + 1 : 0);
+            pend = 1;
+        }
+    }
+    cluster_sync_all();                               // ring rows of every owner visible; nobody stores into a peer any more
+    if (p.presents != nullptr && p.use_cache && rank == 0) {
+        const int Tk = min(p.S, C);
+        const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+        for (int g = 0; g < G; g++) {
+            const int b = b0 + g;
+            if (b >= p.B) break;
+            for (int i = tid; i < NL * 2 * Tk * E; i += NT) {
+                const int e = i % E;
+                int r = i / E;
+                const int t = r % Tk;
+                r /= Tk;
+                const int which = r & 1, l = r >> 1;
+                const int sl2 = (p.S - Tk + t) % C;
+                const int hh = e / hd, d = e - hh * hd;
+                p.presents[(size_t)l * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                    __ldcg(kvb + (size_t)g * kv_per_g + ((size_t)(l * 2 + which) * C + sl2) * E + e);
+            }
+        }
+    }
+}
+
 // per-(image, rank) weight images for the cluster kernel
 __global__ void cluster_image_kernel(const float* __restrict__ blob, float* __restrict__ img, Gpt2Layout L, ClusterLayout C) {
     const int E = L.E, sl = C.sl;
@@ -2519,10 +2773,10 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 8, "variant must be 0..8");
+    TRPX_REQUIRE(variant >= 0 && variant <= 9, "variant must be 0..9");
     TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 32, "warps_per_cta must be 0..32");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
-                     traj_per_warp == 8 || (traj_per_warp == 16 && variant == 7),
+                     traj_per_warp == 8 || (traj_per_warp == 16 && (variant == 7 || variant == 9)),
                  "traj_per_warp must be 0,1,2,4,8 (16 with variant 7)");
     h->tune_variant = variant;
     h->tune_prefetch = (variant == 4) ? 0 : 1;
@@ -2642,7 +2896,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             }
         }
     }
-    bool use_e32 = e32_shape && h->tune_variant != 1 && h->tune_variant != 7 && wbytes + (size_t)scr_per_warp_g1 + 1024 <= (size_t)h->smem_optin;
+    bool use_e32 = e32_shape && h->tune_variant != 1 && h->tune_variant != 7 && h->tune_variant != 9 && wbytes + (size_t)scr_per_warp_g1 + 1024 <= (size_t)h->smem_optin;
     if (use_e32) {
         const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
         int G = h->tune_g;
@@ -2681,14 +2935,18 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
     }
 
     // ---- cluster kernel: wide model, few trajectories ----
-    if (h->img_cl != nullptr && h->tune_variant != 1 && (!e32_shape || h->tune_variant == 7)) {
+    if (h->img_cl != nullptr && h->tune_variant != 1 && (!e32_shape || h->tune_variant == 7 || h->tune_variant == 9)) {
         const ClusterLayout cl = ClusterLayout::make(L.E);
         const int NTc = (h->tune_warps == 16) ? 512 : 256;
         auto smem_of = [&](int G) {
-            return sizeof(float) * ((size_t)cl.att_size + cl.mlp_size + (size_t)L.E * G * (1 + 1 + 3 + 4 + 1 + 1) +
+            return sizeof(float) * ((size_t)cl.att_size + cl.mlp_size + (size_t)L.E * G * ((h->tune_variant != 9 && G <= 2) ? 13 : 11) +
                                     (size_t)(NTc / 32) * 4 * cl.sl * G + (size_t)(NTc / 32) * L.n_ctx);
         };
+        const bool async_x = h->tune_variant != 9;            // variant 9: cluster-barrier exchange (A/B reference)
         auto kernel_of = [&](int G) -> void (*)(ClusterParams) {
+            if (async_x && G <= 2)
+                return NTc == 512 ? (G == 2 ? rollout_cluster_async_kernel<2, 512> : rollout_cluster_async_kernel<1, 512>)
+                                  : (G == 2 ? rollout_cluster_async_kernel<2, 256> : rollout_cluster_async_kernel<1, 256>);
 #define TRPX_CLK(NT_)                                                                                         \
     (G == 16 ? rollout_cluster_kernel<16, NT_>                                                                \
              : G == 8 ? rollout_cluster_kernel<8, NT_>                                                        \
@@ -2718,10 +2976,11 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             if ((B + g - 1) / g <= nc) break;
         }
         const int ngroups = G ? (B + G - 1) / G : 0;
-        // measured (profiles/README.md): one wave of single-trajectory clusters runs a step in 62 us against the
-        // generic kernel's 123 us; larger groups lengthen the exchange phases and lose to it from B = 64 on
+        // measured (profiles/README.md): one wave of clusters of 1-2 trajectories (st.async exchange) runs a step in
+        // 51-58 us against the generic kernel's 123 us; larger groups (cluster-barrier exchange) lose to it
         const bool want = G && max_clusters > 0 &&
-                          (h->tune_variant == 7 || (h->tune_variant == 0 && G == 1 && ngroups <= max_clusters));
+                          (h->tune_variant == 7 || h->tune_variant == 9 ||
+                           (h->tune_variant == 0 && G <= 2 && ngroups <= max_clusters));
         if (want) {
             int rc = ensure_kv(h, (size_t)ngroups * G * kv_per_traj);
             if (rc) return rc;
@@ -2735,7 +2994,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             cfg.dynamicSmemBytes = smem_of(G);
             cfg.stream = st;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            h->last_variant = 7; h->last_grid = ngroups * CLS; h->last_block = NTc;
+            h->last_variant = h->tune_variant == 9 ? 9 : 7; h->last_grid = ngroups * CLS; h->last_block = NTc;
             h->last_smem = (int)smem_of(G); h->last_group = G;
             TRPX_CUDA(cudaLaunchKernelEx(&cfg, kernel_of(G), cp));
             return TRPX_OK;

@@ -81,6 +81,13 @@ __device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1,
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+// 2^x on the SFU (ex2.approx: max error 2 ulp over the whole range; inputs here are <= 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

@@ -433,7 +433,12 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
     __syncwarp();                                     // every lane holds its query: the tile may be overwritten
     const float* Kp = kvl + (size_t)g * kv_per_g + hh * 8;
     const float* Vp = Kp + C * 32;
-    const float scale = 2.8284271247461903f;          // sqrt(8): attention.py:99 divides by sqrt(head size)
+    // Scores are kept in the log2 domain: the query is pre-multiplied ONCE by log2(e)/sqrt(8) (attention.py:99 divides
+    // q.k by sqrt(head size)), so a window row costs its 8 FMAs, one max, and later one subtract + ex2.approx; the
+    // softmax denominator is applied to the 8 outputs instead of the 32 weights.  Each step is <= 2 ulp from the
+    // reference's divide / expf / normalise-then-weight form (parity tests: unchanged at ~5e-7 against the 1e-5 bar).
+#pragma unroll
+    for (int d = 0; d < 8; d++) q[d] *= 0.35355339059327373f * 1.4426950408889634f;
     float sc[NS];
     float m = -INFINITY;
 #pragma unroll
@@ -455,7 +460,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
                 float s0 = 0.f;
 #pragma unroll
                 for (int d = 0; d < 8; d++) s0 = fmaf(q[d], kk[jj][d], s0);
-                const float s1 = (FULLW || slot < L) ? s0 / scale : -INFINITY;
+                const float s1 = (FULLW || slot < L) ? s0 : -INFINITY;
                 sc[j0 + jj] = s1;
                 m = fmaxf(m, s1);
             }
@@ -469,7 +474,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < NS; j++) {
-        const float pj = (FULLW || j * P + part < L) ? expf(sc[j] - m) : 0.f;
+        const float pj = (FULLW || j * P + part < L) ? ex2_approx(sc[j] - m) : 0.f;
         sc[j] = pj;
         sum += pj;
     }
@@ -494,7 +499,7 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
             }
 #pragma unroll
             for (int jj = 0; jj < BS; jj++) {
-                const float pw = sc[j0 + jj] * rs;
+                const float pw = sc[j0 + jj];
 #pragma unroll
                 for (int d = 0; d < 8; d += 2) ffma2(acc[d], acc[d + 1], vv[jj][d], vv[jj][d + 1], pw);
             }
@@ -504,6 +509,8 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
     for (int o = 1; o < P; o <<= 1)
 #pragma unroll
         for (int d = 0; d < 8; d++) acc[d] += __shfl_xor_sync(FULL, acc[d], o);
+#pragma unroll
+    for (int d = 0; d < 8; d++) acc[d] *= rs;
     if (part == 0) {
         if constexpr (ORM > 0) {
             *reinterpret_cast<float4*>(outT + g * ORM + hh * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -790,7 +797,6 @@ __global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel
     const size_t kv_per_g = (size_t)NL * 2 * C * 32;
     float* kvw = p.kv + (size_t)(blockIdx.x * W + warp) * G * kv_per_g;
     const int part = lane & 1, gh = lane >> 1, hh = gh & 3, ga = gh >> 2;      // attention role of the lane
-    const float scale = 2.8284271247461903f;          // sqrt(8): attention.py:99 divides by sqrt(head size)
     uint32_t par = 0;                                 // parity of the next completion of tbar
     int lc = 0;                                       // layers consumed so far (ring position)
 
@@ -880,7 +886,9 @@ __global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel
                     const float4 a = qp[0], b = qp[1];
                     q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
                 }
-                // ---- scores, stage by stage ----
+#pragma unroll
+                for (int d = 0; d < 8; d++) q[d] *= 0.35355339059327373f * 1.4426950408889634f;   // as warp_attn_e32
+                // ---- scores (log2 domain), stage by stage ----
                 float sc[NS];
                 float m = -INFINITY;
 #pragma unroll
@@ -908,7 +916,7 @@ __global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel
                             float s0 = 0.f;
 #pragma unroll
                             for (int d = 0; d < 8; d++) s0 = fmaf(q[d], kk[d], s0);
-                            const float s1 = (stg * BR + row < Lk) ? s0 / scale : -INFINITY;
+                            const float s1 = (stg * BR + row < Lk) ? s0 : -INFINITY;
                             sc[stg * JB + jj] = s1;
                             m = fmaxf(m, s1);
                         }
@@ -922,7 +930,7 @@ __global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel
 #pragma unroll
                 for (int j = 0; j < NS; j++) {
                     const int stg = j / JB, jj = j - stg * JB;
-                    const float pj = (stg * BR + jj * P + part < Lk) ? expf(sc[j] - m) : 0.f;
+                    const float pj = (stg * BR + jj * P + part < Lk) ? ex2_approx(sc[j] - m) : 0.f;
                     sc[j] = pj;
                     sum += pj;
                 }
@@ -951,7 +959,7 @@ __global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel
                             const int row = jj * P + part;
                             float vv[8];
                             lds_row(min(row, min(Lk - stg * BR, BR) - 1), vv);      // clamped rows carry weight 0
-                            const float pw = sc[stg * JB + jj] * rs;
+                            const float pw = sc[stg * JB + jj];
 #pragma unroll
                             for (int d = 0; d < 8; d++) acc[d] = fmaf(pw, vv[d], acc[d]);
                         }
@@ -971,6 +979,8 @@ __global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel
                 }
 #pragma unroll
                 for (int d = 0; d < 8; d++) acc[d] += __shfl_xor_sync(FULL, acc[d], 1);
+#pragma unroll
+                for (int d = 0; d < 8; d++) acc[d] *= rs;
                 if (part == 0) {
 #pragma unroll
                     for (int d = 0; d < 8; d++) scr[(hh * 8 + d) * G + ga] = acc[d];

@@ -81,6 +81,48 @@ __device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1,
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+__device__ __forceinline__ float ex2_approx_fwd(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// gelu_new of two values at once with packed FP32 arithmetic (mul/fma/add.f32x2) + 2 ex2 + 2 rcp on the SFU:
+// x * rcp(1 + 2^(k x (1 + 0.044715 x^2))), k = -2 log2(e) sqrt(2/pi) — the sigmoid form of gelu_new_sig, 4 issue
+// slots per value instead of ~9.
+__device__ __forceinline__ void gelu_new_sig2(float& x0, float& x1) {
+    const float k = -2.0f * 1.4426950408889634f * 0.7978845608028654f;
+    float e0, e1;
+    asm("{\n.reg .b64 x, t, p, kk, ka;\n"
+        "mov.b64 x, {%2, %3};\n"
+        "mov.b64 kk, {%4, %4};\n"
+        "mov.b64 ka, {%5, %5};\n"
+        "mul.rn.f32x2 t, x, x;\n"                    // x^2
+        "fma.rn.f32x2 p, t, ka, kk;\n"               // k (1 + 0.044715 x^2)
+        "mul.rn.f32x2 p, p, x;\n"                    // exponent (log2 domain)
+        "mov.b64 {%0, %1}, p;\n}"
+        : "=f"(e0), "=f"(e1)
+        : "f"(x0), "f"(x1), "f"(k), "f"(k * 0.044715f));
+    e0 = ex2_approx_fwd(e0);
+    e1 = ex2_approx_fwd(e1);
+    float r0, r1;
+    asm("{\n.reg .b64 e, one;\n"
+        "mov.b64 e, {%2, %3};\n"
+        "mov.b64 one, {%4, %4};\n"
+        "add.rn.f32x2 e, e, one;\n"
+        "mov.b64 {%0, %1}, e;\n}"
+        : "=f"(r0), "=f"(r1)
+        : "f"(e0), "f"(e1), "f"(1.0f));
+    asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(r0));
+    asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(r1));
+    asm("{\n.reg .b64 x, r;\n"
+        "mov.b64 x, {%0, %1};\n"
+        "mov.b64 r, {%2, %3};\n"
+        "mul.rn.f32x2 x, x, r;\n"
+        "mov.b64 {%0, %1}, x;\n}"
+        : "+f"(x0), "+f"(x1)
+        : "f"(r0), "f"(r1));
+}
+
 // 2^x on the SFU (ex2.approx: max error 2 ulp over the whole range; inputs here are <= 0)
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

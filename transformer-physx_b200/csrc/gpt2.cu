@@ -654,9 +654,14 @@ __global__ void __launch_bounds__((CACHE && G >= 4) ? 256 : 384, 1) rollout_e32_
                     for (int g = 0; g < G; g++) f[c][g] = w[L.bfc + lane + 32 * c];
                 warp_gemv<G, 4>(scr, w + L.wfc, 32, 128, lane, f);
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int c = 0; c < 4; c++) {
+                    if constexpr (G % 2 == 0) {
 #pragma unroll
-                    for (int g = 0; g < G; g++) f[c][g] = gelu_new_sig(f[c][g]);
+                        for (int g = 0; g < G; g += 2) gelu_new_sig2(f[c][g], f[c][g + 1]);
+                    } else {
+                        f[c][0] = gelu_new_sig(f[c][0]);
+                    }
+                }
                 float acc[1][G];
 #pragma unroll
                 for (int g = 0; g < G; g++) acc[0][g] = w[L.bpr + lane];
@@ -1008,9 +1013,14 @@ __global__ void __launch_bounds__(NCTX >= 32 ? 256 : 416, 1) rollout_e32s_kernel
                     for (int g = 0; g < G; g++) f[c][g] = w[L.bfc + lane + 32 * c];
                 warp_gemv<G, 4>(scr, w + L.wfc, 32, 128, lane, f);
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int c = 0; c < 4; c++) {
+                    if constexpr (G % 2 == 0) {
 #pragma unroll
-                    for (int g = 0; g < G; g++) f[c][g] = gelu_new_sig(f[c][g]);
+                        for (int g = 0; g < G; g += 2) gelu_new_sig2(f[c][g], f[c][g + 1]);
+                    } else {
+                        f[c][0] = gelu_new_sig(f[c][0]);
+                    }
+                }
                 float mo[1][G];
 #pragma unroll
                 for (int g = 0; g < G; g++) mo[0][g] = w[L.bpr + lane];

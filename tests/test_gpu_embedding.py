@@ -237,3 +237,23 @@ def test_cylinder_training_loss_value(golden_dir, dev, name):
     assert abs(float(loss_rec) - float(gold["loss_rec"])) <= 1e-5 * float(gold["loss_rec"])
     with pytest.raises(NotImplementedError):
         head(states, visc)
+
+
+@pytest.mark.parametrize("kind,n", [("lorenz", 16384), ("rossler", 50001)])
+def test_recover_tensor_core_kernel(dev, kind, n):
+    """recover for N >= 16384 runs on the 3xTF32 tensor-core kernel: against the oracle at the FP32 bar, against the
+    FP32 SIMT kernel (mode 1), ragged last tile."""
+    cfg = synth.make_config(kind)
+    w = synth.lorenz_embedding_weights(cfg, 911)
+    emb = make_lorenz(cfg, 911, kind, dev)
+    g = torch.from_numpy(synth.normal_embeds((n, cfg.n_embd), 912)) * 1.5
+    ref = O.lorenz_recover(O.to_torch(w), cfg, g)
+    tc = emb.recover(g.to(dev))
+    emb.set_recover_mode(1)
+    simt = emb.recover(g.to(dev))
+    emb.set_recover_mode(0)
+    assert not torch.equal(tc, simt)                      # really two different kernels
+    e_tc, e_simt = O.rel_l2(tc.cpu(), ref), O.rel_l2(simt.cpu(), ref)
+    print(f"recover {kind} N={n}: rel-L2 tensor-core {e_tc:.2e}, SIMT {e_simt:.2e}")
+    assert e_tc < TOL and e_simt < TOL
+    assert float((tc - simt).abs().max()) < 1e-4 * float(ref.abs().max())

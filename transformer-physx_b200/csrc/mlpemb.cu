@@ -3,6 +3,7 @@
 // (koopmanOperation), :144-157 (koopmanOperator); enn_trainer.py:97-99 (clip_grad_norm_ + optimizer.step).
 #include "mlpemb.cuh"
 #include <cmath>
+#include <algorithm>
 
 using namespace trpx;
 
@@ -229,6 +230,104 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, fl
     }
 }
 
+// ---- K3b (tensor cores): recover for large N --------------------------------------------------------------
+// Layer 1 ([N x 32] . [32 x 500], 91 % of the FLOPs of recover) on the warp-level TF32 MMA with the error-compensated
+// 3xTF32 product (a_lo w_hi + a_hi w_lo + a_hi w_hi, FP32 accumulate: ~2^-21 relative, inside the FP32 parity bar).
+// One warp = one 16-sample M-tile; the weights are split into TF32 hi / lo planes ONCE per CTA into shared memory
+// ([Hp][36] each, row stride 36 makes the B-fragment loads conflict-free), the A fragments (the 16 x 32 inputs) are
+// split once per tile and reused for all 63 n-tiles.  The accumulator fragment of an n-tile (2 hidden units x 2
+// samples per lane) goes through ReLU straight into layer 2 (12 FMAs per lane against one LDS.128 per hidden unit);
+// the three outputs are reduced over the 4 lanes of a row at the end.  Instructions per 16 samples: ~2,900 against
+// ~5,500 for the SIMT kernel.
+constexpr int RTC_THREADS = 384;
+constexpr int RTC_LD = 36;
+
+__device__ __forceinline__ uint32_t rtc_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+__device__ __forceinline__ void rtc_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(RTC_THREADS, 1) mlp_recover_tc_kernel(const float* __restrict__ blob, MlpLayout L,
+                                                                        const float* __restrict__ g,
+                                                                        float* __restrict__ x, long long N) {
+    extern __shared__ __align__(16) float smf[];
+    const int Hd = L.Hd, Hp = (Hd + 7) & ~7;
+    uint32_t* whi = reinterpret_cast<uint32_t*>(smf);         // [Hp][36] TF32 hi plane of V1[n][k]
+    uint32_t* wlo = whi + Hp * RTC_LD;                         // lo plane (FP32 remainder)
+    float4* dB = reinterpret_cast<float4*>(wlo + Hp * RTC_LD); // [Hp] {V2[0..2][n], c1[n]}
+    for (int i = threadIdx.x; i < Hp * ME; i += blockDim.x) {
+        const int n = i / ME, k = i - n * ME;
+        const float w = n < Hd ? __ldg(blob + L.decA + i) : 0.f;
+        const uint32_t hi = rtc_tf32(w);
+        whi[n * RTC_LD + k] = hi;
+        wlo[n * RTC_LD + k] = __float_as_uint(w - __uint_as_float(hi));
+    }
+    for (int i = threadIdx.x; i < Hp; i += blockDim.x)
+        dB[i] = i < Hd ? __ldg(reinterpret_cast<const float4*>(blob + L.decB) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int gq = lane >> 2, q = lane & 3;
+    const long long ntiles = (N + 15) / 16;
+    float c2[MS], mu[MS], sd[MS];
+#pragma unroll
+    for (int c = 0; c < MS; c++) { c2[c] = __ldg(blob + L.c2 + c); mu[c] = __ldg(blob + L.mu + c); sd[c] = __ldg(blob + L.sd + c); }
+    for (long long tile = (long long)blockIdx.x * nw + warp; tile < ntiles; tile += (long long)gridDim.x * nw) {
+        const long long r0 = tile * 16 + gq, r1 = r0 + 8;
+        const float* g0 = g + (r0 < N ? r0 : N - 1) * ME;
+        const float* g1 = g + (r1 < N ? r1 : N - 1) * ME;
+        uint32_t ah[4][4], al[4][4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const float a[4] = {__ldg(g0 + 8 * s + q), __ldg(g1 + 8 * s + q), __ldg(g0 + 8 * s + q + 4), __ldg(g1 + 8 * s + q + 4)};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                ah[s][i] = rtc_tf32(a[i]);
+                al[s][i] = __float_as_uint(a[i] - __uint_as_float(ah[s][i]));
+            }
+        }
+        float y0[MS] = {0.f, 0.f, 0.f}, y1[MS] = {0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int t = 0; t < Hp / 8; t++) {
+            const float4 v0 = dB[8 * t + 2 * q], v1 = dB[8 * t + 2 * q + 1];
+            float acc[4] = {v0.w, v1.w, v0.w, v1.w};          // bias c1 of the lane's two hidden units
+            const uint32_t* bh = whi + (8 * t + gq) * RTC_LD + q;
+            const uint32_t* bl = wlo + (8 * t + gq) * RTC_LD + q;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const uint32_t bh0 = bh[8 * s], bh1 = bh[8 * s + 4], bl0 = bl[8 * s], bl1 = bl[8 * s + 4];
+                rtc_mma(acc, al[s], bh0, bh1);
+                rtc_mma(acc, ah[s], bl0, bl1);
+                rtc_mma(acc, ah[s], bh0, bh1);
+            }
+            const float h00 = fmaxf(acc[0], 0.f), h01 = fmaxf(acc[1], 0.f), h10 = fmaxf(acc[2], 0.f), h11 = fmaxf(acc[3], 0.f);
+            y0[0] = fmaf(h00, v0.x, y0[0]); y0[1] = fmaf(h00, v0.y, y0[1]); y0[2] = fmaf(h00, v0.z, y0[2]);
+            y0[0] = fmaf(h01, v1.x, y0[0]); y0[1] = fmaf(h01, v1.y, y0[1]); y0[2] = fmaf(h01, v1.z, y0[2]);
+            y1[0] = fmaf(h10, v0.x, y1[0]); y1[1] = fmaf(h10, v0.y, y1[1]); y1[2] = fmaf(h10, v0.z, y1[2]);
+            y1[0] = fmaf(h11, v1.x, y1[0]); y1[1] = fmaf(h11, v1.y, y1[1]); y1[2] = fmaf(h11, v1.z, y1[2]);
+        }
+#pragma unroll
+        for (int c = 0; c < MS; c++) {
+            y0[c] += __shfl_xor_sync(FULL, y0[c], 1);
+            y0[c] += __shfl_xor_sync(FULL, y0[c], 2);
+            y1[c] += __shfl_xor_sync(FULL, y1[c], 1);
+            y1[c] += __shfl_xor_sync(FULL, y1[c], 2);
+        }
+        if (q == 0) {
+#pragma unroll
+            for (int c = 0; c < MS; c++) {                   // _unnormalize, embedding_lorenz.py:162-163
+                if (r0 < N) x[r0 * MS + c] = sd[c] * (y0[c] + c2[c]) + mu[c];
+                if (r1 < N) x[r1 * MS + c] = sd[c] * (y1[c] + c2[c]) + mu[c];
+            }
+        }
+    }
+}
+
 // ---- K4: banded Koopman matvec ------------------------------------------------------------------------
 // K = diag(d) + U - U^T with U holding offsets +1 (u1[0..30]) and +2 (u2[0..29])  (embedding_lorenz.py:59-66,
 // 130-137).  g'[i] = d[i] g[i] + u1[i] g[i+1] + u2[i] g[i+2] - u1[i-1] g[i-1] - u2[i-2] g[i-2].
@@ -413,9 +512,27 @@ int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g, float* x, long long N, 
     const MlpLayout L = MlpLayout::make(h->cfg.hidden);
     const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
     TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int Hp = (L.Hd + 7) & ~7;
+    const size_t smem_tc = sizeof(float) * ((size_t)2 * Hp * RTC_LD + (size_t)4 * Hp);
+    if (h->recover_mode != 1 && N >= 16384 && smem_tc + 1024 <= (size_t)h->smem_optin) {
+        // tensor-core kernel: one persistent CTA per SM, 12 warps, 16 samples per warp-tile
+        TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        const long long ntiles = (N + 15) / 16;
+        const int grid = (int)std::min<long long>(h->sm_count, (ntiles + RTC_THREADS / 32 - 1) / (RTC_THREADS / 32));
+        mlp_recover_tc_kernel<<<grid, RTC_THREADS, smem_tc, (cudaStream_t)stream>>>(h->blob, L, g, x, N);
+        TRPX_CUDA(cudaGetLastError());
+        return TRPX_OK;
+    }
     mlp_recover_kernel<<<emb_grid(h, N, 3), EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, g, x, N, nullptr,
                                                                                         nullptr);
     TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int trpx_mlpemb_set_recover_mode(trpx_mlpemb_t h, int mode) {
+    TRPX_REQUIRE(valid(h), "invalid handle");
+    TRPX_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (automatic) or 1 (FP32 SIMT kernel only)");
+    h->recover_mode = mode;
     return TRPX_OK;
 }
 

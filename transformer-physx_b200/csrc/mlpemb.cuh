@@ -16,6 +16,7 @@ struct trpx_mlpemb {
     size_t ws_bytes = 0;
     float* mse_partial = nullptr; // per-CTA squared-error sums of the fused recover + MSE
     int mse_partial_n = 0;
+    int recover_mode = 0;         // 0 automatic, 1 FP32 SIMT kernel only (A/B)
 };
 
 namespace trpx {

@@ -49,6 +49,7 @@ SIGNATURES = {
     "trpx_mlpemb_load_weights": (c_int, [c_void_p, PP, c_int, c_void_p]),
     "trpx_mlpemb_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "trpx_mlpemb_recover": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "trpx_mlpemb_set_recover_mode": (c_int, [c_void_p, c_int]),
     "trpx_mlpemb_recover_mse": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]),
     "trpx_mlpemb_koopman": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "trpx_mlpemb_koopman_matrix": (c_int, [c_void_p, c_void_p, c_void_p]),

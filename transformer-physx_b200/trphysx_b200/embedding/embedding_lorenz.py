@@ -56,6 +56,7 @@ class LorenzEmbedding(EmbeddingModel):
             N.check(lib.trpx_mlpemb_create(ctypes.byref(cfg), idx, ctypes.byref(h)))
             entry = (h, N.WeightTracker())
             self._handles[idx] = entry
+            N.check(lib.trpx_mlpemb_set_recover_mode(h, getattr(self, "_recover_mode", 0)))
         h, tracker = entry
         ws = self._weight_list()
         if tracker.changed(ws):
@@ -95,6 +96,12 @@ class LorenzEmbedding(EmbeddingModel):
         N.check(N.lib().trpx_mlpemb_recover(self._handle(g.device), g.data_ptr(), x.data_ptr(), g.size(0),
                                             N.stream_ptr(g.device)))
         return x
+
+    def set_recover_mode(self, mode: int = 0):
+        """0: automatic (3xTF32 tensor-core kernel for N >= 16384 samples), 1: FP32 SIMT kernel only."""
+        self._recover_mode = mode
+        for h, _ in self._handles.values():
+            N.check(N.lib().trpx_mlpemb_set_recover_mode(h, mode))
 
     def recover_mse(self, g: Tensor, states: Tensor, return_states: bool = False):
         """MSELoss()(recover(g), states) in one launch without materialising the recovered states — the computation

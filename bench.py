@@ -11,6 +11,8 @@ N>1 is weak scaling: every GPU runs its own 65,536-trajectory shard.  No collect
 
   value    trajectory-steps/s, whole job, inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e      same metric through the public module API with HOST buffers: pinned x0 -> H2D, ..., states -> D2H
+           (recover runs in 4 trajectory chunks; a chunk's states travel to the pinned host buffer on a copy stream
+           while the next chunk decodes; the step ends when the last state has reached the host)
   roofline the rollout kernel alone (CUDA events around it): algorithmic FLOPs / duration vs the FP32 FMA peak
            measured in the same run (MEASURED_PEAKS.json has no FP32 entry); HBM view reported beside it
   cpu_baseline   the oracle port (torch CPU, all host threads) on a bounded sample, rank 0 only
@@ -211,12 +213,25 @@ def run_ours(args):
         out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True, return_presents=False)[0]
         return emb.recover(out.view(B * (S + 1), E))
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    NCH = 4                                            # recover in chunks of trajectories; each chunk's states go
+    bounds = [B * i // NCH for i in range(NCH + 1)]    # device -> host on a copy stream while the next one decodes
+
     def pass_e2e():
         x = x0_host.to(dev, non_blocking=True)
         g0 = emb.embed(x)
         out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True, return_presents=False)[0]
-        st = emb.recover(out.view(B * (S + 1), E))
-        states_host.copy_(st.view(B, S + 1, 3), non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        for i in range(NCH):
+            lo, hi = bounds[i], bounds[i + 1]
+            st = emb.recover(out[lo:hi].reshape((hi - lo) * (S + 1), E))
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                states_host[lo:hi].copy_(st.view(hi - lo, S + 1, 3), non_blocking=True)
+                st.record_stream(copy_stream)
+        cur.wait_stream(copy_stream)                   # the step ends when its last state has reached the host
 
     def timed(fn, steps, warmup, sampler=None):
         with torch.no_grad():

@@ -213,25 +213,14 @@ def run_ours(args):
         out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True, return_presents=False)[0]
         return emb.recover(out.view(B * (S + 1), E))
 
+    from trphysx_b200.evaluation import rollout_to_host
     copy_stream = torch.cuda.Stream(device=dev)
-    NCH = 4                                            # recover in chunks of trajectories; each chunk's states go
-    bounds = [B * i // NCH for i in range(NCH + 1)]    # device -> host on a copy stream while the next one decodes
 
     def pass_e2e():
-        x = x0_host.to(dev, non_blocking=True)
-        g0 = emb.embed(x)
-        out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True, return_presents=False)[0]
-        cur = torch.cuda.current_stream(dev)
-        for i in range(NCH):
-            lo, hi = bounds[i], bounds[i + 1]
-            st = emb.recover(out[lo:hi].reshape((hi - lo) * (S + 1), E))
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ready)
-                states_host[lo:hi].copy_(st.view(hi - lo, S + 1, 3), non_blocking=True)
-                st.record_stream(copy_stream)
-        cur.wait_stream(copy_stream)                   # the step ends when its last state has reached the host
+        # ONE public call: pinned x0 -> H2D -> embed -> generate -> recover in 4 trajectory chunks, each chunk's states
+        # going device -> host on the copy stream while the next chunk decodes
+        rollout_to_host(emb, tr, x0_host, S + 1, states_host, device=dev, use_cache=True, chunks=4,
+                        copy_stream=copy_stream)
 
     def timed(fn, steps, warmup, sampler=None):
         with torch.no_grad():

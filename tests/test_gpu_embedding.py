@@ -257,3 +257,23 @@ def test_recover_tensor_core_kernel(dev, kind, n):
     print(f"recover {kind} N={n}: rel-L2 tensor-core {e_tc:.2e}, SIMT {e_simt:.2e}")
     assert e_tc < TOL and e_simt < TOL
     assert float((tc - simt).abs().max()) < 1e-4 * float(ref.abs().max())
+
+
+def test_rollout_to_host_pipeline(dev):
+    """evaluation.rollout_to_host: pinned x0 -> embed -> generate -> chunked recover with overlapped D2H equals the
+    three public calls done one after the other."""
+    from trphysx_b200.evaluation import rollout_to_host
+    from tests.util import make_gpt2
+    cfg = synth.make_config("rossler")
+    emb = make_lorenz(cfg, 921, "rossler", dev)
+    tr = make_gpt2(cfg, 922, False, dev)
+    B, S = 1003, 20
+    x0 = torch.from_numpy(synth.rossler_trajectories(B, 0, seed=923)[:, 0].copy()).pin_memory()
+    host = torch.empty((B, S + 1, 3), dtype=torch.float32).pin_memory()
+    rollout_to_host(emb, tr, x0, S + 1, host, device=dev, chunks=4)
+    torch.cuda.synchronize()
+    g0 = emb.embed(x0.to(dev))
+    out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True)[0]
+    ref = emb.recover(out.view(B * (S + 1), cfg.n_embd)).view(B, S + 1, 3)
+    # chunks of 5,271 samples take the FP32 recover kernel, the single call (21,063 samples) the tensor-core one
+    assert O.rel_l2(host, ref.cpu()) < 1e-6

@@ -33,3 +33,35 @@ def embed_series(embedding_model, series: Tensor, *extra) -> Tensor:
     flat = series.reshape([B * T] + list(series.shape[2:]))
     args = [e.reshape([B * T] + list(e.shape[2:])) for e in extra]
     return embedding_model.embed(flat, *args).view(B, T, -1)
+
+
+@torch.no_grad()
+def rollout_to_host(embedding_model, transformer, x0_host: Tensor, max_length: int, states_host: Tensor,
+                    device=None, use_cache: bool = True, chunks: int = 4, copy_stream=None) -> Tensor:
+    """The evaluation pipeline of `Trainer.eval_states` around `generate()` with HOST buffers:
+    x0_host [B, *state_dims] (pinned) -> device -> embed -> generate(max_length) -> recover -> states_host
+    [B, max_length, *state_dims] (pinned).  The decoder runs in `chunks` slices of trajectories and each slice's states
+    are copied to the host on `copy_stream` while the next slice decodes, so only the last copy is exposed.  Returns
+    `states_host` once the current stream has been made to wait for the copies (call torch.cuda.synchronize() or
+    record an event before reading it on the host)."""
+    dev = torch.device(device) if device is not None else embedding_model.devices[0]
+    B = x0_host.size(0)
+    E = transformer.config.n_embd
+    cur = torch.cuda.current_stream(dev)
+    if copy_stream is None:
+        copy_stream = torch.cuda.Stream(device=dev)
+    x = x0_host.to(dev, non_blocking=True)
+    g0 = embedding_model.embed(x)
+    out = transformer.generate(g0.unsqueeze(1), max_length=max_length, use_cache=use_cache, return_presents=False)[0]
+    chunks = max(1, min(chunks, B))
+    for i in range(chunks):
+        lo, hi = B * i // chunks, B * (i + 1) // chunks
+        st = embedding_model.recover(out[lo:hi].reshape((hi - lo) * max_length, E))
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            states_host[lo:hi].copy_(st.view([hi - lo, max_length] + list(embedding_model.input_dims)), non_blocking=True)
+            st.record_stream(copy_stream)
+    cur.wait_stream(copy_stream)
+    return states_host

@@ -257,6 +257,11 @@ def test_recover_tensor_core_kernel(dev, kind, n):
     print(f"recover {kind} N={n}: rel-L2 tensor-core {e_tc:.2e}, SIMT {e_simt:.2e}")
     assert e_tc < TOL and e_simt < TOL
     assert float((tc - simt).abs().max()) < 1e-4 * float(ref.abs().max())
+    # the fused recover + MSE takes the same kernel at this size
+    target = ref + 0.1 * torch.from_numpy(synth.normal_embeds((n, 3), 913))
+    want = torch.nn.functional.mse_loss(ref, target)
+    got = emb.recover_mse(g.to(dev), target.to(dev))
+    assert abs(float(got) - float(want)) <= 5e-6 * float(want)
 
 
 def test_rollout_to_host_pipeline(dev):

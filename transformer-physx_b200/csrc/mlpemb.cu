@@ -253,10 +253,16 @@ __device__ __forceinline__ void rtc_mma(float (&c)[4], const uint32_t (&a)[4], u
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// With `target` != null it is also the fused recover + MSE (x may then be null): per-CTA squared-error sums go to
+// partial[blockIdx.x], as in the FP32 kernel.
 __global__ void __launch_bounds__(RTC_THREADS, 1) mlp_recover_tc_kernel(const float* __restrict__ blob, MlpLayout L,
                                                                         const float* __restrict__ g,
-                                                                        float* __restrict__ x, long long N) {
+                                                                        float* __restrict__ x, long long N,
+                                                                        const float* __restrict__ target,
+                                                                        float* __restrict__ partial) {
     extern __shared__ __align__(16) float smf[];
+    __shared__ float red[RTC_THREADS / 32];
+    float sq = 0.f;
     const int Hd = L.Hd, Hp = (Hd + 7) & ~7;
     uint32_t* whi = reinterpret_cast<uint32_t*>(smf);         // [Hp][36] TF32 hi plane of V1[n][k]
     uint32_t* wlo = whi + Hp * RTC_LD;                         // lo plane (FP32 remainder)
@@ -321,9 +327,26 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) mlp_recover_tc_kernel(const fl
         if (q == 0) {
 #pragma unroll
             for (int c = 0; c < MS; c++) {                   // _unnormalize, embedding_lorenz.py:162-163
-                if (r0 < N) x[r0 * MS + c] = sd[c] * (y0[c] + c2[c]) + mu[c];
-                if (r1 < N) x[r1 * MS + c] = sd[c] * (y1[c] + c2[c]) + mu[c];
+                const float v0 = sd[c] * (y0[c] + c2[c]) + mu[c], v1 = sd[c] * (y1[c] + c2[c]) + mu[c];
+                if (x != nullptr) {
+                    if (r0 < N) x[r0 * MS + c] = v0;
+                    if (r1 < N) x[r1 * MS + c] = v1;
+                }
+                if (target != nullptr) {
+                    if (r0 < N) { const float d = v0 - target[r0 * MS + c]; sq = fmaf(d, d, sq); }
+                    if (r1 < N) { const float d = v1 - target[r1 * MS + c]; sq = fmaf(d, d, sq); }
+                }
             }
+        }
+    }
+    if (partial != nullptr) {
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < nw; i++) t += red[i];
+            partial[blockIdx.x] = t;
         }
     }
 }
@@ -519,7 +542,7 @@ int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g, float* x, long long N, 
         TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         const long long ntiles = (N + 15) / 16;
         const int grid = (int)std::min<long long>(h->sm_count, (ntiles + RTC_THREADS / 32 - 1) / (RTC_THREADS / 32));
-        mlp_recover_tc_kernel<<<grid, RTC_THREADS, smem_tc, (cudaStream_t)stream>>>(h->blob, L, g, x, N);
+        mlp_recover_tc_kernel<<<grid, RTC_THREADS, smem_tc, (cudaStream_t)stream>>>(h->blob, L, g, x, N, nullptr, nullptr);
         TRPX_CUDA(cudaGetLastError());
         return TRPX_OK;
     }
@@ -544,16 +567,27 @@ int trpx_mlpemb_recover_mse(trpx_mlpemb_t h, const float* g, const float* target
     DeviceGuard guard(h->device);
     const MlpLayout L = MlpLayout::make(h->cfg.hidden);
     const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
-    const int grid = emb_grid(h, N, 3);
+    const int Hp = (L.Hd + 7) & ~7;
+    const size_t smem_tc = sizeof(float) * ((size_t)2 * Hp * RTC_LD + (size_t)4 * Hp);
+    const bool tc = h->recover_mode != 1 && N >= 16384 && smem_tc + 1024 <= (size_t)h->smem_optin;
+    const long long ntiles = (N + 15) / 16;
+    const int grid = tc ? (int)std::min<long long>(h->sm_count, (ntiles + RTC_THREADS / 32 - 1) / (RTC_THREADS / 32))
+                        : emb_grid(h, N, 3);
     if (h->mse_partial == nullptr || h->mse_partial_n < grid) {
         if (h->mse_partial) TRPX_CUDA(cudaFree(h->mse_partial));
         h->mse_partial = nullptr;
         TRPX_CUDA(cudaMalloc(&h->mse_partial, sizeof(float) * grid));
         h->mse_partial_n = grid;
     }
-    TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_recover_kernel<<<grid, EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, g, states_or_null, N, target,
-                                                                           h->mse_partial);
+    if (tc) {
+        TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        mlp_recover_tc_kernel<<<grid, RTC_THREADS, smem_tc, (cudaStream_t)stream>>>(h->blob, L, g, states_or_null, N, target,
+                                                                                     h->mse_partial);
+    } else {
+        TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_recover_kernel<<<grid, EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, g, states_or_null, N, target,
+                                                                               h->mse_partial);
+    }
     TRPX_CUDA(cudaGetLastError());
     sum_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->mse_partial, grid, 1.0f / ((float)N * (float)MS), mse_dev);
     TRPX_CUDA(cudaGetLastError());

@@ -21,6 +21,8 @@ N>1 is weak scaling: every GPU runs its own 65,536-trajectory shard.  No collect
 exist on the GPU box) and prints the same line with "impl": "reference".
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -404,10 +406,28 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on
+    # stdout at communicator creation), so file descriptor 1 points at stderr while the benchmark runs and the JSON
+    # line is written to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    out = [l for l in buf.getvalue().splitlines() if l.strip()]
+    for l in out[:-1]:
+        print(l, file=sys.stderr)
+    if out:
+        print(out[-1], flush=True)
 
 
 if __name__ == "__main__":

@@ -2993,14 +2993,16 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             int nc = 0;
             TRPX_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel_of(g), &q));
             G = g; max_clusters = nc;
-            if ((B + g - 1) / g <= nc) break;
+            // automatic selection also accepts TWO waves of single-trajectory clusters (2 x 51 us per step still beats
+            // the generic kernel's 123 us)
+            if ((B + g - 1) / g <= nc || (h->tune_variant == 0 && g == 1 && B <= 2 * nc)) break;
         }
         const int ngroups = G ? (B + G - 1) / G : 0;
         // measured (profiles/README.md): one wave of clusters of 1-2 trajectories (st.async exchange) runs a step in
         // 51-58 us against the generic kernel's 123 us; larger groups (cluster-barrier exchange) lose to it
         const bool want = G && max_clusters > 0 &&
                           (h->tune_variant == 7 || h->tune_variant == 9 ||
-                           (h->tune_variant == 0 && G <= 2 && ngroups <= max_clusters));
+                           (h->tune_variant == 0 && G <= 2 && ngroups <= (G == 1 ? 2 : 1) * max_clusters));
         if (want) {
             int rc = ensure_kv(h, (size_t)ngroups * G * kv_per_traj);
             if (rc) return rc;

@@ -305,10 +305,13 @@ __global__ void __launch_bounds__(TR_THREADS) train_fwd_bwd_kernel(TrainParams p
             const int i = pair / H, hh = pair - i * H;
             float* Prow = P + (size_t)warp * T;                         // per-warp scratch row (nw <= T rows used)
             attn_row(t1, i, hh, T, E, hd, Prow, lane);
-            for (int d = lane; d < hd; d += 32) {
+            // o_i = P_i . V: lanes = (key part, channel) so that all 32 lanes work for small heads; parts combined by shuffles
+            const int ld = hd < 32 ? hd : 32, nsp = 32 / ld, sp = lane / ld;
+            for (int d = lane % ld; d < hd; d += ld) {
                 float acc = 0.f;
-                for (int j = 0; j <= i; j++) acc = fmaf(Prow[j], t1[j * LQ + 2 * E + hh * hd + d], acc);
-                t2[i * E + hh * hd + d] = acc;
+                for (int j = sp; j <= i; j += nsp) acc = fmaf(Prow[j], t1[j * LQ + 2 * E + hh * hd + d], acc);
+                for (int o = ld; o < 32; o <<= 1) acc += __shfl_xor_sync(FULL, acc, o);
+                if (sp == 0) t2[i * E + hh * hd + d] = acc;
             }
             __syncwarp();
         }
@@ -471,6 +474,7 @@ int trpx_gpt2_train_fwd_bwd(trpx_gpt2_t h, const float* x, const float* labels, 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t TE = (size_t)T * L.E;
     TRPX_REQUIRE(TE <= 2048, "training step supports T * n_embd <= 2048");   // unit counts of mm_xwT<MAXU>
+    TRPX_REQUIRE((L.hd & (L.hd - 1)) == 0, "training step supports power-of-two head sizes");
     const size_t smem = sizeof(float) * (TE * 17 + ((size_t)std::max(T, TR_THREADS / 32) + T) * T + STAGE_FLOATS);
     TRPX_REQUIRE(smem + 1024 <= (size_t)h->smem_optin, "training step needs %zu B of shared memory per sequence", smem);
     const size_t acts_per_seq = (size_t)L.n_layer * 12 * TE + 2 * TE;

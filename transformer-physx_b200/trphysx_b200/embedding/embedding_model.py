@@ -1,55 +1,68 @@
-"""Base classes of the drop-in embedding modules (reference: trphysx/embedding/embedding_model.py:19-147)."""
-import os
-from abc import abstractmethod
+"""Common parents of the Koopman embedding modules and of their training heads.
+
+They carry the part of the reference interface that is not arithmetic (trphysx/embedding/embedding_model.py:19-147):
+the `model_name` / checkpoint convention, the shape and device properties the trainers query, and the rule that the
+compute methods of this package run CUDA kernels which do not record an autograd graph."""
+from typing import List
 
 import torch
 from torch import nn
 
+from ..checkpoint import read_state_dict, write_state_dict
+
 
 class EmbeddingModel(nn.Module):
+    """Parent of LorenzEmbedding / RosslerEmbedding / CylinderEmbedding.
+
+    Subclasses provide `embed`, `recover`, `koopmanOperation`, `koopmanOperator` and `koopmanDiag`; all of them are
+    ctypes calls into libtrpx on the current CUDA stream."""
+
     model_name: str = "embedding_model"
 
     def __init__(self, config):
         super().__init__()
         self.config = config
 
-    @abstractmethod
+    # -- what subclasses must supply -----------------------------------------------------------------------------
     def embed(self, x):
-        raise NotImplementedError("embed function has not been properly overridden")
+        raise NotImplementedError(type(self).__name__ + " does not implement embed()")
 
-    @abstractmethod
     def recover(self, x):
-        raise NotImplementedError("recover function has not been properly overridden")
+        raise NotImplementedError(type(self).__name__ + " does not implement recover()")
 
     @property
-    @abstractmethod
     def koopmanOperator(self):
-        pass
+        raise NotImplementedError(type(self).__name__ + " does not implement koopmanOperator")
 
     @property
-    @abstractmethod
     def koopmanDiag(self):
-        pass
+        raise NotImplementedError(type(self).__name__ + " does not implement koopmanDiag")
+
+    # -- bookkeeping the trainers rely on ------------------------------------------------------------------------
+    @property
+    def embed_dims(self) -> int:
+        return self.config.n_embd
 
     @property
     def input_dims(self):
         return self.config.state_dims
 
     @property
-    def embed_dims(self):
-        return self.config.n_embd
+    def num_parameters(self) -> int:
+        total = 0
+        for p in self.parameters():
+            total += p.numel()
+        return total
 
     @property
-    def num_parameters(self):
-        return sum(p.numel() for p in self.parameters())
-
-    @property
-    def devices(self):
-        devs = []
-        for t in list(self.parameters()) + list(self.buffers()):
-            if t.device not in devs:
-                devs.append(t.device)
-        return devs
+    def devices(self) -> List[torch.device]:
+        """Distinct devices holding parameters or buffers, in first-seen order."""
+        seen = {}
+        for t in self.parameters():
+            seen.setdefault(t.device, None)
+        for t in self.buffers():
+            seen.setdefault(t.device, None)
+        return list(seen)
 
     def _inference_only(self, what: str):
         """The kernels behind embed/recover/koopmanOperation do not record an autograd graph."""
@@ -58,35 +71,30 @@ class EmbeddingModel(nn.Module):
                 f"{what}: autograd through the native kernels is not provided. Use the fused training head "
                 "(e.g. LorenzEmbeddingTrainer) for gradients, or call under torch.no_grad() / model.eval().")
 
+    # -- checkpoints -----------------------------------------------------------------------------------------------
     def save_model(self, save_directory: str, epoch: int = 0) -> None:
-        if os.path.isfile(save_directory):
-            raise FileNotFoundError(f"Provided path ({save_directory}) should be a directory, not a file")
-        os.makedirs(save_directory, exist_ok=True)
-        torch.save(self.state_dict(), os.path.join(save_directory, f"{self.model_name}{epoch:d}.pth"))
+        write_state_dict(self, save_directory, epoch)
 
     def load_model(self, file_or_path_directory: str, epoch: int = 0) -> None:
-        if os.path.isfile(file_or_path_directory):
-            path = file_or_path_directory
-        elif os.path.isdir(file_or_path_directory):
-            path = os.path.join(file_or_path_directory, f"{self.model_name}{epoch:d}.pth")
-        else:
-            raise FileNotFoundError(f"Provided path or file ({file_or_path_directory}) does not exist")
-        self.load_state_dict(torch.load(path, map_location=lambda storage, loc: storage))
+        read_state_dict(self, file_or_path_directory, epoch)
 
 
 class EmbeddingTrainingHead(nn.Module):
-    @abstractmethod
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("forward function has not been properly overridden")
+    """Parent of the `*EmbeddingTrainer` heads: owns `embedding_model` and forwards checkpoint I/O to it."""
 
-    @abstractmethod
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(type(self).__name__ + " does not implement forward()")
+
     def evaluate(self, *args, **kwargs):
-        raise NotImplementedError("evaluate function has not been properly overridden")
+        raise NotImplementedError(type(self).__name__ + " does not implement evaluate()")
+
+    def _model(self) -> EmbeddingModel:
+        model = getattr(self, "embedding_model", None)
+        assert model is not None, "the training head has no embedding_model yet"
+        return model
 
     def save_model(self, *args, **kwargs):
-        assert self.embedding_model is not None, "Must initialize embedding model before saving."
-        self.embedding_model.save_model(*args, **kwargs)
+        self._model().save_model(*args, **kwargs)
 
     def load_model(self, *args, **kwargs):
-        assert self.embedding_model is not None, "Must initialize embedding model before loading."
-        self.embedding_model.load_model(*args, **kwargs)
+        self._model().load_model(*args, **kwargs)

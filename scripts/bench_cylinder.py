@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "transformer-physx_b200")):
     sys.path.insert(0, p)
 import torch  # noqa: E402
-from oracle import synth, trpx_oracle as O  # noqa: E402
+from tests import synth
+from oracle import trpx_oracle as O  # noqa: E402
 from tests.util import make_cylinder, make_gpt2  # noqa: E402
 
 DEC_FLOPS = 234_749_952      # SURVEY.md Appendix B, per frame

@@ -12,7 +12,8 @@ for p in (ROOT, os.path.join(ROOT, "transformer-physx_b200")):
     sys.path.insert(0, p)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
-from oracle import synth, trpx_oracle as O  # noqa: E402
+from tests import synth
+from oracle import trpx_oracle as O  # noqa: E402
 from tests.util import torch_sd  # noqa: E402
 
 

@@ -16,7 +16,21 @@ GPT2_CASES = {
     # Cylinder shape (E=128, 6 layers, hd=32, n_ctx=16)
     "cylinder_init":   dict(kind="cylinder", seed=106, stress=False, B=2, T=16, Tp=6, T2=10, ctx=1, max_length=48),
     "cylinder_stress": dict(kind="cylinder", over=dict(n_layer=3), seed=107, stress=True, B=2, T=16, Tp=5, T2=11, ctx=1, max_length=40),
+    # sigma = 0.1 stress weights: the cached rollout stays well conditioned over the WHOLE horizon (3 x n_ctx + a few
+    # steps) without collapsing to a fixed point (consecutive tokens still differ by ~1 % at 2 x n_ctx), so every token
+    # produced with a full / wrapped KV ring is compared.  B >= 32 so the production trajectories-per-warp groupings
+    # (8 for n_ctx 32, 4 for n_ctx 64) get several full groups plus a ragged one.  fwdB: batch of the teacher-forced part (keeps the fixture small).
+    "rossler_sigma01": dict(kind="rossler", seed=108, stress=True, sigma=0.1, B=40, fwdB=3, T=32, Tp=9, T2=23, ctx=1, max_length=101),
+    "lorenz_sigma01":  dict(kind="lorenz", seed=109, stress=True, sigma=0.1, B=36, fwdB=3, T=64, Tp=21, T2=43, ctx=2, max_length=200),
 }
+
+
+def weights_kw(c):
+    """Keyword arguments of tests.synth.gpt2_weights for a case (stress weights default to sigma = 0.3)."""
+    kw = dict(stress=c["stress"])
+    if "sigma" in c:
+        kw["stress_sigma"] = c["sigma"]
+    return kw
 
 LORENZ_CASES = {
     "lorenz":  dict(kind="lorenz", seed=201, N=37),

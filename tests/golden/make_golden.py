@@ -13,8 +13,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import ref_shim, synth  # noqa: E402
-from tests.golden.cases import (GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES,  # noqa: E402
+from tests import synth
+from oracle import ref_shim  # noqa: E402
+from tests.golden.cases import (weights_kw, GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES,  # noqa: E402
                                 CYL_TRAIN_CASES)
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -26,16 +27,18 @@ def _t(sd):
     return {k: torch.from_numpy(np.array(v)) for k, v in sd.items()}
 
 
-def gpt2_cases(trphysx):
+def gpt2_cases(trphysx, only=None):
     from trphysx.transformer import PhysformerGPT2
     from trphysx.config.configuration_phys import PhysConfig
     for name, c in GPT2_CASES.items():
+        if only and name not in only:
+            continue
         cfg_ns = synth.make_config(c["kind"], **c.get("over", {}))
         cfg = PhysConfig(**vars(cfg_ns))
         model = PhysformerGPT2(cfg, "golden").eval()
-        model.load_state_dict(_t(synth.gpt2_weights(cfg_ns, c["seed"], stress=c["stress"])), strict=True)
+        model.load_state_dict(_t(synth.gpt2_weights(cfg_ns, c["seed"], **weights_kw(c))), strict=True)
         out = {}
-        B, T = c["B"], c["T"]
+        B, T = c.get("fwdB", c["B"]), c["T"]
         x = torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), c["seed"] + 1))
         with torch.no_grad():
             hid, presents = model(x, use_cache=True)
@@ -50,7 +53,7 @@ def gpt2_cases(trphysx):
                 hid2, pres2 = model(x2, past=past, use_cache=True)
                 out["fwd2_hidden"] = hid2.numpy()
                 out["fwd2_present_last"] = pres2[-1].numpy()
-            ctx = torch.from_numpy(synth.normal_embeds((B, c["ctx"], cfg.n_embd), c["seed"] + 3))
+            ctx = torch.from_numpy(synth.normal_embeds((c["B"], c["ctx"], cfg.n_embd), c["seed"] + 3))
             g1 = model.generate(ctx, max_length=c["max_length"], use_cache=True)
             out["gen_cache"] = g1[0].numpy()
             out["gen_cache_present_last"] = g1[1][-1].numpy()
@@ -183,6 +186,8 @@ if __name__ == "__main__":
         gpt2_train_cases(t)                                        # added later: leaves the other fixtures untouched
     elif len(sys.argv) > 1 and sys.argv[1] == "cyltrain":
         cyl_train_cases(t)
+    elif len(sys.argv) > 2 and sys.argv[1] == "gpt2":              # python make_golden.py gpt2 <case> [<case> ...]
+        gpt2_cases(t, only=sys.argv[2:])
     else:
         cyl_train_cases(t)
         gpt2_cases(t)

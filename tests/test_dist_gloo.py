@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oracle import synth, trpx_oracle as O
+from tests import synth
+from oracle import trpx_oracle as O
 
 
 def _free_port():

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import synth, trpx_oracle as O
+from tests import synth
+from oracle import trpx_oracle as O
 from tests.golden.cases import LORENZ_CASES, CYL_CASES, TRAIN_CASES, CYL_TRAIN_CASES
 from tests.util import make_lorenz, make_cylinder, torch_sd
 
@@ -282,3 +283,41 @@ def test_rollout_to_host_pipeline(dev):
     ref = emb.recover(out.view(B * (S + 1), cfg.n_embd)).view(B, S + 1, 3)
     # chunks of 5,271 samples take the FP32 recover kernel, the single call (21,063 samples) the tensor-core one
     assert O.rel_l2(host, ref.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("B,S,auto_variant", [(6, 400, 7), (64, 400, 1)])
+def test_cylinder_end_to_end_config4(dev, B, S, auto_variant):
+    """BASELINE config 4 end to end through the public modules: CylinderEmbedding.embed(x0, visc) -> PhysformerGPT2.
+    generate(max_length = 401, use_cache=True) -> CylinderEmbedding.recover, against the oracle's embed / generate /
+    recover.  B = 6 takes the cluster rollout kernel, B = 64 rollout_generic_kernel<G>1> (automatic selection).  The
+    embedded rollout is compared over the whole horizon; the recovered fields for every trajectory at a spread of time
+    steps (the oracle's decoder costs 0.23 GFLOP per frame on the CPU)."""
+    from tests.util import make_gpt2, stable_prefix
+    cfg = synth.make_config("cylinder")
+    emb = make_cylinder(cfg, 931, dev)
+    w_t = synth.gpt2_weights(cfg, 932, stress=True, stress_sigma=0.05)
+    tr = make_gpt2(cfg, 932, True, dev, sigma=0.05)
+    sd_e = O.to_torch(synth.cylinder_embedding_weights(cfg, 931))
+    x, visc = synth.cylinder_fields(B, seed=933)
+    x, visc = torch.from_numpy(x), torch.from_numpy(visc)
+    with torch.no_grad():
+        g0 = emb.embed(x.to(dev), visc.to(dev))
+        out = tr.generate(g0.unsqueeze(1), max_length=S + 1, use_cache=True, return_presents=False)[0]
+        info = tr.last_launch()
+        assert info["variant"] == auto_variant and (B == 6 or info["group"] > 1), info
+        fields = emb.recover(out.reshape(-1, cfg.n_embd)).view(B, S + 1, 3, 64, 128)
+    g0_ref = O.cylinder_embed(sd_e, cfg, x, visc)
+    assert O.rel_l2(g0.cpu(), g0_ref) < TOL
+    n, ref = stable_prefix(cfg, w_t, g0_ref.unsqueeze(1), S + 1, True)
+    assert n == S + 1, n
+    got = out.cpu()
+    err = O.rel_l2(got, ref)
+    per_step = (got - ref).norm(dim=2).max(0).values / ref.norm(dim=2).max(0).values
+    print(f"cylinder end-to-end B={B}: launch {info}, embedded rollout rel-L2 {err:.2e}, worst step {float(per_step.max()):.2e}")
+    assert err < TOL and float(per_step.max()) < 3 * TOL
+    steps = [0, 1, 15, 16, 17, 100, 250, S] if B <= 8 else [0, 17, S]
+    ref_fields = O.cylinder_recover(sd_e, cfg, ref[:, steps].reshape(-1, cfg.n_embd)).view(B, len(steps), 3, 64, 128)
+    ferr = O.rel_l2(fields[:, steps].cpu(), ref_fields)
+    print(f"cylinder end-to-end B={B}: recovered fields rel-L2 {ferr:.2e} over {B * len(steps)} frames")
+    assert ferr < TOL
+    assert int((fields[:, steps][:, :, 0] == 0).sum()) >= 196 * B * len(steps)      # cylinder cells are masked

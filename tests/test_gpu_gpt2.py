@@ -7,8 +7,9 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import synth, trpx_oracle as O
-from tests.golden.cases import GPT2_CASES, GPT2_TRAIN_CASES
+from tests import synth
+from oracle import trpx_oracle as O
+from tests.golden.cases import GPT2_CASES, GPT2_TRAIN_CASES, weights_kw
 from tests.util import make_gpt2, stable_prefix, torch_sd
 
 pytestmark = pytest.mark.gpu
@@ -29,8 +30,8 @@ def test_forward_matches_reference(golden_dir, dev, name):
     c = GPT2_CASES[name]
     gold = _gold(golden_dir, name)
     cfg = synth.make_config(c["kind"], **c.get("over", {}))
-    m = make_gpt2(cfg, c["seed"], c["stress"], dev)
-    B, T, E = c["B"], c["T"], cfg.n_embd
+    m = make_gpt2(cfg, c["seed"], c["stress"], dev, sigma=c.get("sigma"))
+    B, T, E = c.get("fwdB", c["B"]), c["T"], cfg.n_embd
     x = torch.from_numpy(synth.normal_embeds((B, T, E), c["seed"] + 1)).to(dev)
     with torch.no_grad():
         hid, presents = m(x, use_cache=True)
@@ -55,9 +56,9 @@ def test_generate_matches_reference(golden_dir, dev, name, variant):
     c = GPT2_CASES[name]
     gold = _gold(golden_dir, name)
     cfg = synth.make_config(c["kind"], **c.get("over", {}))
-    m = make_gpt2(cfg, c["seed"], c["stress"], dev)
+    m = make_gpt2(cfg, c["seed"], c["stress"], dev, sigma=c.get("sigma"))
     m.set_rollout_tuning(variant=variant)
-    w_np = synth.gpt2_weights(cfg, c["seed"], stress=c["stress"])
+    w_np = synth.gpt2_weights(cfg, c["seed"], **weights_kw(c))
     ctx_cpu = torch.from_numpy(synth.normal_embeds((c["B"], c["ctx"], cfg.n_embd), c["seed"] + 3))
     ctx = ctx_cpu.to(dev)
     n1, _ = stable_prefix(cfg, w_np, ctx_cpu, c["max_length"], True)
@@ -424,3 +425,128 @@ def test_fused_transformer_step_equals_reference_loop(dev):
     ref, _ = O.gpt2_generate(new_sd, cfg, x0, 20, use_cache=True)
     out = m.generate(x0.to(dev), max_length=20, use_cache=True)[0]
     assert O.rel_l2(out.cpu(), ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Saturated / wrapped KV ring at the production n_ctx with the production groupings
+# ------------------------------------------------------------------------------------------------------------------
+_SAT = [("rossler_sigma01", 2, 8), ("rossler_sigma01", 2, 4), ("rossler_sigma01", 2, 2), ("rossler_sigma01", 5, 0),
+        ("rossler_sigma01", 6, 0), ("rossler_sigma01", 8, 0), ("rossler_sigma01", 1, 4),
+        ("lorenz_sigma01", 2, 4), ("lorenz_sigma01", 2, 8), ("lorenz_sigma01", 2, 1), ("lorenz_sigma01", 5, 0),
+        ("lorenz_sigma01", 6, 0), ("lorenz_sigma01", 8, 0), ("lorenz_sigma01", 1, 8)]
+
+
+@pytest.mark.parametrize("name,variant,G", _SAT)
+def test_saturated_window_production_groups(golden_dir, dev, name, variant, G):
+    """sigma = 0.1 stress weights keep the cached rollout well conditioned over 3 x n_ctx steps WITHOUT collapsing
+    (step-to-step change ~1 % at 2 x n_ctx), so tokens produced with a full and a wrapped ring are compared with the
+    reference's recorded rollout (gpt2_*_sigma01.npz) for every kernel and the production groupings: Rossler
+    (n_ctx 32) 8 trajectories per warp, Lorenz (n_ctx 64) 4 per warp (`FULLW` instantiations), the 16-per-warp kernels
+    (5, 6), the TMA-staged window kernel (8) and the generic kernel with G > 1."""
+    c = GPT2_CASES[name]
+    gold = _gold(golden_dir, name)
+    cfg = synth.make_config(c["kind"])
+    w_np = synth.gpt2_weights(cfg, c["seed"], **weights_kw(c))
+    m = make_gpt2(cfg, c["seed"], True, dev, sigma=c["sigma"])
+    m.set_rollout_tuning(variant=variant, traj_per_warp=G)
+    ctx_cpu = torch.from_numpy(synth.normal_embeds((c["B"], c["ctx"], cfg.n_embd), c["seed"] + 3))
+    n, ref = stable_prefix(cfg, w_np, ctx_cpu, c["max_length"], True)
+    assert n == c["max_length"] and n >= 3 * cfg.n_ctx, n        # the whole horizon is well conditioned ...
+    step = (ref[:, 1:] - ref[:, :-1]).norm(dim=2) / ref[:, 1:].norm(dim=2)
+    assert float(step[:, 2 * cfg.n_ctx].median()) > 1e-3          # ... and has not collapsed to a fixed point
+    out = m.generate(ctx_cpu.to(dev), max_length=c["max_length"], use_cache=True)
+    info = m.last_launch()
+    assert info["variant"] == variant and (G == 0 or info["group"] == G), info
+    got = out[0].cpu()
+    g_ref = torch.from_numpy(gold["gen_cache"])
+    assert O.rel_l2(got, g_ref) < TOL
+    per_step = (got - g_ref).norm(dim=2).max(0).values / g_ref.norm(dim=2).max(0).values
+    assert float(per_step.max()) < 3 * TOL, int(per_step.argmax())
+    late = slice(2 * cfg.n_ctx, None)                             # tokens produced with a wrapped ring only
+    assert O.rel_l2(got[:, late], g_ref[:, late]) < TOL
+    assert O.rel_l2(out[1][-1].cpu(), gold["gen_cache_present_last"]) < TOL
+    _, ref_pres = O.gpt2_generate(O.to_torch(w_np), cfg, ctx_cpu, c["max_length"], use_cache=True)
+    for l in range(cfg.n_layer):
+        assert O.rel_l2(out[1][l].cpu(), ref_pres[l]) < TOL
+    print(f"saturated window {name} variant={variant} G={info['group']}: rel-L2 {O.rel_l2(got, g_ref):.2e}, "
+          f"worst step {float(per_step.max()):.2e}")
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+@pytest.mark.parametrize("B,S", [(64, 40), (300, 24), (512, 20)])
+def test_rollout_generic_kernel_groups_cylinder(dev, B, S, G):
+    """rollout_generic_kernel<G> for G in {2, 4, 8} on the Cylinder-size transformer (the kernel BASELINE config 4 runs
+    from B = 64 on): ragged last group (B = 300 with G = 8), horizons beyond n_ctx = 16 (wrapped ring), both cache
+    modes, presents."""
+    cfg = synth.make_config("cylinder")
+    w_np = synth.gpt2_weights(cfg, 905, stress=True, stress_sigma=0.05)    # well conditioned over 40+ steps, not collapsed
+    m = make_gpt2(cfg, 905, True, dev, sigma=0.05)
+    m.set_rollout_tuning(variant=1, traj_per_warp=G)
+    x0 = torch.from_numpy(synth.normal_embeds((B, 1, cfg.n_embd), 81))
+    for uc in (True, False):
+        n, ref = stable_prefix(cfg, w_np, x0, S + 1, uc)
+        out = m.generate(x0.to(dev), max_length=S + 1, use_cache=uc)
+        info = m.last_launch()
+        assert info["variant"] == 1 and info["group"] == G and info["grid"] == (B + G - 1) // G, info
+        got = out[0].cpu()
+        assert n == S + 1, n
+        err = O.rel_l2(got[:, :n], ref[:, :n])
+        print(f"generic G={G} B={B} use_cache={uc}: rel-L2 {err:.2e} over {n} tokens")
+        assert err < TOL
+        if uc:
+            per_step = (got - ref).norm(dim=2).max(0).values / ref.norm(dim=2).max(0).values
+            assert float(per_step.max()) < 3 * TOL
+            _, ref_pres = O.gpt2_generate(O.to_torch(w_np), cfg, x0, S + 1, use_cache=True)
+            for l in range(cfg.n_layer):
+                assert O.rel_l2(out[1][l].cpu(), ref_pres[l]) < TOL
+
+
+@pytest.mark.parametrize("variant,G", [(7, 1), (7, 2), (9, 1), (9, 2), (7, 4), (7, 8), (7, 16)])
+@pytest.mark.parametrize("B", [7, 70])
+def test_rollout_cluster_kernel_wrapped_ring(dev, B, variant, G):
+    """Cluster kernels over a horizon of 2.5 x n_ctx with weights that keep the whole horizon well conditioned (the
+    sigma = 0.08 cases above only compare the first few tokens): the wrapped ring of every group size is compared."""
+    cfg = synth.make_config("cylinder")
+    w_np = synth.gpt2_weights(cfg, 905, stress=True, stress_sigma=0.05)
+    m = make_gpt2(cfg, 905, True, dev, sigma=0.05)
+    m.set_rollout_tuning(variant=variant, traj_per_warp=G)
+    S = 40
+    x0 = torch.from_numpy(synth.normal_embeds((B, 1, cfg.n_embd), 82))
+    n, ref = stable_prefix(cfg, w_np, x0, S + 1, True)
+    assert n == S + 1
+    out = m.generate(x0.to(dev), max_length=S + 1, use_cache=True)
+    info = m.last_launch()
+    assert info["variant"] == variant and info["group"] == G, info
+    got = out[0].cpu()
+    assert O.rel_l2(got, ref) < TOL
+    per_step = (got - ref).norm(dim=2).max(0).values / ref.norm(dim=2).max(0).values
+    assert float(per_step.max()) < 3 * TOL
+    _, ref_pres = O.gpt2_generate(O.to_torch(w_np), cfg, x0, S + 1, use_cache=True)
+    for l in range(cfg.n_layer):
+        assert O.rel_l2(out[1][l].cpu(), ref_pres[l]) < TOL
+
+
+def test_module_copies_do_not_free_live_handles(dev):
+    """ADVICE r01: deepcopy / shallow copy / DataParallel-style replicas of a module that already holds a native handle;
+    collecting the copy must leave the original's handle alive, and each copy must compute the same rollout."""
+    import copy
+    import gc
+    cfg = synth.make_config("rossler")
+    m = make_gpt2(cfg, 5, True, dev)
+    x = torch.from_numpy(synth.normal_embeds((9, 1, 32), 9)).to(dev)
+    want = m.generate(x, max_length=20, use_cache=True)[0]
+    for make in (copy.deepcopy, copy.copy, lambda mod: mod._replicate_for_data_parallel()):
+        c = make(m)
+        assert torch.equal(c.generate(x, max_length=20, use_cache=True)[0], want)
+        del c
+        gc.collect()
+        torch.cuda.synchronize()
+        assert torch.equal(m.generate(x, max_length=20, use_cache=True)[0], want)
+    m.h[0].mlp.c_fc.weight.data.mul_(1.25)             # a write torch's version counter cannot see ...
+    m.invalidate_weights()                               # ... needs the explicit invalidation
+    got = m.generate(x, max_length=20, use_cache=True)[0]
+    assert not torch.equal(got, want)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref, _ = O.gpt2_generate(sd, cfg, x.cpu(), 20, use_cache=True)
+    n, _ = stable_prefix(cfg, {k: v.numpy() for k, v in sd.items()}, x.cpu(), 20, True)
+    assert n >= 5 and O.rel_l2(got.cpu()[:, :n], ref[:, :n]) < TOL

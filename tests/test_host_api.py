@@ -3,7 +3,8 @@ error behaviour, sharding helper.  Where /root/reference is present the key sets
 import pytest
 import torch
 
-from oracle import ref_shim, synth
+from tests import synth
+from oracle import ref_shim
 from tests.util import torch_sd
 from trphysx_b200 import AutoEmbeddingModel, AutoPhysConfig, AutoPhysTransformer, shard_bounds
 from trphysx_b200.config import CylinderConfig, LorenzConfig, PhysConfig, RosslerConfig
@@ -159,3 +160,35 @@ def test_training_entry_points_refuse_cpu():
     emb = RosslerEmbedding(RosslerConfig())
     with pytest.raises(NotImplementedError):
         eval_states(emb, x, torch.zeros(2, 4, 3))
+
+
+def test_native_handles_are_not_copyable_state():
+    """module copies must never share-and-free native handles.  deepcopy / pickle give the copy a fresh
+    empty cache; shallow copies (copy.copy, nn.DataParallel replicas take __dict__.copy()) share ONE owner object
+    whose finalizer is the only destroyer."""
+    import copy
+    import io
+    from trphysx_b200 import _native as N
+    destroyed = []
+    real = N.HandleCache._destroy_all
+    try:
+        N.HandleCache._destroy_all = staticmethod(lambda entries, sym: (destroyed.append((sym, list(entries))), entries.clear()))
+        for m, sym in ((PhysformerGPT2(LorenzConfig(), "x"), "trpx_gpt2_destroy"),
+                       (LorenzEmbedding(LorenzConfig()), "trpx_mlpemb_destroy"),
+                       (CylinderEmbedding(CylinderConfig()), "trpx_cyl_destroy")):
+            assert isinstance(m._handles, N.HandleCache) and m._handles.destroy_symbol == sym
+            assert not hasattr(type(m), "__del__")
+            m._handles[0] = ("fake-handle", N.WeightTracker())         # pretend a kernel call created one
+            deep = copy.deepcopy(m)
+            assert deep._handles is not m._handles and len(deep._handles) == 0 and len(m._handles) == 1
+            shallow = copy.copy(m)
+            assert shallow._handles is m._handles
+            buf = io.BytesIO()
+            torch.save(m, buf)                                          # ctypes pointers used to make this raise
+            buf.seek(0)
+            loaded = torch.load(buf, weights_only=False)
+            assert len(loaded._handles) == 0 and loaded._handles.destroy_symbol == sym
+            m.invalidate_weights()
+            assert m._handles[0][1].key is None
+    finally:
+        N.HandleCache._destroy_all = real

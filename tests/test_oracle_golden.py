@@ -6,8 +6,9 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import synth, trpx_oracle as O
-from tests.golden.cases import GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES
+from tests import synth
+from oracle import trpx_oracle as O
+from tests.golden.cases import weights_kw, GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES
 
 TOL = 2e-6          # both sides are torch-CPU fp32 executing the same aten ops; only threading differs
 
@@ -21,8 +22,8 @@ def test_gpt2_oracle_matches_reference(golden_dir, name):
     c = GPT2_CASES[name]
     gold = _load(golden_dir, f"gpt2_{name}.npz")
     cfg = synth.make_config(c["kind"], **c.get("over", {}))
-    sd = O.to_torch(synth.gpt2_weights(cfg, c["seed"], stress=c["stress"]))
-    B, T, E = c["B"], c["T"], cfg.n_embd
+    sd = O.to_torch(synth.gpt2_weights(cfg, c["seed"], **weights_kw(c)))
+    B, T, E = c.get("fwdB", c["B"]), c["T"], cfg.n_embd
     x = torch.from_numpy(synth.normal_embeds((B, T, E), c["seed"] + 1))
     hid, presents, _ = O.gpt2_forward(sd, cfg, x, use_cache=True)
     assert O.rel_l2(hid, gold["fwd_hidden"]) < TOL
@@ -33,7 +34,7 @@ def test_gpt2_oracle_matches_reference(golden_dir, name):
     hid2, pres2, _ = O.gpt2_forward(sd, cfg, x2, past=past, use_cache=True)
     assert O.rel_l2(hid2, gold["fwd2_hidden"]) < TOL
     assert O.rel_l2(pres2[-1], gold["fwd2_present_last"]) < TOL
-    ctx = torch.from_numpy(synth.normal_embeds((B, c["ctx"], E), c["seed"] + 3))
+    ctx = torch.from_numpy(synth.normal_embeds((c["B"], c["ctx"], E), c["seed"] + 3))
     g1, pres = O.gpt2_generate(sd, cfg, ctx, c["max_length"], use_cache=True)
     assert g1.shape == gold["gen_cache"].shape
     assert O.rel_l2(g1, gold["gen_cache"]) < 20 * TOL

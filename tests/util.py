@@ -2,19 +2,20 @@
 import numpy as np
 import torch
 
-from oracle import synth
+from tests import synth
 
 
 def torch_sd(sd_np):
     return {k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()}
 
 
-def make_gpt2(cfg_ns, seed, stress, device=None):
+def make_gpt2(cfg_ns, seed, stress, device=None, sigma=None):
     from trphysx_b200.config import PhysConfig
     from trphysx_b200.transformer import PhysformerGPT2
     cfg = PhysConfig(**vars(cfg_ns))
     m = PhysformerGPT2(cfg, "test").eval()
-    m.load_state_dict(torch_sd(synth.gpt2_weights(cfg_ns, seed, stress=stress)), strict=True)
+    kw = {} if sigma is None else {"stress_sigma": sigma}
+    m.load_state_dict(torch_sd(synth.gpt2_weights(cfg_ns, seed, stress=stress, **kw)), strict=True)
     return m.to(device) if device is not None else m
 
 
@@ -39,6 +40,18 @@ def make_cylinder(cfg_ns, seed, device=None):
 _prefix_cache = {}
 
 
+def _weights_digest(weights_np):
+    """Content hash of a weight dict: the cache key must not depend on object identity (ids are reused after GC)."""
+    import hashlib
+    h = hashlib.sha1()
+    for k in sorted(weights_np):
+        a = np.ascontiguousarray(weights_np[k])
+        h.update(k.encode())
+        h.update(str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
 def stable_prefix(cfg_ns, weights_np, ctx, max_length, use_cache, thresh=2e-6):
     """Free rollouts with the stress weights can be chaotic: the reference's OWN float32 arithmetic then drifts
     from exact arithmetic exponentially, and no implementation can match it beyond that point.  Returns
@@ -46,7 +59,8 @@ def stable_prefix(cfg_ns, weights_np, ctx, max_length, use_cache, thresh=2e-6):
     (per-token rel-L2, worst trajectory) of the same oracle run in float64 — the "stated horizon before chaotic
     divergence" of BASELINE.json — and the float32 oracle rollout itself."""
     from oracle import trpx_oracle as O
-    key = (id(weights_np), ctx.shape, float(ctx.sum()), max_length, use_cache, thresh)
+    key = (_weights_digest(weights_np), tuple(vars(cfg_ns).get(k) for k in ("n_ctx", "n_embd", "n_layer", "n_head")),
+           tuple(ctx.shape), _weights_digest({"ctx": ctx.numpy()}), max_length, use_cache, thresh)
     if key not in _prefix_cache:
         a, _ = O.gpt2_generate(O.to_torch(weights_np), cfg_ns, ctx, max_length, use_cache=use_cache)
         b, _ = O.gpt2_generate(O.to_torch(weights_np, torch.float64), cfg_ns, ctx.double(), max_length,

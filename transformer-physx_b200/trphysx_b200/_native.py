@@ -115,6 +115,61 @@ def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+class HandleCache:
+    """device index -> (native handle, WeightTracker) of ONE module, and the only owner of those handles.
+
+    The native handles are destroyed by a `weakref.finalize` of this object, never by the module's `__del__`, and the
+    cache itself is not copyable state: `copy.deepcopy(module)`, pickling (`torch.save(module)`) and
+    `copy.copy(cache)` give the copy a fresh, empty cache whose handles are created lazily on first use, while
+    shallow copies of the module's `__dict__` (`copy.copy(module)`, `nn.DataParallel` replicas) share THIS object, so
+    a handle is freed exactly once, after the last module that can reach it is gone."""
+
+    def __init__(self, destroy_symbol: str):
+        import weakref
+        self.destroy_symbol = destroy_symbol
+        self._entries = {}
+        self._finalizer = weakref.finalize(self, HandleCache._destroy_all, self._entries, destroy_symbol)
+
+    @staticmethod
+    def _destroy_all(entries, destroy_symbol):
+        try:
+            fn = getattr(lib(), destroy_symbol)
+            for h, _ in entries.values():
+                fn(h)
+        except Exception:
+            pass
+        entries.clear()
+
+    def get(self, idx):
+        return self._entries.get(idx)
+
+    def __setitem__(self, idx, entry):
+        self._entries[idx] = entry
+
+    def __getitem__(self, idx):
+        return self._entries[idx]
+
+    def __len__(self):
+        return len(self._entries)
+
+    def values(self):
+        return self._entries.values()
+
+    def invalidate(self):
+        """Forget what was packed: the next call re-sends the module's weights to every handle."""
+        for _, tracker in self._entries.values():
+            tracker.key = None
+
+    def __copy__(self):
+        return HandleCache(self.destroy_symbol)
+
+    def __deepcopy__(self, memo):
+        return HandleCache(self.destroy_symbol)
+
+    def __reduce__(self):
+        return (HandleCache, (self.destroy_symbol,))
+
+
 _weight_epoch = 0
 
 

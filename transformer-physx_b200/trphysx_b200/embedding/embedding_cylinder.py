@@ -46,7 +46,7 @@ class CylinderEmbedding(EmbeddingModel):
         self.kMatrixLT = nn.Sequential(nn.Linear(1, 50), nn.ReLU(), nn.Linear(50, nband))
         self.register_buffer("mu", torch.tensor([0.0, 0.0, 0.0, 0.0]))
         self.register_buffer("std", torch.tensor([1.0, 1.0, 1.0, 1.0]))
-        self._handles = {}
+        self._handles = N.HandleCache("trpx_cyl_destroy")
         self._last_visc = None
         self.kMatrixDiag = None
 
@@ -88,6 +88,13 @@ class CylinderEmbedding(EmbeddingModel):
             self._keepalive = tensors
         return h
 
+    def invalidate_weights(self):
+        """Force the packed native copy of the weights to be rebuilt on the next call.  Needed only after writes that
+        torch's version counters cannot see (`p.data.mul_()`, EMA through `.data`, a custom kernel): parameter updates
+        through autograd-visible in-place ops, optimizers, `load_state_dict`, `.to()` and the fused optimizers of
+        `trphysx_b200.optim` are detected automatically."""
+        self._handles.invalidate()
+
     def set_conv_mode(self, mode: int):
         """2 = pipelined 3xTF32 tensor-core decoder (default), 1 = FP32 SIMT direct convs, 0 = 3xTF32 MMA with
         in-kernel patch build."""
@@ -100,12 +107,6 @@ class CylinderEmbedding(EmbeddingModel):
         for h, _ in self._handles.values():
             N.check(N.lib().trpx_cyl_set_chunk(h, frames))
 
-    def __del__(self):
-        try:
-            for h, _ in self._handles.values():
-                N.lib().trpx_cyl_destroy(h)
-        except Exception:
-            pass
 
     @staticmethod
     def _visc(visc: Tensor, B: int) -> Tensor:

@@ -35,7 +35,7 @@ class LorenzEmbedding(EmbeddingModel):
         self.kMatrixUT = nn.Parameter(0.1 * torch.rand(self.xidx.size(0)))
         self.register_buffer("mu", torch.tensor([0.0, 0.0, 0.0]))
         self.register_buffer("std", torch.tensor([1.0, 1.0, 1.0]))
-        self._handles = {}
+        self._handles = N.HandleCache("trpx_mlpemb_destroy")
         self.kMatrix = None
 
     # ------------------------------------------------------------------ native plumbing
@@ -69,12 +69,13 @@ class LorenzEmbedding(EmbeddingModel):
             self._keepalive = tensors
         return h
 
-    def __del__(self):
-        try:
-            for h, _ in self._handles.values():
-                N.lib().trpx_mlpemb_destroy(h)
-        except Exception:
-            pass
+
+    def invalidate_weights(self):
+        """Force the packed native copy of the weights to be rebuilt on the next call.  Needed only after writes that
+        torch's version counters cannot see (`p.data.mul_()`, EMA through `.data`, a custom kernel): parameter updates
+        through autograd-visible in-place ops, optimizers, `load_state_dict`, `.to()` and the fused optimizers of
+        `trphysx_b200.optim` are detected automatically."""
+        self._handles.invalidate()
 
     # ------------------------------------------------------------------ reference API
     def embed(self, x: Tensor) -> Tensor:
@@ -166,8 +167,9 @@ class _FusedKoopmanLoss(torch.autograd.Function):
                                               loss2.data_ptr(), flat.data_ptr(), N.stream_ptr(dev)))
         ctx.flat = flat
         ctx.shapes = [p.shape for p in params]
-        ctx.mark_non_differentiable(loss2[1])
-        return loss2[0].clone(), loss2[1].clone()
+        loss, loss_rec = loss2[0].clone(), loss2[1].clone()
+        ctx.mark_non_differentiable(loss_rec)       # the reference returns loss_reconstruct detached (:221)
+        return loss, loss_rec
 
     @staticmethod
     def backward(ctx, gloss, _grec):

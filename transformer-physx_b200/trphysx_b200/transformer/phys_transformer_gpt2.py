@@ -131,7 +131,7 @@ class PhysformerGPT2(PhysformerBase):
         self.n_embd = config.n_embd
         if model_name is not None:
             self.model_name = "transformer_" + model_name
-        self._handles = {}            # device index -> (native handle, WeightTracker)
+        self._handles = N.HandleCache("trpx_gpt2_destroy")            # device index -> (native handle, WeightTracker)
         self._pe = None
         self._tuning = (0, 0, 0, 0)
         logger.info("Number of parameters: {}".format(self._num_parameters()))
@@ -178,6 +178,13 @@ class PhysformerGPT2(PhysformerBase):
                                                N.stream_ptr(device)))
             self._keepalive = tensors
         return h
+
+    def invalidate_weights(self):
+        """Force the packed native copy of the weights to be rebuilt on the next call.  Needed only after writes that
+        torch's version counters cannot see (`p.data.mul_()`, EMA through `.data`, a custom kernel): parameter updates
+        through autograd-visible in-place ops, optimizers, `load_state_dict`, `.to()` and the fused optimizers of
+        `trphysx_b200.optim` are detected automatically."""
+        self._handles.invalidate()
 
     # ------------------------------------------------------------------ fused training step (SURVEY 8f-1)
     def _blob_views(self, blob: Tensor) -> List[Tensor]:
@@ -231,12 +238,6 @@ class PhysformerGPT2(PhysformerBase):
         keys = ("variant", "grid", "block", "smem", "group")
         return {k: v.value for k, v in zip(keys, vals)}
 
-    def __del__(self):
-        try:
-            for h, _ in self._handles.values():
-                N.lib().trpx_gpt2_destroy(h)
-        except Exception:
-            pass
 
     # ------------------------------------------------------------------ reference API
     def forward(self, inputs_embeds: Tensor, position_ids: Tensor = None, prop_embeds: Tensor = None,

@@ -39,6 +39,8 @@ class PhysformerTrain(PhysformerBase):
             if inputs_embeds.requires_grad:
                 raise NotImplementedError("gradients with respect to inputs_embeds are not computed by the fused step")
             loss, hidden = _FusedStackLoss.apply(self.transformer, inputs_embeds, labels_embeds, *params)
+            # NOTE: the reference appends `presents` here when use_cache=True (its forward() default); the fused step
+            # does not materialise the KV tensors (nothing in the training loop reads them, utils/trainer.py:244-256)
             return (loss, hidden, labels_embeds)
         outputs = self.transformer.forward(inputs_embeds=inputs_embeds, **kwargs)
         if labels_embeds is not None:

@@ -93,7 +93,7 @@ def test_cylinder_embedding_matches_reference(golden_dir, dev, name):
         assert O.rel_l2(m.koopmanOperator[0].cpu(), gold["kmatrix0"]) < TOL
 
 
-@pytest.mark.parametrize("conv_mode", [0, 1, 2])     # 0: 3xTF32 MMA (in-kernel build), 1: FP32 SIMT, 2: pipelined 3xTF32
+@pytest.mark.parametrize("conv_mode", [0, 1, 2, 3])  # 0: 3xTF32 mma.sync (in-kernel build), 1: FP32 SIMT, 2: pipelined 3xTF32 mma.sync, 3: tcgen05 (default)
 @pytest.mark.parametrize("N,chunk", [(1, 64), (5, 2), (70, 64)])
 def test_cylinder_vs_oracle_chunking(dev, N, chunk, conv_mode):
     cfg = synth.make_config("cylinder")

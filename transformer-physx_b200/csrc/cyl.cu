@@ -3,6 +3,7 @@
 // (embed / recover), :172-196 (koopmanOperation).  All convs are 3x3 cross-correlations with
 // padding=1, padding_mode='replicate'; upsampling is bilinear x2 with align_corners=True.
 #include "common.cuh"
+#include "cyl_umma.cuh"
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -28,14 +29,17 @@ struct trpx_cyl {
     float* ws = nullptr;                 // activation workspace for one chunk of frames
     size_t ws_bytes = 0;
     int chunk = 64;                      // frames per decoder/encoder pass (intermediates stay in L2)
-    int conv_mode = 2;                   // 2 = pipelined 3xTF32 (upsample/split pass + cp.async double-buffered MMA kernel;
-                                         // default), 1 = FP32 SIMT direct conv, 0 = 3xTF32 MMA with in-kernel patch build
+    int conv_mode = 3;                   // 3 = tcgen05 (UMMA) implicit GEMM, patch built in-kernel (default, csrc/cyl_umma.cu);
+                                         // 2 = pipelined 3xTF32 mma.sync (upsample/split pass + cp.async double-buffered MMA
+                                         // kernel), 1 = FP32 SIMT direct conv, 0 = 3xTF32 mma.sync with in-kernel patch build
     int final_mma = 0;                   // route the last 16->3 conv through the pipeline as well (slower, kept for A/B)
     bool chunk_user = false;
     float* wimg = nullptr;               // pre-split weight images of the three heavy decoder layers (mode 2)
     size_t wimg_off[4] = {0, 0, 0, 0};
     float* U = nullptr;                  // upsampled / padded / split layer input for one chunk (mode 2)
     size_t U_bytes = 0;
+    float* uimg = nullptr;               // weight images of the four UMMA layers (mode 3)
+    size_t uimg_off[UMMA_LAYERS + 1] = {0};
 };
 
 namespace {
@@ -609,6 +613,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_pipe_mma_kernel(const
 // (1.2 MFLOP per frame: the generic direct kernel spent more time here than in a 75 MFLOP layer.)  Thread =
 // (pixel, half of the output channels): its 4x3x3 input window sits in 36 registers, weights are warp-uniform
 // LDS.128 broadcasts, stores are coalesced over pixels.
+template <bool CL4>       // CL4: output in channels-last-4 order [n][CO/4][pixel][4] for the UMMA layers
 __global__ void __launch_bounds__(256) cyl_dec0_kernel(const float* __restrict__ g, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ out) {
     constexpr int CI = 4, CO = 128, HS = 4, WS = 8, H0 = 8, W0 = 16;
@@ -637,18 +642,26 @@ __global__ void __launch_bounds__(256) cyl_dec0_kernel(const float* __restrict__
         for (int dy = 0; dy < 3; dy++)
 #pragma unroll
             for (int dx = 0; dx < 3; dx++) win[ci * 9 + dy * 3 + dx] = up[ci][y + dy][x + dx];
-    for (int co = half * 64; co < half * 64 + 64; co++) {
-        const float4* wr = reinterpret_cast<const float4*>(wsm0 + co * 36);
-        float acc = __ldg(bias + co);
+    for (int cq = half * 16; cq < half * 16 + 16; cq++) {
+        float r4[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 9; q4++) {
-            const float4 wv = wr[q4];
-            acc = fmaf(win[4 * q4 + 0], wv.x, acc);
-            acc = fmaf(win[4 * q4 + 1], wv.y, acc);
-            acc = fmaf(win[4 * q4 + 2], wv.z, acc);
-            acc = fmaf(win[4 * q4 + 3], wv.w, acc);
+        for (int k = 0; k < 4; k++) {
+            const int co = 4 * cq + k;
+            const float4* wr = reinterpret_cast<const float4*>(wsm0 + co * 36);
+            float acc = __ldg(bias + co);
+#pragma unroll
+            for (int q4 = 0; q4 < 9; q4++) {
+                const float4 wv = wr[q4];
+                acc = fmaf(win[4 * q4 + 0], wv.x, acc);
+                acc = fmaf(win[4 * q4 + 1], wv.y, acc);
+                acc = fmaf(win[4 * q4 + 2], wv.z, acc);
+                acc = fmaf(win[4 * q4 + 3], wv.w, acc);
+            }
+            r4[k] = fmaxf(acc, 0.f);
+            if (!CL4) out[((size_t)n * CO + co) * (H0 * W0) + px] = r4[k];
         }
-        out[((size_t)n * CO + co) * (H0 * W0) + px] = fmaxf(acc, 0.f);
+        if (CL4)
+            reinterpret_cast<float4*>(out)[((size_t)n * (CO / 4) + cq) * (H0 * W0) + px] = make_float4(r4[0], r4[1], r4[2], r4[3]);
     }
 }
 
@@ -856,6 +869,7 @@ int trpx_cyl_destroy(trpx_cyl_t h) {
     cudaFree(h->ws);
     cudaFree(h->wimg);
     cudaFree(h->U);
+    cudaFree(h->uimg);
     h->magic = 0;
     delete h;
     return TRPX_OK;
@@ -885,13 +899,23 @@ int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w, int n, void* stre
             TRPX_CUDA(cudaGetLastError());
         }
     }
+    {   // weight images of the tcgen05 layers
+        size_t tot = 0;
+        for (int i = 0; i < UMMA_LAYERS; i++) { h->uimg_off[i] = tot; tot += umma_wimg_floats(i); }
+        h->uimg_off[UMMA_LAYERS] = tot;
+        if (h->uimg == nullptr) TRPX_CUDA(cudaMalloc(&h->uimg, tot * sizeof(float)));
+        for (int i = 0; i < UMMA_LAYERS; i++) {
+            int rc = umma_build_wimg(i, h->blob + h->off[T_DEC + 2 + 2 * i], h->uimg + h->uimg_off[i], (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    }
     h->loaded = true;
     return TRPX_OK;
 }
 
 int trpx_cyl_set_conv_mode(trpx_cyl_t h, int mode) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(mode >= 0 && mode <= 2, "conv mode must be 0 (3xTF32 in-kernel build), 1 (FP32 SIMT) or 2 (pipelined 3xTF32)");
+    TRPX_REQUIRE(mode >= 0 && mode <= 3, "conv mode must be 0 (3xTF32 in-kernel build), 1 (FP32 SIMT), 2 (pipelined 3xTF32 mma.sync) or 3 (tcgen05)");
     h->conv_mode = mode;
     return TRPX_OK;
 }
@@ -956,7 +980,7 @@ int trpx_cyl_recover(trpx_cyl_t h, const float* g, float* x, int N, int apply_ma
     const size_t per = a1 + a2 + a3 + a4;
     // frames per pass: 64 keeps one pass's intermediates L2-resident for the SIMT path; the pipelined path is
     // tensor-bound and prefers fewer, larger launches (measured: 256)
-    const int chunk = std::min(N, (h->conv_mode == 2 && !h->chunk_user) ? 256 : h->chunk);
+    const int chunk = std::min(N, (h->conv_mode >= 2 && !h->chunk_user) ? 256 : h->chunk);
     int rc = ensure_ws(h, per * chunk * sizeof(float));
     if (rc) return rc;
     if (h->conv_mode == 2) {
@@ -977,8 +1001,19 @@ int trpx_cyl_recover(trpx_cyl_t h, const float* g, float* x, int N, int apply_ma
         float* p2 = p1 + a1 * chunk;
         float* p3 = p2 + a2 * chunk;
         float* p4 = p3 + a3 * chunk;
+        if (h->conv_mode == 3) {       // tcgen05 implicit GEMMs (csrc/cyl_umma.cu); activations channels-last-4
+            cyl_dec0_kernel<true><<<nn, 256, 0, st>>>(g + (size_t)n0 * h->E, B + h->off[T_DEC + 0], B + h->off[T_DEC + 1], p1);
+            TRPX_CUDA(cudaGetLastError());
+            float* bufs[5] = {p1, p2, p3, p4, x + (size_t)n0 * 3 * HW};
+            for (int l = 0; l < UMMA_LAYERS; l++) {
+                rc = umma_conv_layer(l, bufs[l], h->uimg + h->uimg_off[l], B + h->off[T_DEC + 3 + 2 * l], bufs[l + 1], nn,
+                                     B + h->off[T_MU], B + h->off[T_STD], apply_mask ? h->mask : nullptr, h->sm_count, st);
+                if (rc) return rc;
+            }
+            continue;
+        }
         if (h->conv_mode == 2) {       // pipelined 3xTF32 tensor-core path, all five layers
-            cyl_dec0_kernel<<<nn, 256, 0, st>>>(g + (size_t)n0 * h->E, B + h->off[T_DEC + 0], B + h->off[T_DEC + 1], p1);
+            cyl_dec0_kernel<false><<<nn, 256, 0, st>>>(g + (size_t)n0 * h->E, B + h->off[T_DEC + 0], B + h->off[T_DEC + 1], p1);
             TRPX_CUDA(cudaGetLastError());
             if ((rc = launch_pipe<4, true>(h, p1, h->wimg + h->wimg_off[0], B + h->off[T_DEC + 3], p2, nn, 128, 8, 16, 64, relu, st))) return rc;
             if ((rc = launch_pipe<4, true>(h, p2, h->wimg + h->wimg_off[1], B + h->off[T_DEC + 5], p3, nn, 64, 16, 32, 32, relu, st))) return rc;

@@ -1,0 +1,474 @@
+// Cylinder decoder layers as tcgen05 (UMMA) implicit GEMMs on sm_100a.
+// Reference: trphysx/embedding/embedding_cylinder.py:70-88 (recoveryNet: [Upsample x2 bilinear align_corners=True ->
+// Conv2d 3x3 replicate -> ReLU] x4 -> Conv2d 3x3), :156-170 (recover: un-normalise, cylinder mask).
+//
+// Formulation.  A layer is  out[pix][co] = sum_{dy,dx,ci} P[pix + (dy-1)*PW + (dx-1)][ci] * w[co][ci][dy][dx]  where P is
+// the (upsampled) replicate-padded layer input written as ONE flat sequence of padded pixels over all frames of the
+// pass (PW = W + 2 padded pixels per row, H + 2 rows per frame).  In that flat space a 3x3 tap is a shift of the
+// pixel index, so the patch is staged ONCE in shared memory in the K-major no-swizzle core-matrix order
+// [plane hi|lo][ci/4][pixel][4 floats] and every tap reuses it through the START ADDRESS of the UMMA shared-memory
+// descriptor (scripts/probes/umma_tf32_probe.cu verifies row-shifted descriptors bit-exactly).  The three dx taps are
+// folded into the N dimension:  D[g][dx][co] = sum_{dy,ci} P[g + (dy-1)*PW][ci] * w[co][ci][dy][dx]  is one MMA of
+// N = 3*Cout per (dy, 8 input channels), and  out[f] = D[f-1][0] + D[f][1] + D[f+1][2]  is a +-1 pixel shift done in
+// the epilogue with warp shuffles.  This cuts the A-operand traffic 3x: M128 x N x K8 TF32 MMAs are bound by the
+// 128 B/cycle shared-memory operand fetch for N < 128 (measured: 45.7 / 56.1 / 96.1 cycles at N = 48 / 96 / 192).
+//
+// Precision.  FP32 parity (rel-L2 <= 1e-5) needs the error-compensated product a*w = a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
+// (TF32 hi / lo planes of both operands).  The tensor core truncates its FP32 accumulator once per instruction
+// (probe: -2.4e-6 relative bias after 144 chained MMAs), so the dominant a_hi*w_hi chain gets its own TMEM columns
+// (at most 48 instructions long) and the two small terms accumulate in a second column set; the epilogue adds them.
+// Where 6*Cout <= 256 the a_hi pass computes both column sets in ONE MMA against the concatenated [w_hi | w_lo] rows.
+//
+// Roles (512 threads, one persistent CTA per SM): warps 0-7 epilogue (TMEM -> registers -> global), warp 8 issues the
+// MMAs, warps 9-15 build the patch (bilinear upsample + TF32 split, generic-proxy stores + fence.proxy.async) and one
+// of their lanes streams the layer's weight image with cp.async.bulk; mbarrier full/empty rings between them,
+// tcgen05.commit releases stages and publishes accumulators.
+#include "common.cuh"
+#include "cyl_umma.cuh"
+#include <algorithm>
+
+using namespace trpx;
+
+namespace {
+
+constexpr int UM_EPI_WARPS = 8, UM_PROD_WARPS = 7;
+constexpr int UM_MMA_WARP = UM_EPI_WARPS;
+constexpr int UM_THREADS = (UM_EPI_WARPS + 1 + UM_PROD_WARPS) * 32;       // 512
+constexpr int UM_NPT = UM_PROD_WARPS * 32;                                // producer threads
+constexpr int UM_BLK = 126;                                               // useful rows of a 128-row M block (1 overlap each side)
+constexpr int UM_CHUNK = 16;                                              // output channels per epilogue pass
+
+template <int CIN_, int COUT_, int COUT_REAL_, int H_, int W_, bool UP_, int MB_, int NSTAGE_, bool FINAL_>
+struct UmmaLayer {
+    static constexpr int CIN = CIN_, COUT = COUT_, COUT_REAL = COUT_REAL_, H = H_, W = W_, MB = MB_, NSTAGE = NSTAGE_;
+    static constexpr bool UP = UP_, FINAL = FINAL_;
+    static constexpr int HS = UP ? H / 2 : H, WS = UP ? W / 2 : W;        // layer input size
+    static constexpr int PW = W + 2, FRAME_POS = (H + 2) * PW;            // flat padded pixels per row / frame
+    static constexpr int NPOS = UM_BLK * MB + 2 + 2 * PW;                 // staged positions of one work item
+    static constexpr int N3 = 3 * COUT, N6 = 6 * COUT;
+    static constexpr bool CONCAT = N6 <= 256;                             // a_hi . [w_hi | w_lo] in one MMA
+    static constexpr int KCH = CIN / 8;                                   // K chunks of 8 input channels
+    static constexpr int PATCH_BYTES = 2 * 2 * NPOS * 16;                 // [plane][kc][pos][4 f]
+    static constexpr int W_BYTES = 3 * 2 * N6 * 16;                       // [dy][kc][n][4 f]
+    static constexpr int STAGE_BYTES = PATCH_BYTES + W_BYTES;
+    static constexpr int TMEM_USED = MB * N6;
+    static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static constexpr int PER = (NPOS + UM_NPT - 1) / UM_NPT;              // positions per producer thread
+    static constexpr int EDGE_FLOATS = 2 * 2 * 2 * 4 * UM_CHUNK;          // [group][parity][left|right][quarter][16]
+    static constexpr size_t SMEM = (size_t)NSTAGE * STAGE_BYTES + EDGE_FLOATS * 4 + 256 + 128;
+    static_assert(CIN % 8 == 0 && COUT % 16 == 0 && N3 % 16 == 0 && N3 <= 256, "shape");
+    static_assert(TMEM_USED <= 512, "TMEM");
+    static_assert(UM_BLK * (MB - 1) + 2 * PW + 128 <= NPOS, "patch too small");
+};
+
+struct UmmaArgs {
+    const float* in;        // [N][CIN/4][HS][WS][4]
+    const float* wimg;      // [KCH][dy 3][kc 2][N6][4]
+    const float* bias;      // [COUT_REAL]
+    float* out;
+    const float* mu;
+    const float* sd;
+    const unsigned char* mask;
+    int N;
+    int nitems;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    // K-major, no swizzle: start >> 4 | LBO >> 4 (stride between the two 16-byte K chunks) | SBO = 128 B (stride between
+    // 8-row groups) | descriptor version 1
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    // D = F32 (1 @4), A = B = TF32 (2 @7, 2 @10), both K-major, N >> 3 @17, M >> 4 @24
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(taddr), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    hi = __uint_as_float(u);
+    lo = x - hi;
+}
+
+// bilinear x2 (align_corners=True) source index / weight, as aten's area_pixel_compute_source_index
+struct Lerp1 {
+    int i0, i1;
+    float l1;
+};
+__device__ __forceinline__ Lerp1 lerp1(int dst, int in_size, float scale) {
+    const float real = scale * (float)dst;
+    Lerp1 r;
+    r.i0 = min((int)real, in_size - 1);
+    r.l1 = fminf(fmaxf(real - (float)r.i0, 0.f), 1.f);
+    r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+    return r;
+}
+
+struct PosRec {       // where a staged position reads the layer input (float4 units, channel quad 0)
+    int o00;          // -1: outside the pass (zeros)
+    int dj, di;       // offset of the right / lower neighbour
+    float wy1, wx1;
+};
+
+template <class L>
+__global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const UmmaArgs a) {
+    extern __shared__ __align__(128) unsigned char um_smem[];
+    unsigned char* stages = um_smem;
+    float* edge = reinterpret_cast<float*>(um_smem + (size_t)L::NSTAGE * L::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(edge + L::EDGE_FLOATS);
+    uint64_t* full = bars;                       // [NSTAGE] producers (7 warps) + weight copy (expect_tx)
+    uint64_t* empty = full + L::NSTAGE;          // [NSTAGE] tcgen05.commit
+    uint64_t* tfull = empty + L::NSTAGE;         // [MB] accumulator of block b complete
+    uint64_t* tempty = tfull + L::MB;            // [MB] accumulator of block b drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + L::MB);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < L::NSTAGE; s++) {
+            mbar_init(&full[s], UM_PROD_WARPS + 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < L::MB; b++) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], L::MB == 1 ? UM_EPI_WARPS : 4);
+        }
+    }
+    if (warp == UM_MMA_WARP) tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int T = a.N * L::FRAME_POS;
+
+    if (warp < UM_EPI_WARPS) {
+        // =============================== epilogue ===============================
+        const int eg = warp >> 2, q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        int par = 0;
+        int iter = 0;
+        for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, iter++) {
+            const int g0 = item * (UM_BLK * L::MB);
+            for (int b = (L::MB > 1 ? eg : 0); b < L::MB; b += (L::MB > 1 ? 2 : 1)) {
+                mbar_wait(&tfull[b], iter & 1);
+                tc_fence_after();
+                const int t = q * 32 + lane;                           // row of the block
+                const int g = g0 + UM_BLK * b + t;
+                bool valid = t >= 1 && t <= UM_BLK && g < T;
+                int n = 0, y = 0, x = 0;
+                {
+                    n = g / L::FRAME_POS;
+                    const int r = g - n * L::FRAME_POS;
+                    const int yp = r / L::PW, xp = r - yp * L::PW;
+                    valid = valid && yp >= 1 && yp <= L::H && xp >= 1 && xp <= L::W;
+                    y = yp - 1;
+                    x = xp - 1;
+                }
+                const uint32_t tcol = tmem_base + lane_base + (uint32_t)(b * L::N6);
+                for (int c = (L::MB > 1 ? 0 : eg); c < L::COUT / UM_CHUNK; c += (L::MB > 1 ? 1 : 2)) {
+                    const int co0 = c * UM_CHUNK;
+                    float v[3][UM_CHUNK];
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++) {
+                        uint32_t rh[16], rs[16];
+                        tmem_ld16(tcol + (uint32_t)(dx * L::COUT + co0), rh);
+                        tmem_ld16(tcol + (uint32_t)(L::N3 + dx * L::COUT + co0), rs);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < UM_CHUNK; j++) v[dx][j] = __uint_as_float(rh[j]) + __uint_as_float(rs[j]);
+                    }
+                    float* eb = edge + (size_t)((eg * 2 + par) * 2) * 4 * UM_CHUNK;
+                    if (lane == 31) {
+#pragma unroll
+                        for (int j = 0; j < UM_CHUNK; j++) eb[(0 * 4 + q) * UM_CHUNK + j] = v[0][j];
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < UM_CHUNK; j++) eb[(1 * 4 + q) * UM_CHUNK + j] = v[2][j];
+                    }
+                    named_bar_sync(1 + eg, 128);
+                    float o[UM_CHUNK];
+#pragma unroll
+                    for (int j = 0; j < UM_CHUNK; j++) {
+                        float l = __shfl_up_sync(FULL, v[0][j], 1);
+                        float r = __shfl_down_sync(FULL, v[2][j], 1);
+                        if (lane == 0 && q > 0) l = eb[(0 * 4 + q - 1) * UM_CHUNK + j];
+                        if (lane == 31 && q < 3) r = eb[(1 * 4 + q + 1) * UM_CHUNK + j];
+                        o[j] = (l + v[1][j]) + r;
+                    }
+                    par ^= 1;
+                    if (valid) {
+                        if constexpr (!L::FINAL) {
+                            float4* out4 = reinterpret_cast<float4*>(a.out);
+#pragma unroll
+                            for (int c4 = 0; c4 < UM_CHUNK / 4; c4++) {
+                                const int co = co0 + 4 * c4;
+                                const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias + co));
+                                float4 w;
+                                w.x = fmaxf(o[4 * c4 + 0] + bz.x, 0.f);
+                                w.y = fmaxf(o[4 * c4 + 1] + bz.y, 0.f);
+                                w.z = fmaxf(o[4 * c4 + 2] + bz.z, 0.f);
+                                w.w = fmaxf(o[4 * c4 + 3] + bz.w, 0.f);
+                                out4[(((size_t)n * (L::COUT / 4) + (co >> 2)) * L::H + y) * L::W + x] = w;
+                            }
+                        } else {
+                            const bool masked = a.mask != nullptr && a.mask[y * L::W + x] != 0;
+#pragma unroll
+                            for (int j = 0; j < L::COUT_REAL; j++) {
+                                float w = o[j] + __ldg(a.bias + j);
+                                w = __ldg(a.sd + j) * w + __ldg(a.mu + j);        // embedding_cylinder.py:202-203
+                                if (masked) w = 0.f;                               // :168-169
+                                a.out[(((size_t)n * L::COUT_REAL + j) * L::H + y) * L::W + x] = w;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[b]);
+            }
+        }
+    } else if (warp == UM_MMA_WARP) {
+        // =============================== MMA issue ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc6 = umma_idesc_tf32(128, L::CONCAT ? L::N6 : L::N3);
+            constexpr uint32_t idesc3 = umma_idesc_tf32(128, L::N3);
+            constexpr uint32_t LBO_A = L::NPOS * 16, LBO_B = L::N6 * 16;
+            int s = 0, ph = 0, iter = 0;
+            for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, iter++) {
+                for (int kc = 0; kc < L::KCH; kc++) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sp = smem_u32(stages + (size_t)s * L::STAGE_BYTES);
+                    const uint32_t sw = sp + L::PATCH_BYTES;
+                    for (int b = 0; b < L::MB; b++) {
+                        if (kc == 0) {
+                            mbar_wait(&tempty[b], (iter & 1) ^ 1);
+                            tc_fence_after();
+                        }
+                        const uint32_t tc = tmem_base + (uint32_t)(b * L::N6);
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+                            const uint32_t arow = (uint32_t)(UM_BLK * b + dy * L::PW) * 16u;
+                            const uint64_t a_hi = umma_desc(sp + arow, LBO_A);
+                            const uint64_t a_lo = umma_desc(sp + 2 * L::NPOS * 16 + arow, LBO_A);
+                            const uint32_t wb = sw + (uint32_t)dy * (2 * L::N6 * 16);
+                            const uint32_t first = (kc == 0 && dy == 0) ? 0u : 1u;
+                            if constexpr (L::CONCAT) {
+                                umma_tf32(tc, a_hi, umma_desc(wb, LBO_B), idesc6, first);                  // hh | hl
+                                umma_tf32(tc + L::N3, a_lo, umma_desc(wb, LBO_B), idesc3, 1u);              // + lh
+                            } else {
+                                umma_tf32(tc, a_hi, umma_desc(wb, LBO_B), idesc3, first);                   // hh
+                                umma_tf32(tc + L::N3, a_hi, umma_desc(wb + L::N3 * 16, LBO_B), idesc3, first);   // hl
+                                umma_tf32(tc + L::N3, a_lo, umma_desc(wb, LBO_B), idesc3, 1u);              // + lh
+                            }
+                        }
+                        if (kc == L::KCH - 1) umma_commit(&tfull[b]);
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== producers ===============================
+        const int ptid = tid - (UM_MMA_WARP + 1) * 32;
+        const float sh = L::UP ? (float)(L::HS - 1) / (float)(L::H - 1) : 0.f;
+        const float sw_ = L::UP ? (float)(L::WS - 1) / (float)(L::W - 1) : 0.f;
+        const float4* in4 = reinterpret_cast<const float4*>(a.in);
+        constexpr int QPLANE = L::HS * L::WS;                         // float4 per channel quad of one frame
+        int s = 0, ph = 0;
+        for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+            const int gbase = item * (UM_BLK * L::MB) - L::PW;        // flat position of staged position 0
+            PosRec rec[L::PER];
+#pragma unroll
+            for (int j = 0; j < L::PER; j++) {
+                const int p = ptid + j * UM_NPT;
+                const int g = gbase + p;
+                PosRec r;
+                r.o00 = -1; r.dj = 0; r.di = 0; r.wy1 = 0.f; r.wx1 = 0.f;
+                if (p < L::NPOS && g >= 0 && g < T) {
+                    const int n = g / L::FRAME_POS;
+                    const int rr = g - n * L::FRAME_POS;
+                    const int yp = rr / L::PW, xp = rr - yp * L::PW;
+                    const int y = min(max(yp - 1, 0), L::H - 1), x = min(max(xp - 1, 0), L::W - 1);     // replicate padding
+                    if constexpr (L::UP) {
+                        const Lerp1 ly = lerp1(y, L::HS, sh), lx = lerp1(x, L::WS, sw_);
+                        r.o00 = (n * (L::CIN / 4) * L::HS + ly.i0) * L::WS + lx.i0;
+                        r.dj = lx.i1 - lx.i0;
+                        r.di = (ly.i1 - ly.i0) * L::WS;
+                        r.wy1 = ly.l1;
+                        r.wx1 = lx.l1;
+                    } else {
+                        r.o00 = (n * (L::CIN / 4) * L::HS + y) * L::WS + x;
+                    }
+                }
+                rec[j] = r;
+            }
+            for (int kc = 0; kc < L::KCH; kc++) {
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char* st = stages + (size_t)s * L::STAGE_BYTES;
+                if (ptid == 0) {
+                    mbar_expect_tx(&full[s], L::W_BYTES);
+                    bulk_g2s(st + L::PATCH_BYTES, a.wimg + (size_t)kc * (L::W_BYTES / 4), L::W_BYTES, &full[s]);
+                }
+                const uint32_t sbase = smem_u32(st);
+#pragma unroll
+                for (int j = 0; j < L::PER; j++) {
+                    const int p = ptid + j * UM_NPT;
+                    if (p < L::NPOS) {
+                        const PosRec r = rec[j];
+#pragma unroll
+                        for (int qd = 0; qd < 2; qd++) {
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (r.o00 >= 0) {
+                                const float4* src = in4 + (size_t)(2 * kc + qd) * QPLANE + r.o00;
+                                if constexpr (L::UP) {
+                                    const float4 v00 = __ldg(src), v01 = __ldg(src + r.dj);
+                                    const float4 v10 = __ldg(src + r.di), v11 = __ldg(src + r.di + r.dj);
+                                    const float wx0 = 1.f - r.wx1, wy0 = 1.f - r.wy1;
+                                    v.x = wy0 * (wx0 * v00.x + r.wx1 * v01.x) + r.wy1 * (wx0 * v10.x + r.wx1 * v11.x);
+                                    v.y = wy0 * (wx0 * v00.y + r.wx1 * v01.y) + r.wy1 * (wx0 * v10.y + r.wx1 * v11.y);
+                                    v.z = wy0 * (wx0 * v00.z + r.wx1 * v01.z) + r.wy1 * (wx0 * v10.z + r.wx1 * v11.z);
+                                    v.w = wy0 * (wx0 * v00.w + r.wx1 * v01.w) + r.wy1 * (wx0 * v10.w + r.wx1 * v11.w);
+                                } else {
+                                    v = __ldg(src);
+                                }
+                            }
+                            float h0, h1, h2, h3, l0, l1, l2, l3;
+                            split_tf32(v.x, h0, l0);
+                            split_tf32(v.y, h1, l1);
+                            split_tf32(v.z, h2, l2);
+                            split_tf32(v.w, h3, l3);
+                            const uint32_t d = sbase + (uint32_t)(qd * L::NPOS + p) * 16u;
+                            st_shared_v4(d, h0, h1, h2, h3);
+                            st_shared_v4(d + 2 * L::NPOS * 16, l0, l1, l2, l3);
+                        }
+                    }
+                }
+                fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == UM_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
+// weight image: [kc8][dy][kc 2][n 6*COUT][4]; n = plane*3*COUT + dx*COUT + co; zero for co >= cout_real
+__global__ void umma_wimg_kernel(const float* __restrict__ w, float* __restrict__ img, int CIN, int COUT, int cout_real) {
+    const int N6 = 6 * COUT, N3 = 3 * COUT;
+    const int total = (CIN / 8) * 3 * 2 * N6 * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int r = i;
+        const int e = r % 4; r /= 4;
+        const int n = r % N6; r /= N6;
+        const int kc = r % 2; r /= 2;
+        const int dy = r % 3; const int k8 = r / 3;
+        const int plane = n / N3, m = n % N3, dx = m / COUT, co = m % COUT;
+        const int ci = k8 * 8 + kc * 4 + e;
+        float v = 0.f;
+        if (co < cout_real) v = w[((size_t)co * CIN + ci) * 9 + dy * 3 + dx];
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        img[i] = plane ? lo : hi;
+    }
+}
+
+//                      CIN COUT real  H    W   UP    MB NSTAGE FINAL
+using UL0 = UmmaLayer<128, 64, 64, 16, 32, true, 1, 4, false>;
+using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 4, false>;
+using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 3, false>;
+using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 2, true>;
+
+template <class L>
+int launch_umma(const UmmaArgs& base, int sm_count, cudaStream_t st) {
+    UmmaArgs a = base;
+    const long long T = (long long)a.N * L::FRAME_POS;
+    TRPX_REQUIRE(T < (1LL << 30), "too many frames in one pass (%d)", a.N);
+    // the last valid output position is T - PW - 2; item i covers outputs [i*126*MB + 1, (i+1)*126*MB]
+    a.nitems = (int)((T - L::PW - 2 + (UM_BLK * L::MB) - 1) / (UM_BLK * L::MB));
+    static_assert(L::SMEM <= 227 * 1024, "shared memory");
+    TRPX_CUDA(cudaFuncSetAttribute(cyl_umma_conv_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+    const int grid = std::min(a.nitems, sm_count);
+    cyl_umma_conv_kernel<L><<<grid, UM_THREADS, L::SMEM, st>>>(a);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+}  // namespace
+
+namespace trpx {
+
+size_t umma_wimg_floats(int layer) {
+    switch (layer) {
+        case 0: return (size_t)UL0::KCH * UL0::W_BYTES / 4;
+        case 1: return (size_t)UL1::KCH * UL1::W_BYTES / 4;
+        case 2: return (size_t)UL2::KCH * UL2::W_BYTES / 4;
+        default: return (size_t)UL3::KCH * UL3::W_BYTES / 4;
+    }
+}
+
+int umma_build_wimg(int layer, const float* w, float* img, cudaStream_t st) {
+    const int cin[4] = {128, 64, 32, 16}, cout[4] = {64, 32, 16, 16}, real[4] = {64, 32, 16, 3};
+    TRPX_REQUIRE(layer >= 0 && layer < UMMA_LAYERS, "bad layer");
+    umma_wimg_kernel<<<64, 256, 0, st>>>(w, img, cin[layer], cout[layer], real[layer]);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+int umma_conv_layer(int layer, const float* in_cl4, const float* wimg, const float* bias, float* out, int N,
+                    const float* mu, const float* sd, const unsigned char* mask, int sm_count, cudaStream_t st) {
+    UmmaArgs a{};
+    a.in = in_cl4; a.wimg = wimg; a.bias = bias; a.out = out; a.mu = mu; a.sd = sd; a.mask = mask; a.N = N;
+    switch (layer) {
+        case 0: return launch_umma<UL0>(a, sm_count, st);
+        case 1: return launch_umma<UL1>(a, sm_count, st);
+        case 2: return launch_umma<UL2>(a, sm_count, st);
+        case 3: return launch_umma<UL3>(a, sm_count, st);
+        default: return set_error(TRPX_E_INVALID, "bad layer %d", layer);
+    }
+}
+
+}  // namespace trpx

@@ -96,8 +96,8 @@ class CylinderEmbedding(EmbeddingModel):
         self._handles.invalidate()
 
     def set_conv_mode(self, mode: int):
-        """2 = pipelined 3xTF32 tensor-core decoder (default), 1 = FP32 SIMT direct convs, 0 = 3xTF32 MMA with
-        in-kernel patch build."""
+        """3 = tcgen05 (UMMA) implicit-GEMM decoder (default), 2 = pipelined 3xTF32 mma.sync decoder, 1 = FP32 SIMT direct
+        convs, 0 = 3xTF32 mma.sync with in-kernel patch build."""
         self._conv_mode = mode
         for h, _ in self._handles.values():
             N.check(N.lib().trpx_cyl_set_conv_mode(h, mode))

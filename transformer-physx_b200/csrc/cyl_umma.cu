@@ -3,8 +3,8 @@
 // Conv2d 3x3 replicate -> ReLU] x4 -> Conv2d 3x3), :156-170 (recover: un-normalise, cylinder mask).
 //
 // Formulation.  A layer is  out[pix][co] = sum_{dy,dx,ci} P[pix + (dy-1)*PW + (dx-1)][ci] * w[co][ci][dy][dx]  where P is
-// the (upsampled) replicate-padded layer input written as ONE flat sequence of padded pixels over all frames of the
-// pass (PW = W + 2 padded pixels per row, H + 2 rows per frame).  In that flat space a 3x3 tap is a shift of the
+// the (upsampled) replicate-padded layer input of a frame written as ONE flat sequence of padded pixels (PW = W + 2
+// padded pixels per row, H + 2 rows per frame).  In that flat space a 3x3 tap is a shift of the
 // pixel index, so the patch is staged ONCE in shared memory in the K-major no-swizzle core-matrix order
 // [plane hi|lo][ci/4][pixel][4 floats] and every tap reuses it through the START ADDRESS of the UMMA shared-memory
 // descriptor (scripts/probes/umma_tf32_probe.cu verifies row-shifted descriptors bit-exactly).  The three dx taps are
@@ -19,10 +19,12 @@
 // (at most 48 instructions long) and the two small terms accumulate in a second column set; the epilogue adds them.
 // Where 6*Cout <= 256 the a_hi pass computes both column sets in ONE MMA against the concatenated [w_hi | w_lo] rows.
 //
-// Roles (512 threads, one persistent CTA per SM): warps 0-7 epilogue (TMEM -> registers -> global), warp 8 issues the
-// MMAs, warps 9-15 build the patch (bilinear upsample + TF32 split, generic-proxy stores + fence.proxy.async) and one
-// of their lanes streams the layer's weight image with cp.async.bulk; mbarrier full/empty rings between them,
-// tcgen05.commit releases stages and publishes accumulators.
+// Roles (512 threads, one persistent CTA per SM): warps 0-3 epilogue (TMEM -> registers -> global), warp 4 issues the
+// MMAs, warp 5 is the loader: one lane streams, per stage, the layer-input rows the stage needs and the stage's slice of
+// the weight image into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), warps 6-15 build the
+// patch from the staged rows (bilinear upsample + TF32 split, generic-proxy stores + fence.proxy.async).  mbarrier
+// rings: src_full (TMA -> producers), full (producers + weight copy -> MMA), empty (tcgen05.commit -> loader), and per
+// 128-row block tfull (tcgen05.commit -> epilogue) / tempty (epilogue -> MMA).
 #include "common.cuh"
 #include "cyl_umma.cuh"
 #include <algorithm>
@@ -31,9 +33,9 @@ using namespace trpx;
 
 namespace {
 
-constexpr int UM_EPI_WARPS = 8, UM_PROD_WARPS = 7;
-constexpr int UM_MMA_WARP = UM_EPI_WARPS;
-constexpr int UM_THREADS = (UM_EPI_WARPS + 1 + UM_PROD_WARPS) * 32;       // 512
+constexpr int UM_EPI_WARPS = 4, UM_PROD_WARPS = 10;
+constexpr int UM_MMA_WARP = UM_EPI_WARPS, UM_LOAD_WARP = UM_EPI_WARPS + 1;
+constexpr int UM_THREADS = (UM_EPI_WARPS + 2 + UM_PROD_WARPS) * 32;       // 512
 constexpr int UM_NPT = UM_PROD_WARPS * 32;                                // producer threads
 constexpr int UM_BLK = 126;                                               // useful rows of a 128-row M block (1 overlap each side)
 constexpr int UM_CHUNK = 16;                                              // output channels per epilogue pass
@@ -45,16 +47,21 @@ struct UmmaLayer {
     static constexpr int HS = UP ? H / 2 : H, WS = UP ? W / 2 : W;        // layer input size
     static constexpr int PW = W + 2, FRAME_POS = (H + 2) * PW;            // flat padded pixels per row / frame
     static constexpr int NPOS = UM_BLK * MB + 2 + 2 * PW;                 // staged positions of one work item
+    static constexpr int ITEM_OUT = UM_BLK * MB;                          // output positions of one work item
+    static constexpr int IPF = (FRAME_POS - PW - 2 + ITEM_OUT - 1) / ITEM_OUT;   // work items per frame
+    static constexpr int ROWS_OUT = (NPOS + PW - 2) / PW + 1;             // padded rows a work item can touch
+    static constexpr int SRC_ROWS = UP ? ROWS_OUT / 2 + 3 : ROWS_OUT;     // layer-input rows behind them
+    static constexpr int SRC_BYTES = 2 * SRC_ROWS * WS * 16;              // [quad 2][row][col][4 f]
     static constexpr int N3 = 3 * COUT, N6 = 6 * COUT;
     static constexpr bool CONCAT = N6 <= 256;                             // a_hi . [w_hi | w_lo] in one MMA
     static constexpr int KCH = CIN / 8;                                   // K chunks of 8 input channels
     static constexpr int PATCH_BYTES = 2 * 2 * NPOS * 16;                 // [plane][kc][pos][4 f]
     static constexpr int W_BYTES = 3 * 2 * N6 * 16;                       // [dy][kc][n][4 f]
-    static constexpr int STAGE_BYTES = PATCH_BYTES + W_BYTES;
+    static constexpr int STAGE_BYTES = PATCH_BYTES + W_BYTES + SRC_BYTES;
     static constexpr int TMEM_USED = MB * N6;
     static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static constexpr int PER = (NPOS + UM_NPT - 1) / UM_NPT;              // positions per producer thread
-    static constexpr int EDGE_FLOATS = 2 * 2 * 2 * 4 * UM_CHUNK;          // [group][parity][left|right][quarter][16]
+    static constexpr int EDGE_FLOATS = 2 * 2 * 4 * UM_CHUNK;              // [parity][left|right][quarter][16]
     static constexpr size_t SMEM = (size_t)NSTAGE * STAGE_BYTES + EDGE_FLOATS * 4 + 256 + 128;
     static_assert(CIN % 8 == 0 && COUT % 16 == 0 && N3 % 16 == 0 && N3 <= 256, "shape");
     static_assert(TMEM_USED <= 512, "TMEM");
@@ -139,11 +146,27 @@ __device__ __forceinline__ Lerp1 lerp1(int dst, int in_size, float scale) {
     return r;
 }
 
-struct PosRec {       // where a staged position reads the layer input (float4 units, channel quad 0)
-    int o00;          // -1: outside the pass (zeros)
+struct PosRec {       // where a staged position reads the staged layer-input rows (float4 units, channel quad 0)
+    int o00;          // -1: outside the frame (zeros)
     int dj, di;       // offset of the right / lower neighbour
     float wy1, wx1;
 };
+
+// layer-input rows [i_lo, i_lo + nrows) needed by work item j of a frame (the loader and the producers agree on this)
+template <class L>
+__device__ __forceinline__ void item_src_rows(int lb, int& i_lo, int& nrows) {
+    const int lp0 = max(lb - L::PW, 0), lp1 = min(lb - L::PW + L::NPOS - 1, L::FRAME_POS - 1);
+    const int y0 = min(max(lp0 / L::PW - 1, 0), L::H - 1), y1 = min(max(lp1 / L::PW - 1, 0), L::H - 1);
+    if constexpr (L::UP) {
+        const float sh = (float)(L::HS - 1) / (float)(L::H - 1);
+        i_lo = lerp1(y0, L::HS, sh).i0;
+        nrows = lerp1(y1, L::HS, sh).i1 - i_lo + 1;
+    } else {
+        i_lo = y0;
+        nrows = y1 - y0 + 1;
+    }
+    nrows = min(nrows, L::SRC_ROWS);
+}
 
 template <class L>
 __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const UmmaArgs a) {
@@ -151,9 +174,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
     unsigned char* stages = um_smem;
     float* edge = reinterpret_cast<float*>(um_smem + (size_t)L::NSTAGE * L::STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(edge + L::EDGE_FLOATS);
-    uint64_t* full = bars;                       // [NSTAGE] producers (7 warps) + weight copy (expect_tx)
+    uint64_t* full = bars;                       // [NSTAGE] producers (10 warps) + weight copy (expect_tx)
     uint64_t* empty = full + L::NSTAGE;          // [NSTAGE] tcgen05.commit
-    uint64_t* tfull = empty + L::NSTAGE;         // [MB] accumulator of block b complete
+    uint64_t* src_full = empty + L::NSTAGE;      // [NSTAGE] layer-input rows landed (expect_tx)
+    uint64_t* tfull = src_full + L::NSTAGE;      // [MB] accumulator of block b complete
     uint64_t* tempty = tfull + L::MB;            // [MB] accumulator of block b drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + L::MB);
 
@@ -162,10 +186,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
         for (int s = 0; s < L::NSTAGE; s++) {
             mbar_init(&full[s], UM_PROD_WARPS + 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&src_full[s], 1);
         }
         for (int b = 0; b < L::MB; b++) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], L::MB == 1 ? UM_EPI_WARPS : 4);
+            mbar_init(&tempty[b], UM_EPI_WARPS);
         }
     }
     if (warp == UM_MMA_WARP) tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -173,33 +198,26 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int T = a.N * L::FRAME_POS;
 
     if (warp < UM_EPI_WARPS) {
         // =============================== epilogue ===============================
-        const int eg = warp >> 2, q = warp & 3;
+        const int q = warp;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int par = 0;
         int iter = 0;
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, iter++) {
-            const int g0 = item * (UM_BLK * L::MB);
-            for (int b = (L::MB > 1 ? eg : 0); b < L::MB; b += (L::MB > 1 ? 2 : 1)) {
+            const int n = item / L::IPF;
+            const int lb = (item - n * L::IPF) * L::ITEM_OUT;
+            for (int b = 0; b < L::MB; b++) {
                 mbar_wait(&tfull[b], iter & 1);
                 tc_fence_after();
                 const int t = q * 32 + lane;                           // row of the block
-                const int g = g0 + UM_BLK * b + t;
-                bool valid = t >= 1 && t <= UM_BLK && g < T;
-                int n = 0, y = 0, x = 0;
-                {
-                    n = g / L::FRAME_POS;
-                    const int r = g - n * L::FRAME_POS;
-                    const int yp = r / L::PW, xp = r - yp * L::PW;
-                    valid = valid && yp >= 1 && yp <= L::H && xp >= 1 && xp <= L::W;
-                    y = yp - 1;
-                    x = xp - 1;
-                }
+                const int lp = lb + UM_BLK * b + t;                    // flat padded position inside the frame
+                const int yp = lp / L::PW, xp = lp - yp * L::PW;
+                const bool valid = t >= 1 && t <= UM_BLK && yp >= 1 && yp <= L::H && xp >= 1 && xp <= L::W;
+                const int y = yp - 1, x = xp - 1;
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)(b * L::N6);
-                for (int c = (L::MB > 1 ? 0 : eg); c < L::COUT / UM_CHUNK; c += (L::MB > 1 ? 1 : 2)) {
+                for (int c = 0; c < L::COUT / UM_CHUNK; c++) {
                     const int co0 = c * UM_CHUNK;
                     float v[3][UM_CHUNK];
 #pragma unroll
@@ -211,7 +229,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
 #pragma unroll
                         for (int j = 0; j < UM_CHUNK; j++) v[dx][j] = __uint_as_float(rh[j]) + __uint_as_float(rs[j]);
                     }
-                    float* eb = edge + (size_t)((eg * 2 + par) * 2) * 4 * UM_CHUNK;
+                    if (c == L::COUT / UM_CHUNK - 1) {                 // block drained: the next item may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[b]);
+                    }
+                    float* eb = edge + (size_t)(par * 2) * 4 * UM_CHUNK;
                     if (lane == 31) {
 #pragma unroll
                         for (int j = 0; j < UM_CHUNK; j++) eb[(0 * 4 + q) * UM_CHUNK + j] = v[0][j];
@@ -220,7 +243,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
 #pragma unroll
                         for (int j = 0; j < UM_CHUNK; j++) eb[(1 * 4 + q) * UM_CHUNK + j] = v[2][j];
                     }
-                    named_bar_sync(1 + eg, 128);
+                    named_bar_sync(1, UM_EPI_WARPS * 32);
                     float o[UM_CHUNK];
 #pragma unroll
                     for (int j = 0; j < UM_CHUNK; j++) {
@@ -257,9 +280,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[b]);
             }
         }
     } else if (warp == UM_MMA_WARP) {
@@ -305,48 +325,71 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
             }
         }
         __syncwarp();
+    } else if (warp == UM_LOAD_WARP) {
+        // =============================== loader (TMA bulk copies) ===============================
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+                const int n = item / L::IPF;
+                const int lb = (item - n * L::IPF) * L::ITEM_OUT;
+                int i_lo, nrows;
+                item_src_rows<L>(lb, i_lo, nrows);
+                const uint32_t row_bytes = (uint32_t)nrows * L::WS * 16u;
+                for (int kc = 0; kc < L::KCH; kc++) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char* st = stages + (size_t)s * L::STAGE_BYTES;
+                    mbar_expect_tx(&src_full[s], 2 * row_bytes);
+#pragma unroll
+                    for (int qd = 0; qd < 2; qd++) {
+                        const float* src = a.in + ((((size_t)n * (L::CIN / 4) + 2 * kc + qd) * L::HS + i_lo) * L::WS) * 4;
+                        bulk_g2s(st + L::PATCH_BYTES + L::W_BYTES + qd * (L::SRC_ROWS * L::WS * 16), src, row_bytes, &src_full[s]);
+                    }
+                    mbar_expect_tx(&full[s], L::W_BYTES);
+                    bulk_g2s(st + L::PATCH_BYTES, a.wimg + (size_t)kc * (L::W_BYTES / 4), L::W_BYTES, &full[s]);
+                    if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
     } else {
         // =============================== producers ===============================
-        const int ptid = tid - (UM_MMA_WARP + 1) * 32;
+        const int ptid = tid - (UM_LOAD_WARP + 1) * 32;
         const float sh = L::UP ? (float)(L::HS - 1) / (float)(L::H - 1) : 0.f;
         const float sw_ = L::UP ? (float)(L::WS - 1) / (float)(L::W - 1) : 0.f;
-        const float4* in4 = reinterpret_cast<const float4*>(a.in);
-        constexpr int QPLANE = L::HS * L::WS;                         // float4 per channel quad of one frame
         int s = 0, ph = 0;
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-            const int gbase = item * (UM_BLK * L::MB) - L::PW;        // flat position of staged position 0
+            const int n = item / L::IPF;
+            const int lb = (item - n * L::IPF) * L::ITEM_OUT;
+            int i_lo, nrows;
+            item_src_rows<L>(lb, i_lo, nrows);
             PosRec rec[L::PER];
 #pragma unroll
             for (int j = 0; j < L::PER; j++) {
                 const int p = ptid + j * UM_NPT;
-                const int g = gbase + p;
+                const int lp = lb - L::PW + p;                         // flat padded position inside the frame
                 PosRec r;
                 r.o00 = -1; r.dj = 0; r.di = 0; r.wy1 = 0.f; r.wx1 = 0.f;
-                if (p < L::NPOS && g >= 0 && g < T) {
-                    const int n = g / L::FRAME_POS;
-                    const int rr = g - n * L::FRAME_POS;
-                    const int yp = rr / L::PW, xp = rr - yp * L::PW;
+                if (p < L::NPOS && lp >= 0 && lp < L::FRAME_POS) {
+                    const int yp = lp / L::PW, xp = lp - yp * L::PW;
                     const int y = min(max(yp - 1, 0), L::H - 1), x = min(max(xp - 1, 0), L::W - 1);     // replicate padding
                     if constexpr (L::UP) {
                         const Lerp1 ly = lerp1(y, L::HS, sh), lx = lerp1(x, L::WS, sw_);
-                        r.o00 = (n * (L::CIN / 4) * L::HS + ly.i0) * L::WS + lx.i0;
+                        r.o00 = (ly.i0 - i_lo) * L::WS + lx.i0;
                         r.dj = lx.i1 - lx.i0;
                         r.di = (ly.i1 - ly.i0) * L::WS;
                         r.wy1 = ly.l1;
                         r.wx1 = lx.l1;
                     } else {
-                        r.o00 = (n * (L::CIN / 4) * L::HS + y) * L::WS + x;
+                        r.o00 = (y - i_lo) * L::WS + x;
                     }
+                    if (r.o00 + r.di + r.dj >= nrows * L::WS) r.o00 = -1;          // cannot happen (rows are sized for it)
                 }
                 rec[j] = r;
             }
             for (int kc = 0; kc < L::KCH; kc++) {
-                mbar_wait(&empty[s], ph ^ 1);
+                mbar_wait(&src_full[s], ph);
                 unsigned char* st = stages + (size_t)s * L::STAGE_BYTES;
-                if (ptid == 0) {
-                    mbar_expect_tx(&full[s], L::W_BYTES);
-                    bulk_g2s(st + L::PATCH_BYTES, a.wimg + (size_t)kc * (L::W_BYTES / 4), L::W_BYTES, &full[s]);
-                }
+                const float4* src4 = reinterpret_cast<const float4*>(st + L::PATCH_BYTES + L::W_BYTES);
                 const uint32_t sbase = smem_u32(st);
 #pragma unroll
                 for (int j = 0; j < L::PER; j++) {
@@ -357,17 +400,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                         for (int qd = 0; qd < 2; qd++) {
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (r.o00 >= 0) {
-                                const float4* src = in4 + (size_t)(2 * kc + qd) * QPLANE + r.o00;
+                                const float4* src = src4 + qd * (L::SRC_ROWS * L::WS) + r.o00;
                                 if constexpr (L::UP) {
-                                    const float4 v00 = __ldg(src), v01 = __ldg(src + r.dj);
-                                    const float4 v10 = __ldg(src + r.di), v11 = __ldg(src + r.di + r.dj);
+                                    const float4 v00 = src[0], v01 = src[r.dj];
+                                    const float4 v10 = src[r.di], v11 = src[r.di + r.dj];
                                     const float wx0 = 1.f - r.wx1, wy0 = 1.f - r.wy1;
                                     v.x = wy0 * (wx0 * v00.x + r.wx1 * v01.x) + r.wy1 * (wx0 * v10.x + r.wx1 * v11.x);
                                     v.y = wy0 * (wx0 * v00.y + r.wx1 * v01.y) + r.wy1 * (wx0 * v10.y + r.wx1 * v11.y);
                                     v.z = wy0 * (wx0 * v00.z + r.wx1 * v01.z) + r.wy1 * (wx0 * v10.z + r.wx1 * v11.z);
                                     v.w = wy0 * (wx0 * v00.w + r.wx1 * v01.w) + r.wy1 * (wx0 * v10.w + r.wx1 * v11.w);
                                 } else {
-                                    v = __ldg(src);
+                                    v = src[0];
                                 }
                             }
                             float h0, h1, h2, h3, l0, l1, l2, l3;
@@ -421,14 +464,13 @@ using UL0 = UmmaLayer<128, 64, 64, 16, 32, true, 1, 4, false>;
 using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 4, false>;
 using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 3, false>;
 using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 2, true>;
+static_assert(UL0::SMEM <= 227 * 1024 && UL1::SMEM <= 227 * 1024 && UL2::SMEM <= 227 * 1024 && UL3::SMEM <= 227 * 1024, "smem");
 
 template <class L>
 int launch_umma(const UmmaArgs& base, int sm_count, cudaStream_t st) {
     UmmaArgs a = base;
-    const long long T = (long long)a.N * L::FRAME_POS;
-    TRPX_REQUIRE(T < (1LL << 30), "too many frames in one pass (%d)", a.N);
-    // the last valid output position is T - PW - 2; item i covers outputs [i*126*MB + 1, (i+1)*126*MB]
-    a.nitems = (int)((T - L::PW - 2 + (UM_BLK * L::MB) - 1) / (UM_BLK * L::MB));
+    TRPX_REQUIRE((long long)a.N * L::IPF < (1LL << 30), "too many frames in one pass (%d)", a.N);
+    a.nitems = a.N * L::IPF;     // item j of a frame covers its flat output positions [j*126*MB + 1, (j+1)*126*MB]
     static_assert(L::SMEM <= 227 * 1024, "shared memory");
     TRPX_CUDA(cudaFuncSetAttribute(cyl_umma_conv_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     const int grid = std::min(a.nitems, sm_count);

@@ -1,8 +1,12 @@
-"""Import the UNMODIFIED reference (`trphysx`) from /root/reference in THIS container.
+"""Import the UNMODIFIED reference (`trphysx`).
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing under `-m gpu`,
-smoke() or bench.py may call this.  It is used by tests/golden/make_golden.py (fixture generation) and
-by tests/test_oracle_vs_reference.py (which skips when the reference is absent).
+TEST / BASELINE INFRASTRUCTURE.  Two locations are tried, in this order:
+  1. /root/reference (the read-only source tree; exists in the build container only): used by
+     tests/golden/make_golden.py (fixture generation), tests/test_oracle_vs_reference.py and tests/test_host_api.py;
+  2. baseline/_ref (git-ignored `pip install --no-deps --target baseline/_ref` of that tree, made by
+     __graft_entry__.build(); it travels to the GPU box with the snapshot): used ONLY by bench.py's reference arm
+     (`--impl reference`, `cpu_baseline`), which times the reference's own modules on the host cores.
+Nothing under `-m gpu` or smoke() calls this.
 
 `trphysx/__init__.py:5-10` eagerly imports data_utils (h5py) and utils -> viz (matplotlib); neither is
 installed and neither is touched by the hot path, so empty stub packages are served for them
@@ -15,11 +19,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("TRPX_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("TRPX_REFERENCE_ROOT", "/root/reference"), os.path.join(_REPO, "baseline", "_ref")]
+REF_ROOT = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "trphysx"))), _CANDIDATES[0])
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "trphysx"))
+
+
+def source_tree() -> bool:
+    """True when the reference is the full source tree (has examples/: the Rossler module lives there)."""
+    return os.path.isdir(os.path.join(REF_ROOT, "examples", "rossler"))
 
 
 class _Stub(types.ModuleType):

@@ -125,13 +125,13 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* __restrict__ Aimg
 // ---------------------------------------------------------------------------------------------------------------
 // rate: one thread issues `iters` x 16 MMAs (16 distinct 4 KB A slices, `nb` distinct B slices) into two alternating
 // accumulators; cycles from first issue to completion.
-__global__ void __launch_bounds__(128) probe_rate(int N, int iters, int same_a, unsigned long long* cyc) {
+__global__ void __launch_bounds__(128) probe_rate(int N, int iters, int same_a, int misalign_rows, unsigned long long* cyc) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     float* s = reinterpret_cast<float*>(smem);
-    for (int i = tid; i < (64 * 1024 + 64 * 1024) / 4; i += 128) s[i] = 0.0f;
+    for (int i = tid; i < (64 * 1024 + 64 * 1024 + 4096) / 4; i += 128) s[i] = 0.0f;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) mbar_init(&bar, 1);
     FENCE_PROXY();
@@ -141,14 +141,14 @@ __global__ void __launch_bounds__(128) probe_rate(int N, int iters, int same_a, 
     const uint32_t tmem = tmem_base_s;
     if (tid == 0) {
         const uint32_t idesc = make_idesc(128, N);
-        const uint32_t a0 = smem_u32(smem), b0 = a0 + 64 * 1024;
+        const uint32_t a0 = smem_u32(smem) + misalign_rows * 16, b0 = smem_u32(smem) + 64 * 1024;
         // A slice j: 128 rows x 8 k at 16-byte row pitch: chunk 0 at +0, chunk 1 at +2048 (LBO), SBO = 128
         const unsigned long long t0 = clock64();
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const uint64_t ad = make_desc(a0 + (same_a ? 0 : j * 4096), 2048, 128);
-                const uint64_t bd = make_desc(b0 + (j & 3) * (uint32_t)(N * 32), (uint32_t)N * 16, 128);
+                const uint64_t bd = make_desc(b0 + 4096 + (j & 3) * (uint32_t)(N * 32), (uint32_t)N * 16, 128);
                 umma_tf32(tmem + (uint32_t)((j & 1) * 256), ad, bd, idesc, 1u);
             }
         }
@@ -284,11 +284,12 @@ int main() {
         const int nb = prop.multiProcessorCount;
         CK(cudaMalloc(&dc, nb * sizeof(unsigned long long)));
         std::vector<unsigned long long> hc(nb);
-        for (int same_a = 0; same_a < 2; same_a++)
+        for (int mis = 0; mis < 2; mis++)
             for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
+                const int same_a = 0, misalign = mis ? 2 : 0;      // A start 2 rows (32 B) off the 128-byte core-matrix boundary
                 const int iters = 256;
-                probe_rate<<<nb, 128, 128 * 1024>>>(N, iters, same_a, dc);      // warm-up
-                probe_rate<<<nb, 128, 128 * 1024>>>(N, iters, same_a, dc);
+                probe_rate<<<nb, 128, 136 * 1024>>>(N, iters, same_a, misalign, dc);      // warm-up
+                probe_rate<<<nb, 128, 136 * 1024>>>(N, iters, same_a, misalign, dc);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("rate kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
                 CK(cudaMemcpy(hc.data(), dc, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -299,7 +300,7 @@ int main() {
                 const double per = mean / (iters * 16.0);
                 printf("rate M128 N=%3d K8 tf32 (%s): %.1f cycles per MMA (max CTA %.1f) -> %.0f MAC/cycle/SM; math floor N/2 = %.0f cycles, "
                        "smem-operand model (4096+32N)/128 = %.0f cycles\n",
-                       N, same_a ? "same A slice" : "16 A slices", per, (double)mx / (iters * 16.0), 128.0 * N * 8 / per, N / 2.0,
+                       N, mis ? "A start misaligned by 2 rows" : "A start 128 B aligned", per, (double)mx / (iters * 16.0), 128.0 * N * 8 / per, N / 2.0,
                        (4096 + 32.0 * N) / 128);
             }
         cudaFree(dc);

@@ -23,11 +23,14 @@
 // MMAs, warp 5 is the loader: one lane streams, per stage, the layer-input rows the stage needs and the stage's slice of
 // the weight image into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), warps 6-15 build the
 // patch from the staged rows (bilinear upsample + TF32 split, generic-proxy stores + fence.proxy.async).  mbarrier
-// rings: src_full (TMA -> producers), full (producers + weight copy -> MMA), empty (tcgen05.commit -> loader), and per
-// 128-row block tfull (tcgen05.commit -> epilogue) / tempty (epilogue -> MMA).
+// rings: a DEEP load ring (rows + weights of a K chunk are small; the loader runs 3-6 chunks ahead, which is what hides
+// the ~1.5 us TMA round trip) with ld_full (TMA -> producers, MMA) / ld_empty (producers + tcgen05.commit -> loader), a
+// two-slot patch ring with p_full (producers -> MMA) / p_empty (tcgen05.commit -> producers), and per 128-row block
+// tfull (tcgen05.commit -> epilogue) / tempty (epilogue -> MMA).
 #include "common.cuh"
 #include "cyl_umma.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 using namespace trpx;
 
@@ -40,15 +43,17 @@ constexpr int UM_NPT = UM_PROD_WARPS * 32;                                // pro
 constexpr int UM_BLK = 126;                                               // useful rows of a 128-row M block (1 overlap each side)
 constexpr int UM_CHUNK = 16;                                              // output channels per epilogue pass
 
-template <int CIN_, int COUT_, int COUT_REAL_, int H_, int W_, bool UP_, int MB_, int NSTAGE_, bool FINAL_>
+template <int CIN_, int COUT_, int COUT_REAL_, int H_, int W_, bool UP_, int MB_, int LS_, bool FINAL_>
 struct UmmaLayer {
-    static constexpr int CIN = CIN_, COUT = COUT_, COUT_REAL = COUT_REAL_, H = H_, W = W_, MB = MB_, NSTAGE = NSTAGE_;
+    static constexpr int CIN = CIN_, COUT = COUT_, COUT_REAL = COUT_REAL_, H = H_, W = W_, MB = MB_;
+    static constexpr int LS = LS_;                                        // load ring depth (layer-input rows + weight slice of a K chunk)
+    static constexpr int PS = 2;                                          // patch ring depth (one being built, one being multiplied)
     static constexpr bool UP = UP_, FINAL = FINAL_;
     static constexpr int HS = UP ? H / 2 : H, WS = UP ? W / 2 : W;        // layer input size
     static constexpr int PW = W + 2, FRAME_POS = (H + 2) * PW;            // flat padded pixels per row / frame
     static constexpr int NPOS = UM_BLK * MB + 2 + 2 * PW;                 // staged positions of one work item
     static constexpr int ITEM_OUT = UM_BLK * MB;                          // output positions of one work item
-    static constexpr int IPF = (FRAME_POS - PW - 2 + ITEM_OUT - 1) / ITEM_OUT;   // work items per frame
+    static constexpr int IPF = (H * PW + W + ITEM_OUT - 1) / ITEM_OUT;    // work items per frame (last output: row H, column W)
     static constexpr int ROWS_OUT = (NPOS + PW - 2) / PW + 1;             // padded rows a work item can touch
     static constexpr int SRC_ROWS = UP ? ROWS_OUT / 2 + 3 : ROWS_OUT;     // layer-input rows behind them
     static constexpr int SRC_BYTES = 2 * SRC_ROWS * WS * 16;              // [quad 2][row][col][4 f]
@@ -57,12 +62,12 @@ struct UmmaLayer {
     static constexpr int KCH = CIN / 8;                                   // K chunks of 8 input channels
     static constexpr int PATCH_BYTES = 2 * 2 * NPOS * 16;                 // [plane][kc][pos][4 f]
     static constexpr int W_BYTES = 3 * 2 * N6 * 16;                       // [dy][kc][n][4 f]
-    static constexpr int STAGE_BYTES = PATCH_BYTES + W_BYTES + SRC_BYTES;
+    static constexpr int LOAD_BYTES = W_BYTES + SRC_BYTES;                // one load-ring slot: [weights][rows]
     static constexpr int TMEM_USED = MB * N6;
     static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
-    static constexpr int PER = (NPOS + UM_NPT - 1) / UM_NPT;              // positions per producer thread
     static constexpr int EDGE_FLOATS = 2 * 2 * 4 * UM_CHUNK;              // [parity][left|right][quarter][16]
-    static constexpr size_t SMEM = (size_t)NSTAGE * STAGE_BYTES + EDGE_FLOATS * 4 + 256 + 128;
+    static constexpr size_t RING_BYTES = (size_t)PS * PATCH_BYTES + (size_t)LS * LOAD_BYTES;
+    static constexpr size_t SMEM = RING_BYTES + EDGE_FLOATS * 4 + 512 + 128;
     static_assert(CIN % 8 == 0 && COUT % 16 == 0 && N3 % 16 == 0 && N3 <= 256, "shape");
     static_assert(TMEM_USED <= 512, "TMEM");
     static_assert(UM_BLK * (MB - 1) + 2 * PW + 128 <= NPOS, "patch too small");
@@ -78,6 +83,9 @@ struct UmmaArgs {
     const unsigned char* mask;
     int N;
     int nitems;
+    int debug;              // TRPX_UMMA_DEBUG bits (timing experiments only, results are garbage): 1 producers idle, 2 no MMAs,
+                            // 4 epilogue skips the stores, 8 no fence.proxy.async, 16 no layer-input TMA, 32 no weight TMA,
+                            // 64 epilogue skips TMEM loads and the edge exchange
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -146,12 +154,6 @@ __device__ __forceinline__ Lerp1 lerp1(int dst, int in_size, float scale) {
     return r;
 }
 
-struct PosRec {       // where a staged position reads the staged layer-input rows (float4 units, channel quad 0)
-    int o00;          // -1: outside the frame (zeros)
-    int dj, di;       // offset of the right / lower neighbour
-    float wy1, wx1;
-};
-
 // layer-input rows [i_lo, i_lo + nrows) needed by work item j of a frame (the loader and the producers agree on this)
 template <class L>
 __device__ __forceinline__ void item_src_rows(int lb, int& i_lo, int& nrows) {
@@ -171,22 +173,27 @@ __device__ __forceinline__ void item_src_rows(int lb, int& i_lo, int& nrows) {
 template <class L>
 __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const UmmaArgs a) {
     extern __shared__ __align__(128) unsigned char um_smem[];
-    unsigned char* stages = um_smem;
-    float* edge = reinterpret_cast<float*>(um_smem + (size_t)L::NSTAGE * L::STAGE_BYTES);
+    unsigned char* patches = um_smem;                                    // [PS][PATCH_BYTES]
+    unsigned char* loads = um_smem + (size_t)L::PS * L::PATCH_BYTES;     // [LS][weights | layer-input rows]
+    float* edge = reinterpret_cast<float*>(um_smem + L::RING_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(edge + L::EDGE_FLOATS);
-    uint64_t* full = bars;                       // [NSTAGE] producers (10 warps) + weight copy (expect_tx)
-    uint64_t* empty = full + L::NSTAGE;          // [NSTAGE] tcgen05.commit
-    uint64_t* src_full = empty + L::NSTAGE;      // [NSTAGE] layer-input rows landed (expect_tx)
-    uint64_t* tfull = src_full + L::NSTAGE;      // [MB] accumulator of block b complete
+    uint64_t* p_full = bars;                     // [PS] patch built (producer warps)
+    uint64_t* p_empty = p_full + L::PS;          // [PS] patch consumed (tcgen05.commit)
+    uint64_t* ld_full = p_empty + L::PS;         // [LS] rows + weights landed (TMA complete_tx)
+    uint64_t* ld_empty = ld_full + L::LS;        // [LS] rows read by the producers + weights consumed (tcgen05.commit)
+    uint64_t* tfull = ld_empty + L::LS;          // [MB] accumulator of block b complete
     uint64_t* tempty = tfull + L::MB;            // [MB] accumulator of block b drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + L::MB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < L::NSTAGE; s++) {
-            mbar_init(&full[s], UM_PROD_WARPS + 1);
-            mbar_init(&empty[s], 1);
-            mbar_init(&src_full[s], 1);
+        for (int s = 0; s < L::PS; s++) {
+            mbar_init(&p_full[s], UM_PROD_WARPS);
+            mbar_init(&p_empty[s], 1);
+        }
+        for (int s = 0; s < L::LS; s++) {
+            mbar_init(&ld_full[s], 1);
+            mbar_init(&ld_empty[s], UM_PROD_WARPS + 1);
         }
         for (int b = 0; b < L::MB; b++) {
             mbar_init(&tfull[b], 1);
@@ -194,6 +201,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
         }
     }
     if (warp == UM_MMA_WARP) tmem_alloc(tmem_slot, L::TMEM_COLS);
+    // staged positions outside the frame (first / last work item of a frame) are never written: start from zeros so
+    // that the rows of the accumulator nobody reads are at least finite
+    {
+        float4* pz = reinterpret_cast<float4*>(patches);
+        for (int i = tid; i < L::PS * L::PATCH_BYTES / 16; i += UM_THREADS) pz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
             const int n = item / L::IPF;
             const int lb = (item - n * L::IPF) * L::ITEM_OUT;
             for (int b = 0; b < L::MB; b++) {
-                mbar_wait(&tfull[b], iter & 1);
+                mbar_wait_backoff(&tfull[b], iter & 1, 64);
                 tc_fence_after();
                 const int t = q * 32 + lane;                           // row of the block
                 const int lp = lb + UM_BLK * b + t;                    // flat padded position inside the frame
@@ -217,6 +231,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                 const bool valid = t >= 1 && t <= UM_BLK && yp >= 1 && yp <= L::H && xp >= 1 && xp <= L::W;
                 const int y = yp - 1, x = xp - 1;
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)(b * L::N6);
+                if (a.debug & 64) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[b]);
+                    continue;
+                }
                 for (int c = 0; c < L::COUT / UM_CHUNK; c++) {
                     const int co0 = c * UM_CHUNK;
                     float v[3][UM_CHUNK];
@@ -254,7 +274,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                         o[j] = (l + v[1][j]) + r;
                     }
                     par ^= 1;
-                    if (valid) {
+                    if (valid && !(a.debug & 4)) {
                         if constexpr (!L::FINAL) {
                             float4* out4 = reinterpret_cast<float4*>(a.out);
 #pragma unroll
@@ -288,13 +308,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
             constexpr uint32_t idesc6 = umma_idesc_tf32(128, L::CONCAT ? L::N6 : L::N3);
             constexpr uint32_t idesc3 = umma_idesc_tf32(128, L::N3);
             constexpr uint32_t LBO_A = L::NPOS * 16, LBO_B = L::N6 * 16;
-            int s = 0, ph = 0, iter = 0;
+            int ps = 0, pph = 0, ls = 0, lph = 0, iter = 0;
             for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, iter++) {
                 for (int kc = 0; kc < L::KCH; kc++) {
-                    mbar_wait(&full[s], ph);
+                    mbar_wait(&ld_full[ls], lph);
+                    mbar_wait(&p_full[ps], pph);
                     tc_fence_after();
-                    const uint32_t sp = smem_u32(stages + (size_t)s * L::STAGE_BYTES);
-                    const uint32_t sw = sp + L::PATCH_BYTES;
+                    const uint32_t sp = smem_u32(patches + (size_t)ps * L::PATCH_BYTES);
+                    const uint32_t sw = smem_u32(loads + (size_t)ls * L::LOAD_BYTES);
                     for (int b = 0; b < L::MB; b++) {
                         if (kc == 0) {
                             mbar_wait(&tempty[b], (iter & 1) ^ 1);
@@ -303,6 +324,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                         const uint32_t tc = tmem_base + (uint32_t)(b * L::N6);
 #pragma unroll
                         for (int dy = 0; dy < 3; dy++) {
+                            if (a.debug & 2) break;
                             const uint32_t arow = (uint32_t)(UM_BLK * b + dy * L::PW) * 16u;
                             const uint64_t a_hi = umma_desc(sp + arow, LBO_A);
                             const uint64_t a_lo = umma_desc(sp + 2 * L::NPOS * 16 + arow, LBO_A);
@@ -319,8 +341,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                         }
                         if (kc == L::KCH - 1) umma_commit(&tfull[b]);
                     }
-                    umma_commit(&empty[s]);
-                    if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                    umma_commit(&p_empty[ps]);
+                    umma_commit(&ld_empty[ls]);
+                    if (++ps == L::PS) { ps = 0; pph ^= 1; }
+                    if (++ls == L::LS) { ls = 0; lph ^= 1; }
                 }
             }
         }
@@ -336,98 +360,119 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                 item_src_rows<L>(lb, i_lo, nrows);
                 const uint32_t row_bytes = (uint32_t)nrows * L::WS * 16u;
                 for (int kc = 0; kc < L::KCH; kc++) {
-                    mbar_wait(&empty[s], ph ^ 1);
-                    unsigned char* st = stages + (size_t)s * L::STAGE_BYTES;
-                    mbar_expect_tx(&src_full[s], 2 * row_bytes);
+                    mbar_wait(&ld_empty[s], ph ^ 1);
+                    unsigned char* st = loads + (size_t)s * L::LOAD_BYTES;
+                    const bool do_src = !(a.debug & 16), do_w = !(a.debug & 32);
+                    mbar_expect_tx(&ld_full[s], (do_src ? 2 * row_bytes : 0) + (do_w ? L::W_BYTES : 0));
 #pragma unroll
                     for (int qd = 0; qd < 2; qd++) {
                         const float* src = a.in + ((((size_t)n * (L::CIN / 4) + 2 * kc + qd) * L::HS + i_lo) * L::WS) * 4;
-                        bulk_g2s(st + L::PATCH_BYTES + L::W_BYTES + qd * (L::SRC_ROWS * L::WS * 16), src, row_bytes, &src_full[s]);
+                        if (do_src) bulk_g2s(st + L::W_BYTES + qd * (L::SRC_ROWS * L::WS * 16), src, row_bytes, &ld_full[s]);
                     }
-                    mbar_expect_tx(&full[s], L::W_BYTES);
-                    bulk_g2s(st + L::PATCH_BYTES, a.wimg + (size_t)kc * (L::W_BYTES / 4), L::W_BYTES, &full[s]);
-                    if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                    if (do_w) bulk_g2s(st, a.wimg + (size_t)kc * (L::W_BYTES / 4), L::W_BYTES, &ld_full[s]);
+                    if (++s == L::LS) { s = 0; ph ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else {
         // =============================== producers ===============================
+        // One thread owns ONE padded column xp (both channel quads of the stage: two independent dependency chains) and a
+        // slice of the item's rows, and walks down them: the horizontally interpolated layer-input rows it needs stay in
+        // registers (each serves two output rows).  The producers are latency bound (few warps, ~6 cycles per issued
+        // instruction), so what counts is instructions per thread and independent work inside a thread.
         const int ptid = tid - (UM_LOAD_WARP + 1) * 32;
+        constexpr int RSPLIT_ = UM_NPT / L::PW;
+        constexpr int RSPLIT = RSPLIT_ < 1 ? 1 : (RSPLIT_ > L::ROWS_OUT ? L::ROWS_OUT : RSPLIT_);
+        static_assert(L::PW <= UM_NPT, "one producer thread per padded column");
+        const bool active = ptid < L::PW * RSPLIT;
+        const int xp = ptid % L::PW, rs = ptid / L::PW;
+        const int xsrc = min(max(xp - 1, 0), L::W - 1);                    // replicate padding
         const float sh = L::UP ? (float)(L::HS - 1) / (float)(L::H - 1) : 0.f;
-        const float sw_ = L::UP ? (float)(L::WS - 1) / (float)(L::W - 1) : 0.f;
-        int s = 0, ph = 0;
+        int j0 = xsrc, dj = 0;
+        float wx1 = 0.f;
+        if constexpr (L::UP) {
+            const Lerp1 lx = lerp1(xsrc, L::WS, (float)(L::WS - 1) / (float)(L::W - 1));
+            j0 = lx.i0; dj = lx.i1 - lx.i0; wx1 = lx.l1;
+        }
+        const float wx0 = 1.f - wx1;
+        constexpr int QS = L::SRC_ROWS * L::WS;                            // float4 per staged quad
+        int ps = 0, pph = 0, ls = 0, lph = 0;
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
             const int n = item / L::IPF;
             const int lb = (item - n * L::IPF) * L::ITEM_OUT;
             int i_lo, nrows;
             item_src_rows<L>(lb, i_lo, nrows);
-            PosRec rec[L::PER];
-#pragma unroll
-            for (int j = 0; j < L::PER; j++) {
-                const int p = ptid + j * UM_NPT;
-                const int lp = lb - L::PW + p;                         // flat padded position inside the frame
-                PosRec r;
-                r.o00 = -1; r.dj = 0; r.di = 0; r.wy1 = 0.f; r.wx1 = 0.f;
-                if (p < L::NPOS && lp >= 0 && lp < L::FRAME_POS) {
-                    const int yp = lp / L::PW, xp = lp - yp * L::PW;
-                    const int y = min(max(yp - 1, 0), L::H - 1), x = min(max(xp - 1, 0), L::W - 1);     // replicate padding
-                    if constexpr (L::UP) {
-                        const Lerp1 ly = lerp1(y, L::HS, sh), lx = lerp1(x, L::WS, sw_);
-                        r.o00 = (ly.i0 - i_lo) * L::WS + lx.i0;
-                        r.dj = lx.i1 - lx.i0;
-                        r.di = (ly.i1 - ly.i0) * L::WS;
-                        r.wy1 = ly.l1;
-                        r.wx1 = lx.l1;
-                    } else {
-                        r.o00 = (y - i_lo) * L::WS + x;
-                    }
-                    if (r.o00 + r.di + r.dj >= nrows * L::WS) r.o00 = -1;          // cannot happen (rows are sized for it)
-                }
-                rec[j] = r;
-            }
+            const int lp_a = max(lb - L::PW, 0), lp_b = min(lb - L::PW + L::NPOS, L::FRAME_POS);     // staged flat range
+            const int yp_a = lp_a / L::PW, yp_b = (lp_b - 1) / L::PW;
+            const int per = (yp_b - yp_a + RSPLIT) / RSPLIT;
+            const int r0 = yp_a + rs * per, r1 = min(r0 + per, yp_b + 1);
             for (int kc = 0; kc < L::KCH; kc++) {
-                mbar_wait(&src_full[s], ph);
-                unsigned char* st = stages + (size_t)s * L::STAGE_BYTES;
-                const float4* src4 = reinterpret_cast<const float4*>(st + L::PATCH_BYTES + L::W_BYTES);
-                const uint32_t sbase = smem_u32(st);
+                mbar_wait(&ld_full[ls], lph);
+                mbar_wait(&p_empty[ps], pph ^ 1);
+                if (active && !(a.debug & 1)) {
+                    const float4* src4 = reinterpret_cast<const float4*>(loads + (size_t)ls * L::LOAD_BYTES + L::W_BYTES);
+                    const uint32_t dbase = smem_u32(patches + (size_t)ps * L::PATCH_BYTES);
+                    int cur = -1000;
+                    float4 hA[2], hB[2];
+                    hA[0] = hA[1] = hB[0] = hB[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int yp = r0; yp < r1; yp++) {
+                        const int y = min(max(yp - 1, 0), L::H - 1);
+                        float4 v[2];
+                        if constexpr (L::UP) {
+                            const Lerp1 ly = lerp1(y, L::HS, sh);
+                            if (ly.i0 != cur) {
+                                const float4* ra = src4 + (ly.i0 - i_lo) * L::WS + j0;
+                                const float4* rb = src4 + (min(ly.i0 + 1, L::HS - 1) - i_lo) * L::WS + j0;
+                                const bool shift = ly.i0 == cur + 1;
 #pragma unroll
-                for (int j = 0; j < L::PER; j++) {
-                    const int p = ptid + j * UM_NPT;
-                    if (p < L::NPOS) {
-                        const PosRec r = rec[j];
-#pragma unroll
-                        for (int qd = 0; qd < 2; qd++) {
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (r.o00 >= 0) {
-                                const float4* src = src4 + qd * (L::SRC_ROWS * L::WS) + r.o00;
-                                if constexpr (L::UP) {
-                                    const float4 v00 = src[0], v01 = src[r.dj];
-                                    const float4 v10 = src[r.di], v11 = src[r.di + r.dj];
-                                    const float wx0 = 1.f - r.wx1, wy0 = 1.f - r.wy1;
-                                    v.x = wy0 * (wx0 * v00.x + r.wx1 * v01.x) + r.wy1 * (wx0 * v10.x + r.wx1 * v11.x);
-                                    v.y = wy0 * (wx0 * v00.y + r.wx1 * v01.y) + r.wy1 * (wx0 * v10.y + r.wx1 * v11.y);
-                                    v.z = wy0 * (wx0 * v00.z + r.wx1 * v01.z) + r.wy1 * (wx0 * v10.z + r.wx1 * v11.z);
-                                    v.w = wy0 * (wx0 * v00.w + r.wx1 * v01.w) + r.wy1 * (wx0 * v10.w + r.wx1 * v11.w);
-                                } else {
-                                    v = src[0];
+                                for (int qd = 0; qd < 2; qd++) {
+                                    if (shift) {
+                                        hA[qd] = hB[qd];
+                                    } else {
+                                        const float4 u0 = ra[qd * QS], u1 = ra[qd * QS + dj];
+                                        hA[qd] = make_float4(wx0 * u0.x + wx1 * u1.x, wx0 * u0.y + wx1 * u1.y,
+                                                             wx0 * u0.z + wx1 * u1.z, wx0 * u0.w + wx1 * u1.w);
+                                    }
+                                    const float4 u0 = rb[qd * QS], u1 = rb[qd * QS + dj];
+                                    hB[qd] = make_float4(wx0 * u0.x + wx1 * u1.x, wx0 * u0.y + wx1 * u1.y,
+                                                         wx0 * u0.z + wx1 * u1.z, wx0 * u0.w + wx1 * u1.w);
                                 }
+                                cur = ly.i0;
                             }
-                            float h0, h1, h2, h3, l0, l1, l2, l3;
-                            split_tf32(v.x, h0, l0);
-                            split_tf32(v.y, h1, l1);
-                            split_tf32(v.z, h2, l2);
-                            split_tf32(v.w, h3, l3);
-                            const uint32_t d = sbase + (uint32_t)(qd * L::NPOS + p) * 16u;
-                            st_shared_v4(d, h0, h1, h2, h3);
-                            st_shared_v4(d + 2 * L::NPOS * 16, l0, l1, l2, l3);
+                            const float wy1 = ly.l1, wy0 = 1.f - wy1;
+#pragma unroll
+                            for (int qd = 0; qd < 2; qd++)
+                                v[qd] = make_float4(wy0 * hA[qd].x + wy1 * hB[qd].x, wy0 * hA[qd].y + wy1 * hB[qd].y,
+                                                    wy0 * hA[qd].z + wy1 * hB[qd].z, wy0 * hA[qd].w + wy1 * hB[qd].w);
+                        } else {
+                            v[0] = src4[(y - i_lo) * L::WS + j0];
+                            v[1] = src4[QS + (y - i_lo) * L::WS + j0];
+                        }
+                        const int p = yp * L::PW + xp - (lb - L::PW);
+                        if (p >= 0 && p < L::NPOS) {
+#pragma unroll
+                            for (int qd = 0; qd < 2; qd++) {
+                                float h0, h1, h2, h3, l0, l1, l2, l3;
+                                split_tf32(v[qd].x, h0, l0);
+                                split_tf32(v[qd].y, h1, l1);
+                                split_tf32(v[qd].z, h2, l2);
+                                split_tf32(v[qd].w, h3, l3);
+                                const uint32_t d = dbase + (uint32_t)(qd * L::NPOS + p) * 16u;
+                                st_shared_v4(d, h0, h1, h2, h3);
+                                st_shared_v4(d + 2 * L::NPOS * 16, l0, l1, l2, l3);
+                            }
                         }
                     }
                 }
-                fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                if (!(a.debug & 8)) fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
-                if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                if (lane == 0) {
+                    mbar_arrive(&p_full[ps]);
+                    mbar_arrive(&ld_empty[ls]);       // the staged rows have been read
+                }
+                if (++ps == L::PS) { ps = 0; pph ^= 1; }
+                if (++ls == L::LS) { ls = 0; lph ^= 1; }
             }
         }
     }
@@ -459,21 +504,40 @@ __global__ void umma_wimg_kernel(const float* __restrict__ w, float* __restrict_
     }
 }
 
-//                      CIN COUT real  H    W   UP    MB NSTAGE FINAL
+//                      CIN COUT real  H    W   UP    MB  LS  FINAL
 using UL0 = UmmaLayer<128, 64, 64, 16, 32, true, 1, 4, false>;
-using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 4, false>;
-using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 3, false>;
-using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 2, true>;
+using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 6, false>;
+using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 5, false>;
+using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 3, true>;
 static_assert(UL0::SMEM <= 227 * 1024 && UL1::SMEM <= 227 * 1024 && UL2::SMEM <= 227 * 1024 && UL3::SMEM <= 227 * 1024, "smem");
 
 template <class L>
 int launch_umma(const UmmaArgs& base, int sm_count, cudaStream_t st) {
     UmmaArgs a = base;
     TRPX_REQUIRE((long long)a.N * L::IPF < (1LL << 30), "too many frames in one pass (%d)", a.N);
+    {
+        const char* dbg = getenv("TRPX_UMMA_DEBUG");
+        a.debug = dbg ? atoi(dbg) : 0;
+    }
     a.nitems = a.N * L::IPF;     // item j of a frame covers its flat output positions [j*126*MB + 1, (j+1)*126*MB]
     static_assert(L::SMEM <= 227 * 1024, "shared memory");
     TRPX_CUDA(cudaFuncSetAttribute(cyl_umma_conv_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
     const int grid = std::min(a.nitems, sm_count);
+    if (getenv("TRPX_UMMA_TIMING")) {          // development aid: per-layer device time (synchronises)
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        cyl_umma_conv_kernel<L><<<grid, UM_THREADS, L::SMEM, st>>>(a);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "umma layer CIN=%d COUT=%d N=%d items=%d chunks/item=%d: %.1f us (%.0f cycles per chunk per CTA at 1.75 GHz)\n", L::CIN,
+                L::COUT, a.N, a.nitems, L::KCH, ms * 1e3,
+                ms * 1e-3 * 1.75e9 / ((double)((a.nitems + grid - 1) / grid) * L::KCH));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return TRPX_OK;
+    }
     cyl_umma_conv_kernel<L><<<grid, UM_THREADS, L::SMEM, st>>>(a);
     TRPX_CUDA(cudaGetLastError());
     return TRPX_OK;

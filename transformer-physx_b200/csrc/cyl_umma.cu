@@ -19,9 +19,9 @@
 // (at most 48 instructions long) and the two small terms accumulate in a second column set; the epilogue adds them.
 // Where 6*Cout <= 256 the a_hi pass computes both column sets in ONE MMA against the concatenated [w_hi | w_lo] rows.
 //
-// Roles (512 threads, one persistent CTA per SM): warps 0-3 epilogue (TMEM -> registers -> global), warp 4 issues the
-// MMAs, warp 5 is the loader: one lane streams, per stage, the layer-input rows the stage needs and the stage's slice of
-// the weight image into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), warps 6-15 build the
+// Roles (640 threads, one persistent CTA per SM): warps 0-7 epilogue (two groups of four; TMEM -> registers -> global),
+// warp 8 issues the MMAs, warp 9 is the loader: one lane streams, per stage, the layer-input rows the stage needs and the stage's slice of
+// the weight image into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), warps 10-19 build the
 // patch from the staged rows (bilinear upsample + TF32 split, generic-proxy stores + fence.proxy.async).  mbarrier
 // rings: a DEEP load ring (rows + weights of a K chunk are small; the loader runs 3-6 chunks ahead, which is what hides
 // the ~1.5 us TMA round trip) with ld_full (TMA -> producers, MMA) / ld_empty (producers + tcgen05.commit -> loader), a
@@ -36,18 +36,22 @@ using namespace trpx;
 
 namespace {
 
-constexpr int UM_EPI_WARPS = 4, UM_PROD_WARPS = 10;
+constexpr int UM_EPI_WARPS = 8, UM_PROD_WARPS = 10;                       // two epilogue groups of 4 warps (one per TMEM lane quarter)
 constexpr int UM_MMA_WARP = UM_EPI_WARPS, UM_LOAD_WARP = UM_EPI_WARPS + 1;
-constexpr int UM_THREADS = (UM_EPI_WARPS + 2 + UM_PROD_WARPS) * 32;       // 512
+constexpr int UM_THREADS = (UM_EPI_WARPS + 2 + UM_PROD_WARPS) * 32;       // 640
 constexpr int UM_NPT = UM_PROD_WARPS * 32;                                // producer threads
 constexpr int UM_BLK = 126;                                               // useful rows of a 128-row M block (1 overlap each side)
-constexpr int UM_CHUNK = 16;                                              // output channels per epilogue pass
+constexpr int UM_CHUNK = 16;                                              // output channels per epilogue pass (4 for the 3-channel last layer)
 
-template <int CIN_, int COUT_, int COUT_REAL_, int H_, int W_, bool UP_, int MB_, int LS_, bool FINAL_>
+template <int CIN_, int COUT_, int COUT_REAL_, int H_, int W_, bool UP_, int MB_, int NBUF_, int PS_, int LS_, bool FINAL_>
 struct UmmaLayer {
     static constexpr int CIN = CIN_, COUT = COUT_, COUT_REAL = COUT_REAL_, H = H_, W = W_, MB = MB_;
     static constexpr int LS = LS_;                                        // load ring depth (layer-input rows + weight slice of a K chunk)
-    static constexpr int PS = 2;                                          // patch ring depth (one being built, one being multiplied)
+    static constexpr int PS = PS_;                                        // patch ring depth
+    static constexpr int NBUF = NBUF_;                                    // TMEM accumulator buffers (2: the epilogue of item i overlaps the MMAs of item i+1)
+    static constexpr int EC = FINAL_ ? 4 : UM_CHUNK;                      // output channels per epilogue pass
+    static constexpr int NCHUNK = FINAL_ ? 1 : COUT_ / UM_CHUNK;          // epilogue passes per block
+    static constexpr int EPI_GROUPS_PER_BLOCK = (NCHUNK % 2 == 0) ? 2 : 1;   // (block, chunk) units are dealt round-robin to the 2 groups
     static constexpr bool UP = UP_, FINAL = FINAL_;
     static constexpr int HS = UP ? H / 2 : H, WS = UP ? W / 2 : W;        // layer input size
     static constexpr int PW = W + 2, FRAME_POS = (H + 2) * PW;            // flat padded pixels per row / frame
@@ -63,9 +67,9 @@ struct UmmaLayer {
     static constexpr int PATCH_BYTES = 2 * 2 * NPOS * 16;                 // [plane][kc][pos][4 f]
     static constexpr int W_BYTES = 3 * 2 * N6 * 16;                       // [dy][kc][n][4 f]
     static constexpr int LOAD_BYTES = W_BYTES + SRC_BYTES;                // one load-ring slot: [weights][rows]
-    static constexpr int TMEM_USED = MB * N6;
+    static constexpr int TMEM_USED = NBUF * MB * N6;
     static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
-    static constexpr int EDGE_FLOATS = 2 * 2 * 4 * UM_CHUNK;              // [parity][left|right][quarter][16]
+    static constexpr int EDGE_FLOATS = 2 * 2 * 2 * 4 * UM_CHUNK;          // [group][parity][left|right][quarter][16]
     static constexpr size_t RING_BYTES = (size_t)PS * PATCH_BYTES + (size_t)LS * LOAD_BYTES;
     static constexpr size_t SMEM = RING_BYTES + EDGE_FLOATS * 4 + 512 + 128;
     static_assert(CIN % 8 == 0 && COUT % 16 == 0 && N3 % 16 == 0 && N3 <= 256, "shape");
@@ -120,6 +124,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -138,6 +146,24 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     hi = __uint_as_float(u);
     lo = x - hi;
+}
+
+// packed FP32 (f32x2) helpers: (d0, d1) = (a0, a1) * b   and   (d0, d1) = (a0, a1) - (b0, b1)
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b) {
+    asm("{\n.reg .b64 ra, rb, rc;\n"
+        "mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %4};\n"
+        "mul.rn.f32x2 rc, ra, rb;\n"
+        "mov.b64 {%0, %1}, rc;\n}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b));
+}
+__device__ __forceinline__ void fsub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n.reg .b64 ra, rb, rc;\n"
+        "mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n"
+        "sub.rn.f32x2 rc, ra, rb;\n"
+        "mov.b64 {%0, %1}, rc;\n}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
 // bilinear x2 (align_corners=True) source index / weight, as aten's area_pixel_compute_source_index
@@ -181,9 +207,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
     uint64_t* p_empty = p_full + L::PS;          // [PS] patch consumed (tcgen05.commit)
     uint64_t* ld_full = p_empty + L::PS;         // [LS] rows + weights landed (TMA complete_tx)
     uint64_t* ld_empty = ld_full + L::LS;        // [LS] rows read by the producers + weights consumed (tcgen05.commit)
-    uint64_t* tfull = ld_empty + L::LS;          // [MB] accumulator of block b complete
-    uint64_t* tempty = tfull + L::MB;            // [MB] accumulator of block b drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + L::MB);
+    uint64_t* tfull = ld_empty + L::LS;          // [NBUF][MB] accumulator of block b complete
+    uint64_t* tempty = tfull + L::NBUF * L::MB;  // [NBUF][MB] accumulator of block b drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + L::NBUF * L::MB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -195,9 +221,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
             mbar_init(&ld_full[s], 1);
             mbar_init(&ld_empty[s], UM_PROD_WARPS + 1);
         }
-        for (int b = 0; b < L::MB; b++) {
+        for (int b = 0; b < L::NBUF * L::MB; b++) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], UM_EPI_WARPS);
+            mbar_init(&tempty[b], 4 * L::EPI_GROUPS_PER_BLOCK);
         }
     }
     if (warp == UM_MMA_WARP) tmem_alloc(tmem_slot, L::TMEM_COLS);
@@ -215,70 +241,97 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
 
     if (warp < UM_EPI_WARPS) {
         // =============================== epilogue ===============================
-        const int q = warp;
+        // two groups of four warps (warp % 4 = TMEM lane quarter); the (block, 16-channel chunk) units of an item are
+        // dealt round-robin to the groups
+        const int eg = warp >> 2, q = warp & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int par = 0;
         int iter = 0;
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, iter++) {
             const int n = item / L::IPF;
             const int lb = (item - n * L::IPF) * L::ITEM_OUT;
+            const int buf = L::NBUF == 2 ? (iter & 1) : 0;
+            const uint32_t tpar = L::NBUF == 2 ? ((iter >> 1) & 1) : (iter & 1);
             for (int b = 0; b < L::MB; b++) {
-                mbar_wait_backoff(&tfull[b], iter & 1, 64);
+                if (L::EPI_GROUPS_PER_BLOCK == 1 && ((b * L::NCHUNK) & 1) != eg) continue;       // NCHUNK odd: whole block to one group
+                mbar_wait_backoff(&tfull[buf * L::MB + b], tpar, 32);
                 tc_fence_after();
                 const int t = q * 32 + lane;                           // row of the block
                 const int lp = lb + UM_BLK * b + t;                    // flat padded position inside the frame
                 const int yp = lp / L::PW, xp = lp - yp * L::PW;
                 const bool valid = t >= 1 && t <= UM_BLK && yp >= 1 && yp <= L::H && xp >= 1 && xp <= L::W;
                 const int y = yp - 1, x = xp - 1;
-                const uint32_t tcol = tmem_base + lane_base + (uint32_t)(b * L::N6);
+                const uint32_t tcol = tmem_base + lane_base + (uint32_t)((buf * L::MB + b) * L::N6);
                 if (a.debug & 64) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[b]);
+                    if (lane == 0) mbar_arrive(&tempty[buf * L::MB + b]);
                     continue;
                 }
-                for (int c = 0; c < L::COUT / UM_CHUNK; c++) {
-                    const int co0 = c * UM_CHUNK;
-                    float v[3][UM_CHUNK];
+                constexpr int CSTEP = L::EPI_GROUPS_PER_BLOCK;        // 2: this group takes every other chunk of the block
+                constexpr int EC = L::EC;
+                for (int c = (CSTEP == 2 ? eg : 0); c < L::NCHUNK; c += CSTEP) {
+                    const int co0 = c * EC;
+                    float v[3][EC];
 #pragma unroll
                     for (int dx = 0; dx < 3; dx++) {
-                        uint32_t rh[16], rs[16];
-                        tmem_ld16(tcol + (uint32_t)(dx * L::COUT + co0), rh);
-                        tmem_ld16(tcol + (uint32_t)(L::N3 + dx * L::COUT + co0), rs);
+                        uint32_t rh[EC], rs[EC];
+                        if constexpr (EC == 16) {
+                            tmem_ld16(tcol + (uint32_t)(dx * L::COUT + co0), rh);
+                            tmem_ld16(tcol + (uint32_t)(L::N3 + dx * L::COUT + co0), rs);
+                        } else {
+                            tmem_ld4(tcol + (uint32_t)(dx * L::COUT + co0), rh);
+                            tmem_ld4(tcol + (uint32_t)(L::N3 + dx * L::COUT + co0), rs);
+                        }
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < UM_CHUNK; j++) v[dx][j] = __uint_as_float(rh[j]) + __uint_as_float(rs[j]);
+                        for (int j = 0; j < EC; j++) v[dx][j] = __uint_as_float(rh[j]) + __uint_as_float(rs[j]);
                     }
-                    if (c == L::COUT / UM_CHUNK - 1) {                 // block drained: the next item may overwrite it
+                    if (c + CSTEP >= L::NCHUNK) {                      // this group is done with the block's accumulator
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[b]);
+                        if (lane == 0) mbar_arrive(&tempty[buf * L::MB + b]);
                     }
-                    float* eb = edge + (size_t)(par * 2) * 4 * UM_CHUNK;
+                    // rows 31|32, 63|64, 95|96 of the block sit in different warps: their dx = 0 / dx = 2 partial sums travel
+                    // through shared memory (one float4 vector store / load per 4 channels)
+                    float4* eb = reinterpret_cast<float4*>(edge + (size_t)((eg * 2 + par) * 2) * 4 * UM_CHUNK);
                     if (lane == 31) {
 #pragma unroll
-                        for (int j = 0; j < UM_CHUNK; j++) eb[(0 * 4 + q) * UM_CHUNK + j] = v[0][j];
+                        for (int j = 0; j < EC / 4; j++) eb[(0 * 4 + q) * (UM_CHUNK / 4) + j] = make_float4(v[0][4 * j], v[0][4 * j + 1], v[0][4 * j + 2], v[0][4 * j + 3]);
                     }
                     if (lane == 0) {
 #pragma unroll
-                        for (int j = 0; j < UM_CHUNK; j++) eb[(1 * 4 + q) * UM_CHUNK + j] = v[2][j];
+                        for (int j = 0; j < EC / 4; j++) eb[(1 * 4 + q) * (UM_CHUNK / 4) + j] = make_float4(v[2][4 * j], v[2][4 * j + 1], v[2][4 * j + 2], v[2][4 * j + 3]);
                     }
-                    named_bar_sync(1, UM_EPI_WARPS * 32);
-                    float o[UM_CHUNK];
+                    named_bar_sync(1 + eg, 128);
+                    float lv[EC], rv[EC], o[EC];
 #pragma unroll
-                    for (int j = 0; j < UM_CHUNK; j++) {
-                        float l = __shfl_up_sync(FULL, v[0][j], 1);
-                        float r = __shfl_down_sync(FULL, v[2][j], 1);
-                        if (lane == 0 && q > 0) l = eb[(0 * 4 + q - 1) * UM_CHUNK + j];
-                        if (lane == 31 && q < 3) r = eb[(1 * 4 + q + 1) * UM_CHUNK + j];
-                        o[j] = (l + v[1][j]) + r;
+                    for (int j = 0; j < EC; j++) {
+                        lv[j] = __shfl_up_sync(FULL, v[0][j], 1);
+                        rv[j] = __shfl_down_sync(FULL, v[2][j], 1);
                     }
+                    if (lane == 0 && q > 0) {
+#pragma unroll
+                        for (int j = 0; j < EC / 4; j++) {
+                            const float4 e = eb[(0 * 4 + q - 1) * (UM_CHUNK / 4) + j];
+                            lv[4 * j] = e.x; lv[4 * j + 1] = e.y; lv[4 * j + 2] = e.z; lv[4 * j + 3] = e.w;
+                        }
+                    }
+                    if (lane == 31 && q < 3) {
+#pragma unroll
+                        for (int j = 0; j < EC / 4; j++) {
+                            const float4 e = eb[(1 * 4 + q + 1) * (UM_CHUNK / 4) + j];
+                            rv[4 * j] = e.x; rv[4 * j + 1] = e.y; rv[4 * j + 2] = e.z; rv[4 * j + 3] = e.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < EC; j++) o[j] = (lv[j] + v[1][j]) + rv[j];
                     par ^= 1;
                     if (valid && !(a.debug & 4)) {
                         if constexpr (!L::FINAL) {
                             float4* out4 = reinterpret_cast<float4*>(a.out);
 #pragma unroll
-                            for (int c4 = 0; c4 < UM_CHUNK / 4; c4++) {
+                            for (int c4 = 0; c4 < EC / 4; c4++) {
                                 const int co = co0 + 4 * c4;
                                 const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias + co));
                                 float4 w;
@@ -316,12 +369,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                     tc_fence_after();
                     const uint32_t sp = smem_u32(patches + (size_t)ps * L::PATCH_BYTES);
                     const uint32_t sw = smem_u32(loads + (size_t)ls * L::LOAD_BYTES);
+                    const int buf = L::NBUF == 2 ? (iter & 1) : 0;
+                    const uint32_t tpar = L::NBUF == 2 ? ((iter >> 1) & 1) : (iter & 1);
                     for (int b = 0; b < L::MB; b++) {
                         if (kc == 0) {
-                            mbar_wait(&tempty[b], (iter & 1) ^ 1);
+                            mbar_wait(&tempty[buf * L::MB + b], tpar ^ 1);
                             tc_fence_after();
                         }
-                        const uint32_t tc = tmem_base + (uint32_t)(b * L::N6);
+                        const uint32_t tc = tmem_base + (uint32_t)((buf * L::MB + b) * L::N6);
 #pragma unroll
                         for (int dy = 0; dy < 3; dy++) {
                             if (a.debug & 2) break;
@@ -339,7 +394,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                                 umma_tf32(tc + L::N3, a_lo, umma_desc(wb, LBO_B), idesc3, 1u);              // + lh
                             }
                         }
-                        if (kc == L::KCH - 1) umma_commit(&tfull[b]);
+                        if (kc == L::KCH - 1) umma_commit(&tfull[buf * L::MB + b]);
                     }
                     umma_commit(&p_empty[ps]);
                     umma_commit(&ld_empty[ls]);
@@ -360,7 +415,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                 item_src_rows<L>(lb, i_lo, nrows);
                 const uint32_t row_bytes = (uint32_t)nrows * L::WS * 16u;
                 for (int kc = 0; kc < L::KCH; kc++) {
-                    mbar_wait(&ld_empty[s], ph ^ 1);
+                    mbar_wait_backoff(&ld_empty[s], ph ^ 1, 40);
                     unsigned char* st = loads + (size_t)s * L::LOAD_BYTES;
                     const bool do_src = !(a.debug & 16), do_w = !(a.debug & 32);
                     mbar_expect_tx(&ld_full[s], (do_src ? 2 * row_bytes : 0) + (do_w ? L::W_BYTES : 0));
@@ -377,13 +432,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
         __syncwarp();
     } else {
         // =============================== producers ===============================
-        // One thread owns ONE padded column xp (both channel quads of the stage: two independent dependency chains) and a
-        // slice of the item's rows, and walks down them: the horizontally interpolated layer-input rows it needs stay in
-        // registers (each serves two output rows).  The producers are latency bound (few warps, ~6 cycles per issued
-        // instruction), so what counts is instructions per thread and independent work inside a thread.
+        // One thread owns ONE padded column xp (both channel quads of the chunk: two independent dependency chains) and
+        // a slice of RPT rows of the item.  Everything that depends only on the position (source rows, interpolation
+        // weights, patch offset) is computed once per item; per chunk a row costs, per quad, 4 packed FMAs for the vertical
+        // interpolation, 4 cvt + 2 packed subtractions for the TF32 split and 2 STS.128, plus 2 LDS.128 + 4 packed FMAs
+        // whenever the source row advances (every other output row).  The producers are latency bound (few warps), so
+        // instructions per thread and independent chains per thread are what count.
         const int ptid = tid - (UM_LOAD_WARP + 1) * 32;
         constexpr int RSPLIT_ = UM_NPT / L::PW;
         constexpr int RSPLIT = RSPLIT_ < 1 ? 1 : (RSPLIT_ > L::ROWS_OUT ? L::ROWS_OUT : RSPLIT_);
+        constexpr int RPT = (L::ROWS_OUT + RSPLIT - 1) / RSPLIT;           // rows per thread
         static_assert(L::PW <= UM_NPT, "one producer thread per padded column");
         const bool active = ptid < L::PW * RSPLIT;
         const int xp = ptid % L::PW, rs = ptid / L::PW;
@@ -405,63 +463,93 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
             item_src_rows<L>(lb, i_lo, nrows);
             const int lp_a = max(lb - L::PW, 0), lp_b = min(lb - L::PW + L::NPOS, L::FRAME_POS);     // staged flat range
             const int yp_a = lp_a / L::PW, yp_b = (lp_b - 1) / L::PW;
-            const int per = (yp_b - yp_a + RSPLIT) / RSPLIT;
-            const int r0 = yp_a + rs * per, r1 = min(r0 + per, yp_b + 1);
+            // per-row records of this thread (rows yp_a + rs*RPT ...): float4 offsets of the two source rows in the staged
+            // quad (rowA < 0: nothing to do), vertical weight, byte offset in the patch
+            int rowA[RPT], rowB[RPT];
+            uint32_t poff[RPT];
+            float w1[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+                const int yp = yp_a + rs * RPT + r;
+                const int p = yp * L::PW + xp - (lb - L::PW);
+                rowA[r] = -1; rowB[r] = 0; w1[r] = 0.f; poff[r] = 0;
+                if (active && yp <= yp_b && p >= 0 && p < L::NPOS) {
+                    const int y = min(max(yp - 1, 0), L::H - 1);
+                    if constexpr (L::UP) {
+                        const Lerp1 ly = lerp1(y, L::HS, sh);
+                        rowA[r] = (ly.i0 - i_lo) * L::WS + j0;
+                        rowB[r] = (min(ly.i0 + 1, L::HS - 1) - i_lo) * L::WS + j0;
+                        w1[r] = ly.l1;
+                    } else {
+                        rowA[r] = (y - i_lo) * L::WS + j0;
+                    }
+                    poff[r] = (uint32_t)p * 16u;
+                }
+            }
             for (int kc = 0; kc < L::KCH; kc++) {
-                mbar_wait(&ld_full[ls], lph);
-                mbar_wait(&p_empty[ps], pph ^ 1);
-                if (active && !(a.debug & 1)) {
+                mbar_wait_backoff(&ld_full[ls], lph, 40);
+                mbar_wait_backoff(&p_empty[ps], pph ^ 1, 40);
+                if (!(a.debug & 1)) {
                     const float4* src4 = reinterpret_cast<const float4*>(loads + (size_t)ls * L::LOAD_BYTES + L::W_BYTES);
                     const uint32_t dbase = smem_u32(patches + (size_t)ps * L::PATCH_BYTES);
-                    int cur = -1000;
-                    float4 hA[2], hB[2];
-                    hA[0] = hA[1] = hB[0] = hB[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int yp = r0; yp < r1; yp++) {
-                        const int y = min(max(yp - 1, 0), L::H - 1);
-                        float4 v[2];
+                    int cur = -1;
+                    float hA[2][4], hB[2][4];
+#pragma unroll
+                    for (int r = 0; r < RPT; r++) {
+                        if (rowA[r] < 0) continue;
+                        float v[2][4];
                         if constexpr (L::UP) {
-                            const Lerp1 ly = lerp1(y, L::HS, sh);
-                            if (ly.i0 != cur) {
-                                const float4* ra = src4 + (ly.i0 - i_lo) * L::WS + j0;
-                                const float4* rb = src4 + (min(ly.i0 + 1, L::HS - 1) - i_lo) * L::WS + j0;
-                                const bool shift = ly.i0 == cur + 1;
+                            if (rowA[r] != cur) {
+                                const bool shift = rowA[r] == cur + L::WS && cur >= 0;
 #pragma unroll
                                 for (int qd = 0; qd < 2; qd++) {
                                     if (shift) {
-                                        hA[qd] = hB[qd];
-                                    } else {
-                                        const float4 u0 = ra[qd * QS], u1 = ra[qd * QS + dj];
-                                        hA[qd] = make_float4(wx0 * u0.x + wx1 * u1.x, wx0 * u0.y + wx1 * u1.y,
-                                                             wx0 * u0.z + wx1 * u1.z, wx0 * u0.w + wx1 * u1.w);
-                                    }
-                                    const float4 u0 = rb[qd * QS], u1 = rb[qd * QS + dj];
-                                    hB[qd] = make_float4(wx0 * u0.x + wx1 * u1.x, wx0 * u0.y + wx1 * u1.y,
-                                                         wx0 * u0.z + wx1 * u1.z, wx0 * u0.w + wx1 * u1.w);
-                                }
-                                cur = ly.i0;
-                            }
-                            const float wy1 = ly.l1, wy0 = 1.f - wy1;
 #pragma unroll
-                            for (int qd = 0; qd < 2; qd++)
-                                v[qd] = make_float4(wy0 * hA[qd].x + wy1 * hB[qd].x, wy0 * hA[qd].y + wy1 * hB[qd].y,
-                                                    wy0 * hA[qd].z + wy1 * hB[qd].z, wy0 * hA[qd].w + wy1 * hB[qd].w);
-                        } else {
-                            v[0] = src4[(y - i_lo) * L::WS + j0];
-                            v[1] = src4[QS + (y - i_lo) * L::WS + j0];
-                        }
-                        const int p = yp * L::PW + xp - (lb - L::PW);
-                        if (p >= 0 && p < L::NPOS) {
+                                        for (int e = 0; e < 4; e++) hA[qd][e] = hB[qd][e];
+                                    } else {
+                                        const float4 u0 = src4[qd * QS + rowA[r]], u1 = src4[qd * QS + rowA[r] + dj];
+                                        fmul2(hA[qd][0], hA[qd][1], u0.x, u0.y, wx0);
+                                        fmul2(hA[qd][2], hA[qd][3], u0.z, u0.w, wx0);
+                                        ffma2(hA[qd][0], hA[qd][1], u1.x, u1.y, wx1);
+                                        ffma2(hA[qd][2], hA[qd][3], u1.z, u1.w, wx1);
+                                    }
+                                    const float4 t0 = src4[qd * QS + rowB[r]], t1 = src4[qd * QS + rowB[r] + dj];
+                                    fmul2(hB[qd][0], hB[qd][1], t0.x, t0.y, wx0);
+                                    fmul2(hB[qd][2], hB[qd][3], t0.z, t0.w, wx0);
+                                    ffma2(hB[qd][0], hB[qd][1], t1.x, t1.y, wx1);
+                                    ffma2(hB[qd][2], hB[qd][3], t1.z, t1.w, wx1);
+                                }
+                                cur = rowA[r];
+                            }
+                            const float wy1 = w1[r], wy0 = 1.f - wy1;
 #pragma unroll
                             for (int qd = 0; qd < 2; qd++) {
-                                float h0, h1, h2, h3, l0, l1, l2, l3;
-                                split_tf32(v[qd].x, h0, l0);
-                                split_tf32(v[qd].y, h1, l1);
-                                split_tf32(v[qd].z, h2, l2);
-                                split_tf32(v[qd].w, h3, l3);
-                                const uint32_t d = dbase + (uint32_t)(qd * L::NPOS + p) * 16u;
-                                st_shared_v4(d, h0, h1, h2, h3);
-                                st_shared_v4(d + 2 * L::NPOS * 16, l0, l1, l2, l3);
+                                fmul2(v[qd][0], v[qd][1], hA[qd][0], hA[qd][1], wy0);
+                                fmul2(v[qd][2], v[qd][3], hA[qd][2], hA[qd][3], wy0);
+                                ffma2(v[qd][0], v[qd][1], hB[qd][0], hB[qd][1], wy1);
+                                ffma2(v[qd][2], v[qd][3], hB[qd][2], hB[qd][3], wy1);
                             }
+                        } else {
+#pragma unroll
+                            for (int qd = 0; qd < 2; qd++) {
+                                const float4 u = src4[qd * QS + rowA[r]];
+                                v[qd][0] = u.x; v[qd][1] = u.y; v[qd][2] = u.z; v[qd][3] = u.w;
+                            }
+                        }
+#pragma unroll
+                        for (int qd = 0; qd < 2; qd++) {
+                            float h[4], l[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                uint32_t u;
+                                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[qd][e]));
+                                h[e] = __uint_as_float(u);
+                            }
+                            fsub2(l[0], l[1], v[qd][0], v[qd][1], h[0], h[1]);
+                            fsub2(l[2], l[3], v[qd][2], v[qd][3], h[2], h[3]);
+                            const uint32_t d = dbase + (uint32_t)(qd * L::NPOS) * 16u + poff[r];
+                            st_shared_v4(d, h[0], h[1], h[2], h[3]);
+                            st_shared_v4(d + 2 * L::NPOS * 16, l[0], l[1], l[2], l[3]);
                         }
                     }
                 }
@@ -504,11 +592,11 @@ __global__ void umma_wimg_kernel(const float* __restrict__ w, float* __restrict_
     }
 }
 
-//                      CIN COUT real  H    W   UP    MB  LS  FINAL
-using UL0 = UmmaLayer<128, 64, 64, 16, 32, true, 1, 4, false>;
-using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 6, false>;
-using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 5, false>;
-using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 3, true>;
+//                      CIN COUT real  H    W   UP    MB NBUF PS LS FINAL
+using UL0 = UmmaLayer<128, 64, 64, 16, 32, true, 1, 1, 3, 4, false>;
+using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 1, 3, 5, false>;
+using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 1, 3, 3, false>;
+using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 1, 2, 3, true>;
 static_assert(UL0::SMEM <= 227 * 1024 && UL1::SMEM <= 227 * 1024 && UL2::SMEM <= 227 * 1024 && UL3::SMEM <= 227 * 1024, "smem");
 
 template <class L>

@@ -37,6 +37,10 @@ int         trpx_probe_fp32_fma(int device, float* tflops_out);
 /* Measured dense TF32 throughput of the warp-level mma.sync.m16n8k8 path (SASS HMMA.1688.F32.TF32) in TFLOP/s:
  * the denominator (divided by 3 for the error-compensated 3xTF32 product) of the tensor-core rollout kernel. */
 int         trpx_probe_tf32_mma(int device, float* tflops_out);
+/* Dense TF32 rate of the 5th-generation tensor cores (tcgen05.mma kind::tf32, M128 x N256 x K8 from shared memory,
+ * accumulators in TMEM) in TFLOP/s: the denominator of the Cylinder decoder's roofline (its error-compensated 3xTF32
+ * product runs at a third of it). */
+int         trpx_probe_umma_tf32(int device, float* tflops_out);
 /* Measured rate (GB/s) of the KV-window access pattern of the cache-mode rollout with the arithmetic removed:
  * 4 trajectories per warp, per (step, layer) two windows of n_ctx rows of 128 B read with 256-bit loads
  * (`rows_in_flight` per lane: 4, 8 or 16) plus two rows appended; `prefetch` adds the bulk L2 prefetch the rollout
@@ -193,10 +197,11 @@ int trpx_cyl_destroy(trpx_cyl_t h);
 int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w_dev, int n_tensors, void* stream);
 /* Frames per encoder/decoder pass (default 64): intermediates of one pass stay L2-resident. */
 int trpx_cyl_set_chunk(trpx_cyl_t h, int frames);
-/* Decoder conv path of the three heavy upsample+conv layers: 2 = pipelined 3xTF32 tensor-core path (default):
- * one upsample/pad/TF32-split pass into an L2-resident scratch, then a cp.async double-buffered mma.sync
- * implicit GEMM with per-chunk FP32 accumulation; 1 = FP32 SIMT direct convolution; 0 = 3xTF32 MMA with
- * in-kernel patch build (kept for A/B: same speed as 1, larger rounding error).  See profiles/README.md. */
+/* Decoder conv path (embedding_cylinder.py:70-88): 3 = tcgen05 (UMMA) TF32 implicit GEMMs with TMA-staged layer
+ * input and weights, the bilinear upsample + TF32 hi/lo split fused into the kernel's producer warps, accumulators in
+ * TMEM (default, csrc/cyl_umma.cu); 2 = pipelined 3xTF32 mma.sync path (separate upsample/pad/split pass, cp.async
+ * double-buffered MMA kernel); 1 = FP32 SIMT direct convolution; 0 = 3xTF32 mma.sync with in-kernel patch build.
+ * 0-2 are kept for A/B measurements (profiles/README.md). */
 int trpx_cyl_set_conv_mode(trpx_cyl_t h, int mode);
 /* CylinderEmbedding.embed (:138-154): x[N,3,64,128], visc[N] -> g[N,128] */
 int trpx_cyl_embed(trpx_cyl_t h, const float* x_dev, const float* visc_dev, float* g_dev, int N, void* stream);

@@ -631,7 +631,71 @@ int launch_umma(const UmmaArgs& base, int sm_count, cudaStream_t st) {
     return TRPX_OK;
 }
 
+// tcgen05 TF32 peak probe: every SM issues M128 x N256 x K8 MMAs (the math-bound shape) back to back from shared memory
+__global__ void __launch_bounds__(128) umma_tf32_probe_kernel(int iters) {
+    extern __shared__ __align__(128) unsigned char um_smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float* z = reinterpret_cast<float*>(um_smem);
+    for (int i = tid; i < (64 * 1024 + 32 * 1024) / 4; i += 128) z[i] = 0.f;
+    if (warp == 0) tmem_alloc(&slot, 512);
+    if (tid == 0) mbar_init(&bar, 1);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if (tid == 0) {
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 256);
+        const uint32_t a0 = smem_u32(um_smem), b0 = a0 + 64 * 1024;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                umma_tf32(tmem + (uint32_t)((j & 1) * 256), umma_desc(a0 + j * 4096, 2048), umma_desc(b0 + (j & 3) * 8192, 4096), idesc, 1u);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
+
+extern "C" int trpx_probe_umma_tf32(int device, float* tflops_out) {
+    TRPX_REQUIRE(tflops_out != nullptr, "null output");
+    int n = 0;
+    TRPX_CUDA(cudaGetDeviceCount(&n));
+    TRPX_REQUIRE(device >= 0 && device < n, "device %d out of range", device);
+    DeviceGuard guard(device);
+    int sms = 0;
+    TRPX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int smem = 96 * 1024 + 128;
+    TRPX_CUDA(cudaFuncSetAttribute(umma_tf32_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaEvent_t e0, e1;
+    TRPX_CUDA(cudaEventCreate(&e0));
+    TRPX_CUDA(cudaEventCreate(&e1));
+    const int iters = 2000;
+    umma_tf32_probe_kernel<<<sms, 128, smem>>>(20);
+    float best = 0.f;
+    for (int rep = 0; rep < 3; rep++) {
+        TRPX_CUDA(cudaEventRecord(e0));
+        umma_tf32_probe_kernel<<<sms, 128, smem>>>(iters);
+        TRPX_CUDA(cudaEventRecord(e1));
+        TRPX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        TRPX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 128 * 256 * 8 * 16.0 * (double)iters * (double)sms;
+        best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    TRPX_CUDA(cudaGetLastError());
+    *tflops_out = best;
+    return TRPX_OK;
+}
 
 namespace trpx {
 

@@ -37,9 +37,11 @@ def embed_series(embedding_model, series: Tensor, *extra) -> Tensor:
 
 @torch.no_grad()
 def rollout_to_host(embedding_model, transformer, x0_host: Tensor, max_length: int, states_host: Tensor,
-                    device=None, use_cache: bool = True, chunks: int = 4, copy_stream=None) -> Tensor:
+                    device=None, use_cache: bool = True, chunks: int = 4, copy_stream=None,
+                    visc_host: Tensor = None) -> Tensor:
     """The evaluation pipeline of `Trainer.eval_states` around `generate()` with HOST buffers:
-    x0_host [B, *state_dims] (pinned) -> device -> embed -> generate(max_length) -> recover -> states_host
+    x0_host [B, *state_dims] (pinned; plus visc_host [B, 1] for the Cylinder embedding) -> device -> embed ->
+    generate(max_length) -> recover -> states_host
     [B, max_length, *state_dims] (pinned).  The decoder runs in `chunks` slices of trajectories and each slice's states
     are copied to the host on `copy_stream` while the next slice decodes, so only the last copy is exposed.  Returns
     `states_host` once the current stream has been made to wait for the copies (call torch.cuda.synchronize() or
@@ -51,7 +53,10 @@ def rollout_to_host(embedding_model, transformer, x0_host: Tensor, max_length: i
     if copy_stream is None:
         copy_stream = torch.cuda.Stream(device=dev)
     x = x0_host.to(dev, non_blocking=True)
-    g0 = embedding_model.embed(x)
+    if visc_host is not None:           # Cylinder: embed(x, visc) (embedding_cylinder.py:138)
+        g0 = embedding_model.embed(x, visc_host.to(dev, non_blocking=True))
+    else:
+        g0 = embedding_model.embed(x)
     out = transformer.generate(g0.unsqueeze(1), max_length=max_length, use_cache=use_cache, return_presents=False)[0]
     chunks = max(1, min(chunks, B))
     for i in range(chunks):

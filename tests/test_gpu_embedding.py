@@ -322,3 +322,35 @@ def test_cylinder_end_to_end_config4(dev, B, S, auto_variant):
     print(f"cylinder end-to-end B={B}: recovered fields rel-L2 {ferr:.2e} over {B * len(steps)} frames")
     assert ferr < TOL
     assert int((fields[:, steps][:, :, 0] == 0).sum()) >= 196 * B * len(steps)      # cylinder cells are masked
+
+
+def test_feature_cache_blocks_and_round_trip(dev, tmp_path):
+    """data_utils.build_feature_cache (PhysicalDataset's constructor logic, dataset_phys.py:53-86 + LorenzDataset /
+    CylinderDataset.embed_data): blocks of the bulk-embedded series equal the oracle's embedding of the same windows,
+    eval=True keeps the states, ndata stops early, the second call is served from the pickle."""
+    from trphysx_b200.data_utils import build_feature_cache, cached_features_file
+    cfg = synth.make_config("lorenz")
+    emb = make_lorenz(cfg, 812, "lorenz", dev)
+    sd = O.to_torch(synth.lorenz_embedding_weights(cfg, 812))
+    series = {str(k): synth.lorenz_trajectories(1, 40, seed=60 + k)[0] for k in range(3)}      # three [41, 3] series
+    data = tmp_path / "lorenz.hdf5"
+    data.write_bytes(b"")
+    ex, st = build_feature_cache(emb, str(data), series, block_size=16, stride=8, ndata=2, eval=True)
+    assert len(ex) == 2 * 4 and len(st) == len(ex)                    # (41 - 16)//8 + 1 = 4 blocks per series, 2 series
+    assert ex[0].device.type == "cpu" and ex[0].shape == (16, 32) and st[0].shape == (16, 3)
+    s1 = torch.from_numpy(series["1"])
+    assert torch.equal(st[5], s1[8:24])
+    assert O.rel_l2(ex[5], O.lorenz_embed(sd, cfg, s1[8:24])) < TOL
+    assert os.path.isfile(cached_features_file(str(data), emb, 16, ndata=2))
+    ex2, st2 = build_feature_cache(emb, str(data), None, block_size=16, stride=8, ndata=2, eval=True)   # from the cache
+    assert all(torch.equal(a, b) for a, b in zip(ex, ex2)) and all(torch.equal(a, b) for a, b in zip(st, st2))
+    # Cylinder series carry their viscosity (2 / Re, dataset_cylinder.py:36)
+    ccfg = synth.make_config("cylinder")
+    cemb = make_cylinder(ccfg, 55, dev)
+    csd = O.to_torch(synth.cylinder_embedding_weights(ccfg, 55))
+    x, _ = synth.cylinder_fields(6, seed=9)
+    cex, _ = build_feature_cache(cemb, str(tmp_path / "cyl.hdf5"), {"400": x}, block_size=4, stride=2,
+                                 visc_of_key=lambda k: 2.0 / float(k))
+    assert len(cex) == 2 and cex[0].shape == (4, 128)
+    ref = O.cylinder_embed(csd, ccfg, torch.from_numpy(x), torch.full((6, 1), 2.0 / 400.0))
+    assert O.rel_l2(torch.cat([cex[0], cex[1][2:]]), ref) < TOL

@@ -192,3 +192,43 @@ def test_native_handles_are_not_copyable_state():
             assert m._handles[0][1].key is None
     finally:
         N.HandleCache._destroy_all = real
+
+
+def test_feature_cache_format_matches_reference(tmp_path):
+    """the pickle feature cache of trphysx/data_utils/dataset_phys.py:60-65,88-111 — same file name, same
+    (examples, states) tuple of CPU tensors; a cache written here is read back by the reference's own read_cache (when
+    the reference is importable) and one written with the reference's recipe is read here."""
+    import pickle
+    from trphysx_b200.data_utils import cached_features_file, read_cache, write_cache
+    emb = LorenzEmbedding(LorenzConfig())
+    data = tmp_path / "lorenz_valid.hdf5"
+    data.write_bytes(b"")
+    name = cached_features_file(str(data), emb, 64, ndata=8)
+    assert name == str(tmp_path / "cached8_LorenzEmbedding_64_lorenz_valid.hdf5")
+    assert cached_features_file(str(data), emb, 64, cache_path=str(tmp_path / "missing")) == \
+        str(tmp_path / "cached-1_LorenzEmbedding_64_lorenz_valid.hdf5")
+    examples = [torch.randn(64, 32) for _ in range(3)]
+    states = [torch.randn(64, 3) for _ in range(3)]
+    write_cache(name, examples, states)
+    with open(name, "rb") as f:                                   # exactly what dataset_phys.py:97 unpickles
+        ex2, st2 = pickle.load(f)
+    assert isinstance(ex2, list) and all(torch.equal(a, b) for a, b in zip(ex2, examples))
+    assert all(torch.equal(a, b) for a, b in zip(st2, states))
+    ref_style = tmp_path / "ref_cache"
+    with open(ref_style, "wb") as f:                              # dataset_phys.py:107-108
+        pickle.dump((examples, []), f, protocol=pickle.HIGHEST_PROTOCOL)
+    ex3, st3 = read_cache(str(ref_style))
+    assert len(ex3) == 3 and st3 == [] and torch.equal(ex3[1], examples[1])
+    if ref_shim.available():
+        ref_shim.load()
+        from trphysx.data_utils.dataset_phys import PhysicalDataset
+
+        class _Probe(PhysicalDataset):                            # read_cache without the HDF5 constructor
+            def __init__(self):
+                pass
+
+            def embed_data(self, *a, **k):
+                pass
+        p = _Probe()
+        p.read_cache(name)
+        assert torch.equal(p.examples[2], examples[2]) and torch.equal(p.states[0], states[0])

@@ -8,7 +8,7 @@ All compute runs in libtrpx.so (hand-written sm_100a CUDA, include/trpx.h); ther
 """
 __version__ = "0.1.0"
 
-from . import config, embedding, transformer  # noqa: F401
+from . import config, data_utils, embedding, transformer  # noqa: F401
 from .config import AutoPhysConfig, PhysConfig  # noqa: F401
 from .embedding import AutoEmbeddingModel  # noqa: F401
 from .transformer import AutoPhysTransformer, PhysformerGPT2, PhysformerTrain  # noqa: F401

@@ -213,6 +213,18 @@ int trpx_cyl_recover(trpx_cyl_t h, const float* g_dev, float* x_dev, int N, int 
 int trpx_cyl_koopman(trpx_cyl_t h, const float* g_dev, const float* visc_dev, float* gnext_dev,
                      float* kdiag_dev, float* kmat_dev, int N, void* stream);
 
+/* CylinderEmbeddingTrainer.forward + backward (embedding_cylinder.py:236-281; the step body of
+ * embedding/training/enn_trainer.py:93-96) in one call:
+ *   states_dev [B,T,3,64,128], visc_dev [B];  w_rec 1e1, w_dyn 1e1, w_reg 1e-2 in the reference
+ *   loss2_dev[2] = {loss, loss_reconstruct};  grad_dev = flat gradient [trpx_cyl_num_params = 262,535] in
+ *   nn.Module.parameters() order: observableNet.{0,2,4,6,8}.{weight,bias}, observableNetFC.0.{weight,bias},
+ *   recoveryNet.{1,4,7,10,12}.{weight,bias}, kMatrixDiagNet / kMatrixUT / kMatrixLT .{0.weight,0.bias,2.weight,2.bias}.
+ *   `grad_scale` multiplies the gradient (1/world_size before a SUM all-reduce).  Deterministic (no atomics). */
+int trpx_cyl_train_fwd_bwd(trpx_cyl_t h, const float* states_dev, const float* visc_dev, int B, int T,
+                           float w_rec, float w_dyn, float w_reg, float grad_scale,
+                           float* loss2_dev, float* grad_dev, void* stream);
+long long trpx_cyl_num_params(trpx_cyl_t h);
+
 #ifdef __cplusplus
 }
 #endif

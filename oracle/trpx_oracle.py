@@ -23,7 +23,7 @@ Reference lines restated (relative to /root/reference):
   gpt2_generate       trphysx/transformer/generate_utils.py:25-56, 66-110, 112-169
   lorenz_*            trphysx/embedding/embedding_lorenz.py:74-167 (Rossler: examples/rossler/
                       rossler_module/embedding_rossler.py:71-161, identical arithmetic)
-  cylinder_*          trphysx/embedding/embedding_cylinder.py:112-222
+  cylinder_*          trphysx/embedding/embedding_cylinder.py:112-222 (training loss :236-281)
   lorenz_train_loss   trphysx/embedding/embedding_lorenz.py:181-221 (weights: Rossler :195-215)
   clip_adam_step      trphysx/embedding/training/enn_trainer.py:93-102 + torch.optim.Adam semantics
 """
@@ -332,6 +332,48 @@ def cylinder_koopman_matrix(sd: SD, cfg, visc: Tensor) -> Tuple[Tensor, Tensor]:
 def cylinder_koopman(sd: SD, cfg, g: Tensor, visc: Tensor) -> Tensor:
     K, _ = cylinder_koopman_matrix(sd, cfg, visc)
     return torch.bmm(K, g.unsqueeze(-1)).squeeze(-1)
+
+
+CYL_PARAM_ORDER = ([f"observableNet.{i}.{k}" for i in (0, 2, 4, 6, 8) for k in ("weight", "bias")] +
+                   ["observableNetFC.0.weight", "observableNetFC.0.bias"] +
+                   [f"recoveryNet.{i}.{k}" for i in (1, 4, 7, 10, 12) for k in ("weight", "bias")] +
+                   [f"{net}.{i}.{k}" for net in ("kMatrixDiagNet", "kMatrixUT", "kMatrixLT") for i in (0, 2)
+                    for k in ("weight", "bias")])                                  # nn.Module.parameters() order
+
+
+def cylinder_train_loss(sd: SD, cfg, states: Tensor, visc: Tensor, w_rec: float = 1e1, w_dyn: float = 1e1,
+                        w_reg: float = 1e-2) -> Tuple[Tensor, Tensor]:
+    """CylinderEmbeddingTrainer.forward (embedding_cylinder.py:236-281).  states [B,T,3,64,128], visc [B,1].
+    The per-step reconstruction comes from forward() (decoder WITHOUT the cylinder mask, fact 8), the Koopman
+    prediction is decoded by recover() (WITH it); the regulariser sums K^2 over the per-sample operators."""
+    mse = F.mse_loss
+    x0 = states[:, 0]
+    g0 = cylinder_embed(sd, cfg, x0, visc)
+    xr0 = cylinder_recover(sd, cfg, g0, apply_mask=False)
+    loss = w_rec * mse(x0, xr0)
+    loss_rec = mse(x0, xr0).detach()
+    g_old = g0
+    for t in range(1, states.shape[1]):
+        xt = states[:, t]
+        xr = cylinder_recover(sd, cfg, cylinder_embed(sd, cfg, xt, visc), apply_mask=False)
+        K, _ = cylinder_koopman_matrix(sd, cfg, visc)
+        g_pred = torch.bmm(K, g_old.unsqueeze(-1)).squeeze(-1)
+        xg = cylinder_recover(sd, cfg, g_pred, apply_mask=True)
+        loss = loss + w_dyn * mse(xg, xt) + w_rec * mse(xr, xt) + w_reg * torch.sum(K ** 2)
+        loss_rec = loss_rec + mse(xr, xt).detach()
+        g_old = g_pred
+    return loss, loss_rec
+
+
+def cylinder_train_grads(sd: SD, cfg, states: Tensor, visc: Tensor, **kw):
+    """loss, loss_reconstruct and the flat gradient in nn.Module.parameters() order."""
+    params = {k: sd[k].clone().requires_grad_(True) for k in CYL_PARAM_ORDER}
+    full = dict(sd)
+    full.update(params)
+    loss, loss_rec = cylinder_train_loss(full, cfg, states, visc, **kw)
+    grads = torch.autograd.grad(loss, [params[k] for k in CYL_PARAM_ORDER], allow_unused=True)   # T = 1: no Koopman step
+    grads = [g if g is not None else torch.zeros_like(params[k]) for g, k in zip(grads, CYL_PARAM_ORDER)]
+    return loss.detach(), loss_rec, torch.cat([g.reshape(-1) for g in grads])
 
 
 # ==================================================================================================

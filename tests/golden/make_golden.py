@@ -174,10 +174,14 @@ def cyl_train_cases(trphysx):
         x, visc = synth.cylinder_fields(B * T, seed=c["seed"])
         states = torch.from_numpy(x).view(B, T, 3, 64, 128)
         visc = torch.from_numpy(visc).view(B, T, 1)[:, 0]
-        with torch.no_grad():
-            loss, loss_rec = head(states, visc)
-        np.savez_compressed(os.path.join(OUT, f"cyltrain_{name}.npz"), loss=loss.numpy(), loss_rec=loss_rec.numpy())
-        print("cyltrain", name, float(loss), float(loss_rec))
+        loss, loss_rec = head(states, visc)                   # the step body of enn_trainer.py:93-96
+        loss = loss.sum()
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in head.parameters()])
+        norm = torch.nn.utils.clip_grad_norm_(head.parameters(), 0.1)
+        np.savez_compressed(os.path.join(OUT, f"cyltrain_{name}.npz"), loss=loss.detach().numpy(), loss_rec=loss_rec.numpy(),
+                            grad=flat.numpy(), norm=norm.numpy())
+        print("cyltrain", name, float(loss), float(loss_rec), flat.shape, float(norm))
 
 
 if __name__ == "__main__":

@@ -217,27 +217,94 @@ def test_eval_states_fused_recover_mse(dev, kind):
     assert O.rel_l2(ge.cpu().view(-1, cfg.n_embd), O.lorenz_embed(O.to_torch(w), cfg, series.view(-1, 3))) < TOL
 
 
-@pytest.mark.parametrize("name", list(CYL_TRAIN_CASES))
-def test_cylinder_training_loss_value(golden_dir, dev, name):
-    """CylinderEmbeddingTrainer.forward under no_grad: the reference's recorded (loss, loss_reconstruct)
-    (embedding_cylinder.py:236-281); with gradients enabled it refuses (conv backward is a next row)."""
+def _cyl_head(cfg, seed, dev):
     from trphysx_b200.embedding.embedding_cylinder import CylinderEmbeddingTrainer
+    head = CylinderEmbeddingTrainer(cfg)
+    head.embedding_model.load_state_dict(torch_sd(synth.cylinder_embedding_weights(cfg, seed)))
+    return head.to(dev)
+
+
+@pytest.mark.parametrize("name", list(CYL_TRAIN_CASES))
+def test_cylinder_training_step_matches_reference(golden_dir, dev, name):
+    """CylinderEmbeddingTrainer.forward + loss.backward() (embedding_cylinder.py:236-281, enn_trainer.py:93-96) against
+    the reference's recorded loss, loss_reconstruct, flat gradient (all 262,535 entries, parameters() order) and
+    clip_grad_norm_ value; the loss VALUE under no_grad (inference kernels) must agree with the fused step."""
     c = CYL_TRAIN_CASES[name]
     gold = np.load(os.path.join(golden_dir, f"cyltrain_{name}.npz"))
     cfg = synth.make_config("cylinder")
-    head = CylinderEmbeddingTrainer(cfg)
-    head.embedding_model.load_state_dict(torch_sd(synth.cylinder_embedding_weights(cfg, c["seed"])))
-    head.to(dev)
+    head = _cyl_head(cfg, c["seed"], dev)
     B, T = c["B"], c["T"]
     x, visc = synth.cylinder_fields(B * T, seed=c["seed"])
     states = torch.from_numpy(x).view(B, T, 3, 64, 128).to(dev)
     visc = torch.from_numpy(visc).view(B, T, 1)[:, 0].to(dev)
     with torch.no_grad():
-        loss, loss_rec = head(states, visc)
+        loss_v, loss_rec_v = head(states, visc)
+    assert abs(float(loss_v) - float(gold["loss"])) <= 1e-5 * float(gold["loss"])
+    assert abs(float(loss_rec_v) - float(gold["loss_rec"])) <= 1e-5 * float(gold["loss_rec"])
+    loss, loss_rec = head(states, visc)
+    assert not loss_rec.requires_grad
+    loss.backward()
     assert abs(float(loss) - float(gold["loss"])) <= 1e-5 * float(gold["loss"])
     assert abs(float(loss_rec) - float(gold["loss_rec"])) <= 1e-5 * float(gold["loss_rec"])
-    with pytest.raises(NotImplementedError):
-        head(states, visc)
+    flat = torch.cat([p.grad.reshape(-1) for p in head.parameters()]).cpu()
+    err = O.rel_l2(flat, gold["grad"])
+    off, worst = 0, (0.0, "")
+    for k, p in head.embedding_model.named_parameters():       # every tensor on its own: small ones must not hide
+        n = p.numel()
+        e = O.rel_l2(flat[off:off + n], gold["grad"][off:off + n])
+        worst = max(worst, (e, k))
+        off += n
+    print(f"cylinder training step: loss {float(loss):.5f}, flat gradient rel-L2 {err:.2e}, worst tensor {worst[1]} {worst[0]:.2e}")
+    assert err < TOL and worst[0] < 3 * TOL, worst
+    norm = torch.nn.utils.clip_grad_norm_(head.parameters(), 0.1)
+    assert abs(float(norm) - float(gold["norm"])) <= 1e-5 * float(gold["norm"])
+
+
+@pytest.mark.parametrize("B,T", [(3, 2), (5, 2), (2, 1)])
+def test_cylinder_training_step_vs_oracle_and_descent(dev, B, T):
+    """Sizes without a fixture against the oracle's autograd, determinism (two calls give the same bits), and the loss goes
+    down under plain SGD through the same handle.  The yardstick is the oracle in FLOAT64: for some shapes (B=3, T=2) the
+    FP32 CPU backward of the reference is itself 1e-4..3e-4 away from it per tensor (oneDNN picks a less accurate
+    algorithm), so each tensor is allowed max(1e-5, 4x the FP32 reference's own deviation), as in the transformer
+    training-step test."""
+    cfg = synth.make_config("cylinder")
+    head = _cyl_head(cfg, 612, dev)
+    w_np = synth.cylinder_embedding_weights(cfg, 612)
+    sd = O.to_torch(w_np)
+    x, visc = synth.cylinder_fields(B * T, seed=77)
+    states_c = torch.from_numpy(x).view(B, T, 3, 64, 128)
+    visc_c = torch.from_numpy(visc).view(B, T, 1)[:, 0]
+    ref_loss, ref_rec, ref_grad32 = O.cylinder_train_grads(sd, cfg, states_c, visc_c)
+    _, _, ref_grad = O.cylinder_train_grads(O.to_torch(w_np, torch.float64), cfg, states_c.double(), visc_c.double())
+    states, visc = states_c.to(dev), visc_c.to(dev)
+    losses, first = [], None
+    for it in range(3):
+        head.zero_grad(set_to_none=True)
+        loss, rec = head(states, visc)
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in head.parameters()])
+        if it == 0:
+            assert abs(float(loss) - float(ref_loss)) <= 1e-5 * float(ref_loss)
+            assert abs(float(rec) - float(ref_rec)) <= 1e-5 * float(ref_rec)
+            off, fc = 0, flat.cpu().double()
+            for k, p in head.embedding_model.named_parameters():
+                n = p.numel()
+                if float(ref_grad[off:off + n].norm()) > 0:
+                    noise = O.rel_l2(ref_grad32[off:off + n].double(), ref_grad[off:off + n])
+                    e = O.rel_l2(fc[off:off + n], ref_grad[off:off + n])
+                    assert e < max(TOL, 4 * noise), (k, e, noise)
+                else:
+                    assert float(fc[off:off + n].abs().max()) == 0.0, k
+                off += n
+            head.zero_grad(set_to_none=True)
+            loss2, _ = head(states, visc)
+            loss2.backward()
+            assert torch.equal(flat, torch.cat([p.grad.reshape(-1) for p in head.parameters()])) and float(loss2) == float(loss)
+        losses.append(float(loss))
+        with torch.no_grad():
+            for p in head.parameters():
+                p.add_(p.grad, alpha=-2e-3)
+    assert losses[2] < losses[1] < losses[0], losses
 
 
 @pytest.mark.parametrize("kind,n", [("lorenz", 16384), ("rossler", 50001)])

@@ -8,7 +8,8 @@ import torch
 
 from tests import synth
 from oracle import trpx_oracle as O
-from tests.golden.cases import weights_kw, GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES
+from tests.golden.cases import (weights_kw, GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES,
+                                CYL_TRAIN_CASES)
 
 TOL = 2e-6          # both sides are torch-CPU fp32 executing the same aten ops; only threading differs
 
@@ -148,3 +149,21 @@ def test_gpt2_train_step_oracle(golden_dir, name):
         assert sorted(keys) == sorted(grads)              # same set of tensors receives a gradient
     for k in keys:
         assert O.rel_l2(grads[k], gold["grad." + k]) < 5 * TOL, k
+
+
+@pytest.mark.parametrize("name", list(CYL_TRAIN_CASES))
+def test_cylinder_train_step_oracle(golden_dir, name):
+    """Cylinder Koopman training loss and flat gradient against the reference's recorded backward()."""
+    c = CYL_TRAIN_CASES[name]
+    gold = _load(golden_dir, f"cyltrain_{name}.npz")
+    cfg = synth.make_config("cylinder")
+    sd = O.to_torch(synth.cylinder_embedding_weights(cfg, c["seed"]))
+    B, T = c["B"], c["T"]
+    x, visc = synth.cylinder_fields(B * T, seed=c["seed"])
+    states = torch.from_numpy(x).view(B, T, 3, 64, 128)
+    visc = torch.from_numpy(visc).view(B, T, 1)[:, 0]
+    loss, loss_rec, grad = O.cylinder_train_grads(sd, cfg, states, visc)
+    assert abs(float(loss) - float(gold["loss"])) <= 2e-6 * float(gold["loss"])
+    assert abs(float(loss_rec) - float(gold["loss_rec"])) <= 2e-6 * float(gold["loss_rec"])
+    assert grad.numel() == gold["grad"].size == 262535
+    assert O.rel_l2(grad, gold["grad"]) < 5e-6

@@ -2,52 +2,15 @@
 // Reference: trphysx/embedding/embedding_cylinder.py:42-67 (encoder), :70-88 (decoder), :138-170
 // (embed / recover), :172-196 (koopmanOperation).  All convs are 3x3 cross-correlations with
 // padding=1, padding_mode='replicate'; upsampling is bilinear x2 with align_corners=True.
-#include "common.cuh"
-#include "cyl_umma.cuh"
+#include "cyl.cuh"
 #include <cmath>
 #include <vector>
 #include <algorithm>
 
 using namespace trpx;
 
-namespace {
-constexpr int CYL_H = 64, CYL_W = 128;
-constexpr int NBAND = 4;
-}  // namespace
-
-struct trpx_cyl {
-    uint32_t magic = 0x63796c31u;
-    int E = 128;
-    float eps = 1e-5f;
-    int device = 0;
-    int sm_count = 0;
-    bool loaded = false;
-    float* blob = nullptr;               // all 36 tensors back to back
-    size_t off[36] = {0};
-    size_t total = 0;
-    unsigned char* mask = nullptr;       // [64][128] cylinder mask
-    float* ws = nullptr;                 // activation workspace for one chunk of frames
-    size_t ws_bytes = 0;
-    int chunk = 64;                      // frames per decoder/encoder pass (intermediates stay in L2)
-    int conv_mode = 3;                   // 3 = tcgen05 (UMMA) implicit GEMM, patch built in-kernel (default, csrc/cyl_umma.cu);
-                                         // 2 = pipelined 3xTF32 mma.sync (upsample/split pass + cp.async double-buffered MMA
-                                         // kernel), 1 = FP32 SIMT direct conv, 0 = 3xTF32 mma.sync with in-kernel patch build
-    int final_mma = 0;                   // route the last 16->3 conv through the pipeline as well (slower, kept for A/B)
-    bool chunk_user = false;
-    float* wimg = nullptr;               // pre-split weight images of the three heavy decoder layers (mode 2)
-    size_t wimg_off[4] = {0, 0, 0, 0};
-    float* U = nullptr;                  // upsampled / padded / split layer input for one chunk (mode 2)
-    size_t U_bytes = 0;
-    float* uimg = nullptr;               // weight images of the four UMMA layers (mode 3)
-    size_t uimg_off[UMMA_LAYERS + 1] = {0};
-};
-
-namespace {
-
-bool valid(trpx_cyl_t h) { return h != nullptr && h->magic == 0x63796c31u; }
-
-// tensor sizes, in the order documented in include/trpx.h
-void tensor_sizes(int E, size_t (&n)[36]) {
+namespace trpx {
+void cyl_tensor_sizes(int E, size_t (&n)[36]) {
     const int c4 = E / 32;
     const int nband = (E - 1) + (E - 2) + (E - 3) + (E - 4);
     size_t s[36] = {4, 4,
@@ -59,24 +22,12 @@ void tensor_sizes(int E, size_t (&n)[36]) {
                     50, 50, (size_t)nband * 50, (size_t)nband};
     for (int i = 0; i < 36; i++) n[i] = s[i];
 }
+}  // namespace trpx
 
-enum { T_MU = 0, T_STD = 1, T_ENC = 2, T_LNW = 12, T_LNB = 13, T_DEC = 14, T_KD = 24, T_KU = 28, T_KL = 32 };
+namespace {
 
-// ---- bilinear x2 (align_corners=True) source index / weight, as aten's area_pixel_compute_* ------------
-struct Lerp {
-    int i0, i1;
-    float l0, l1;
-};
-__device__ __forceinline__ Lerp lerp_idx(int dst, int in_size, float scale) {
-    // real = scale * dst ; i0 = min(int(real), in-1) ; l1 = clamp(real - i0, 0, 1) ; i1 = i0 + (i0 < in-1)
-    const float real = scale * (float)dst;
-    Lerp r;
-    r.i0 = min((int)real, in_size - 1);
-    r.l1 = fminf(fmaxf(real - (float)r.i0, 0.f), 1.f);
-    r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
-    r.l0 = 1.f - r.l1;
-    return r;
-}
+bool valid(trpx_cyl_t h) { return cyl_valid(h); }
+void tensor_sizes(int E, size_t (&n)[36]) { cyl_tensor_sizes(E, n); }
 
 // ---- encoder input: cat(x, visc) then (x - mu) / std  (embedding_cylinder.py:149-150, 198-200) ----------
 __global__ void cyl_prep_kernel(const float* __restrict__ x, const float* __restrict__ visc, const float* __restrict__ mu,
@@ -870,6 +821,7 @@ int trpx_cyl_destroy(trpx_cyl_t h) {
     cudaFree(h->wimg);
     cudaFree(h->U);
     cudaFree(h->uimg);
+    cudaFree(h->tws);
     h->magic = 0;
     delete h;
     return TRPX_OK;

@@ -67,6 +67,9 @@ SIGNATURES = {
     "trpx_cyl_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "trpx_cyl_recover": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trpx_cyl_koopman": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "trpx_cyl_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
+                                       c_void_p, c_void_p, c_void_p]),
+    "trpx_cyl_num_params": (c_longlong, [c_void_p]),
 }
 
 _lib = None

@@ -176,10 +176,43 @@ class CylinderEmbedding(EmbeddingModel):
         return self.kMatrixDiag
 
 
+class _FusedCylinderKoopmanLoss(torch.autograd.Function):
+    """loss, loss_reconstruct = f(states, visc; params): forward AND backward run in one native call
+    (csrc/cyl_train.cu); backward() only hands the stored flat gradient (nn.Module.parameters() order) to autograd."""
+
+    @staticmethod
+    def forward(ctx, model, states, visc, w_rec, w_dyn, w_reg, *params):
+        lib = N.lib()
+        dev = states.device
+        h = model._handle(dev)
+        B, T = states.size(0), states.size(1)
+        nparam = int(lib.trpx_cyl_num_params(h))
+        loss2 = torch.empty(2, device=dev, dtype=torch.float32)
+        flat = torch.empty(nparam, device=dev, dtype=torch.float32)
+        N.check(lib.trpx_cyl_train_fwd_bwd(h, states.data_ptr(), visc.data_ptr(), B, T, w_rec, w_dyn, w_reg, 1.0,
+                                           loss2.data_ptr(), flat.data_ptr(), N.stream_ptr(dev)))
+        ctx.flat = flat
+        ctx.shapes = [p.shape for p in params]
+        loss, loss_rec = loss2[0].clone(), loss2[1].clone()
+        ctx.mark_non_differentiable(loss_rec)       # the reference accumulates loss_reconstruct detached (:250,275)
+        return loss, loss_rec
+
+    @staticmethod
+    def backward(ctx, gloss, _grec):
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp))
+            grads.append((ctx.flat[off:off + n] * gloss).view(shp))
+            off += n
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
 class CylinderEmbeddingTrainer(EmbeddingTrainingHead):
-    """evaluate() and the VALUE of the training loss (forward() under torch.no_grad(), e.g. for validation curves)
-    are served by the kernels; its gradient — the Cylinder Koopman TRAINING step, conv backward — is a "next" row
-     and raises until it is built."""
+    """Training head: forward(states [B,T,3,64,128], viscosity [B]) -> (loss, loss_reconstruct)
+    (embedding_cylinder.py:224-281).  With gradients enabled the loss and the gradient of every parameter come from ONE
+    fused native forward+backward (`loss.backward()` only scatters it); under torch.no_grad() the value is computed
+    with the inference kernels."""
+    W_REC, W_DYN, W_REG = 1e1, 1e1, 1e-2
 
     def __init__(self, config) -> None:
         super().__init__()
@@ -189,13 +222,18 @@ class CylinderEmbeddingTrainer(EmbeddingTrainingHead):
         """(loss, loss_reconstruct) of embedding_cylinder.py:236-281: 1e1 MSE(x, recover(embed(x))) per step (decoder
         without mask, as `forward()` of the reference) + 1e1 MSE(x_t, recover(K g_{t-1})) (with mask)
         + 1e-2 sum(K^2) over the per-sample operators."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.embedding_model.parameters()):
-            raise NotImplementedError("Cylinder embedding training step (conv backward) is not built yet; "
-                                      "call under torch.no_grad() for the loss value")
         assert states.size(0) == viscosity.size(0), \
             "State variable and viscosity tensor should have the same batch dimensions."
         m = self.embedding_model
         device = m.devices[0]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in m.parameters()):
+            m.train()
+            st = N.require_cuda_f32(states.to(device), "states")
+            assert st.dim() == 5 and tuple(st.shape[2:]) == (3, 64, 128), "states must be [B, T, 3, 64, 128]"
+            v = m._visc(viscosity.to(device), st.size(0))
+            loss, loss_rec = _FusedCylinderKoopmanLoss.apply(m, st, v, self.W_REC, self.W_DYN, self.W_REG, *list(m.parameters()))
+            m._last_visc = v
+            return loss, loss_rec
         mse = nn.functional.mse_loss
         viscosity = viscosity.to(device)
         xin0 = states[:, 0].to(device)

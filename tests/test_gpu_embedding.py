@@ -421,3 +421,47 @@ def test_feature_cache_blocks_and_round_trip(dev, tmp_path):
     assert len(cex) == 2 and cex[0].shape == (4, 128)
     ref = O.cylinder_embed(csd, ccfg, torch.from_numpy(x), torch.full((6, 1), 2.0 / 400.0))
     assert O.rel_l2(torch.cat([cex[0], cex[1][2:]]), ref) < TOL
+
+
+def test_fused_cylinder_step_equals_reference_loop(dev):
+    """FusedKoopmanStep on the Cylinder head (fused fwd+bwd -> clip + Adam on the flat master buffer, no autograd graph)
+    against the reference's step body run by torch on the oracle graph (enn_trainer.py:93-102: loss.backward();
+    clip_grad_norm_(0.1); Adam(lr, weight_decay).step()), two steps; afterwards embed() sees the updated weights."""
+    from trphysx_b200.optim import FusedClipAdam, FusedKoopmanStep
+    cfg = synth.make_config("cylinder")
+    head = _cyl_head(cfg, 731, dev)
+    w_np = synth.cylinder_embedding_weights(cfg, 731)
+    sd = {k: (v.clone().requires_grad_(True) if k in O.CYL_PARAM_ORDER else v) for k, v in O.to_torch(w_np).items()}
+    leaves = [sd[k] for k in O.CYL_PARAM_ORDER]
+    ref_opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-8)
+    B, T = 2, 3
+    x, visc = synth.cylinder_fields(B * T, seed=732)
+    states_c = torch.from_numpy(x).view(B, T, 3, 64, 128)
+    visc_c = torch.from_numpy(visc).view(B, T, 1)[:, 0]
+    ref_losses = []
+    for _ in range(2):
+        ref_opt.zero_grad()
+        loss, _ = O.cylinder_train_loss(sd, cfg, states_c, visc_c)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(leaves, 0.1)
+        ref_opt.step()
+        ref_losses.append(float(loss))
+    opt = FusedClipAdam(head.parameters(), lr=1e-3, weight_decay=1e-8, max_norm=0.1)
+    step = FusedKoopmanStep(head, opt)
+    states, visc = states_c.to(dev), visc_c.to(dev)
+    for i in range(2):
+        l2 = step(states, visc)
+        assert abs(float(l2[0]) - ref_losses[i]) <= 2e-5 * ref_losses[i], (i, float(l2[0]), ref_losses[i])
+    # Adam divides by sqrt(v): entries whose gradient is at the FP32 noise level step by +-lr on that noise on both
+    # sides, so the parameters agree to lr-sized absolute errors on a few entries; the UPDATES must agree as a whole
+    got = dict(head.embedding_model.named_parameters())
+    w0 = O.to_torch(w_np)
+    for k in O.CYL_PARAM_ORDER:
+        a, b = got[k].detach().cpu(), sd[k].detach()
+        assert O.rel_l2(a, b) < 1e-4, k
+        assert O.rel_l2(a - w0[k], b - w0[k]) < 5e-2, k
+    m = head.embedding_model.eval()
+    with torch.no_grad():
+        g = m.embed(states[:, 0], visc)
+    cur = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    assert O.rel_l2(g.cpu(), O.cylinder_embed(cur, cfg, states_c[:, 0], visc_c)) < TOL        # the kernels use the UPDATED weights

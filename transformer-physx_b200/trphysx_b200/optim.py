@@ -77,15 +77,23 @@ class FusedKoopmanStep:
         self.loss2 = torch.zeros(2, device=dev, dtype=torch.float32)
 
     @torch.no_grad()
-    def __call__(self, states: torch.Tensor):
-        """states [B, T, 3] on the model's device.  Returns the device tensor [loss, loss_reconstruct]."""
+    def __call__(self, states: torch.Tensor, viscosity: torch.Tensor = None):
+        """states [B, T, 3] (Lorenz / Rossler) or [B, T, 3, 64, 128] with viscosity [B] (Cylinder) on the model's
+        device.  Returns the device tensor [loss, loss_reconstruct]."""
         m = self.head.embedding_model
+        m.train()
         states = N.require_cuda_f32(states, "states")
         dev = states.device
         h = m._handle(dev)
-        N.check(N.lib().trpx_mlpemb_train_fwd_bwd(
-            h, states.data_ptr(), states.size(0), states.size(1), self.head.W_RECON, self.head.W_DYN,
-            self.head.W_REG, 1.0, self.loss2.data_ptr(), self.opt.grad.data_ptr(), N.stream_ptr(dev)))
+        if viscosity is not None:                   # Cylinder head (embedding_cylinder.py:236-281)
+            v = m._visc(viscosity.to(dev), states.size(0))
+            N.check(N.lib().trpx_cyl_train_fwd_bwd(
+                h, states.data_ptr(), v.data_ptr(), states.size(0), states.size(1), self.head.W_REC, self.head.W_DYN,
+                self.head.W_REG, 1.0, self.loss2.data_ptr(), self.opt.grad.data_ptr(), N.stream_ptr(dev)))
+        else:
+            N.check(N.lib().trpx_mlpemb_train_fwd_bwd(
+                h, states.data_ptr(), states.size(0), states.size(1), self.head.W_RECON, self.head.W_DYN,
+                self.head.W_REG, 1.0, self.loss2.data_ptr(), self.opt.grad.data_ptr(), N.stream_ptr(dev)))
         if self.world > 1:
             from .parallel import average_flat_grad
             average_flat_grad(self.opt.grad, self.world)

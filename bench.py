@@ -396,6 +396,29 @@ def record_koopman_train(dev, world, rank):
                                  "bound by construction (SURVEY 8d K7)"}}, ms
 
 
+def record_forward(dev, fp32_peak):
+    """PhysformerGPT2.forward teacher-forced over 4,096 Lorenz sequences of 64 tokens: the tensor-core kernel
+    (3xTF32 mma.sync) beside the block-GEMV kernel it replaces."""
+    from tests import synth
+    from tests.util import make_gpt2
+    cfg = synth.make_config("lorenz")
+    m = make_gpt2(cfg, 17, False, dev)
+    B, T = 4096, 64
+    x = torch.randn(B, T, cfg.n_embd, device=dev)
+    flops = B * T * cfg.n_layer * (24 * 32 * 32 + 4 * (T / 2) * 32) + B * T * 2 * 32 * 32
+    out = {"workload": f"lorenz forward B={B} T={T} (teacher forced, use_cache=False)"}
+    for variant, key in ((0, "forward_e32_tc_kernel"), (1, "forward_kernel")):
+        m.set_rollout_tuning(variant=variant)
+        ms = timed_ms(lambda: m(x, use_cache=False), 5, 2)
+        out[key] = {"ms": ms, "tokens_per_s": B * T / (ms * 1e-3), "tflops": flops / (ms * 1e-3) / 1e12}
+    tf = out["forward_e32_tc_kernel"]["tflops"]
+    out["roofline"] = {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                       "note": "algorithmic FLOPs (n_layer*(24E^2 + 4*(T/2)*E) + 2E^2 per token) against the FP32 FMA peak measured "
+                               "in this run; the dense part runs as 3xTF32 mma.sync, the causal attention on the FP32 pipe"}
+    out["speedup_vs_block_gemv"] = out["forward_kernel"]["ms"] / out["forward_e32_tc_kernel"]["ms"]
+    return out
+
+
 def extra_records(args, dev, world, rank, flush, peaks, fp32_peak, umma_peak):
     """Every other BASELINE config, measured in this run.  All ranks execute this (the training step has a collective)."""
     import torch.distributed as dist
@@ -443,6 +466,7 @@ def extra_records(args, dev, world, rank, flush, peaks, fp32_peak, umma_peak):
                          "limiter": f"{groups} warp groups of {launch['group']} trajectories on {slots} resident warp slots "
                                     f"({groups / max(slots, 1):.2f} waves) + fixed embed/recover launches"}
     if rank == 0 and not args.no_configs:
+        rec["forward_teacher_forced"] = record_forward(dev, fp32_peak)
         rec["lorenz256"] = record_lorenz(dev, "lorenz", 256, 128, flush, peaks, fp32_peak)
         rec["lorenz_sweep"] = [record_lorenz(dev, "lorenz", B, S, flush, peaks, fp32_peak, e2e=False)
                                for B, S in ((1024, 64), (65536, 256), (262144, 128))]

@@ -550,3 +550,31 @@ def test_module_copies_do_not_free_live_handles(dev):
     ref, _ = O.gpt2_generate(sd, cfg, x.cpu(), 20, use_cache=True)
     n, _ = stable_prefix(cfg, {k: v.numpy() for k, v in sd.items()}, x.cpu(), 20, True)
     assert n >= 5 and O.rel_l2(got.cpu()[:, :n], ref[:, :n]) < TOL
+
+
+@pytest.mark.parametrize("kind,B,T,Tp", [("lorenz", 33, 19, 0), ("lorenz", 5, 64, 0), ("lorenz", 7, 23, 30), ("rossler", 130, 32, 0),
+                                         ("rossler", 3, 1, 31)])
+def test_forward_tensor_core_kernel(dev, kind, B, T, Tp):
+    """forward_e32_tc_kernel (3xTF32 mma.sync, one 16-token M tile per warp; E = 32 models) against the oracle and against
+    the block-GEMV forward_kernel (variant 1): ragged token counts (T not a multiple of 16), a past window, presents."""
+    cfg = synth.make_config(kind)
+    w_np = synth.gpt2_weights(cfg, 941, stress=True, stress_sigma=0.2)
+    m = make_gpt2(cfg, 941, True, dev, sigma=0.2)
+    sd = O.to_torch(w_np)
+    x = torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), 942))
+    past = past_ref = None
+    if Tp:
+        xp = torch.from_numpy(synth.normal_embeds((B, Tp, cfg.n_embd), 943))
+        _, past_ref, _ = O.gpt2_forward(sd, cfg, xp, use_cache=True)
+        past = [p_.to(dev) for p_ in past_ref]
+    hid_ref, pres_ref, _ = O.gpt2_forward(sd, cfg, x, past=past_ref, use_cache=True)
+    outs = {}
+    for variant in (0, 1):
+        m.set_rollout_tuning(variant=variant)
+        with torch.no_grad():
+            hid, pres = m(x.to(dev), past=past, use_cache=True)
+        assert O.rel_l2(hid.cpu(), hid_ref) < TOL
+        for l in range(cfg.n_layer):
+            assert O.rel_l2(pres[l].cpu(), pres_ref[l]) < TOL
+        outs[variant] = hid
+    assert not torch.equal(outs[0], outs[1])          # really two kernels

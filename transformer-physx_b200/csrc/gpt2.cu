@@ -2556,6 +2556,221 @@ __global__ void __launch_bounds__(GEN_THREADS) forward_kernel(ForwardParams p) {
     }
 }
 
+// ---- teacher-forced forward on tensor cores (E = 32, 4 heads of 8, T + Tp <= 64) ---------------------------------
+// forward_kernel above runs a sequence through block-wide GEMVs of 8 tokens with a CTA barrier after each (160 of
+// them for T = 64): 3 TFLOP/s.  Here a sequence is four 16-token M tiles, one per warp; every dense op of a layer is a
+// warp-level 3xTF32 product (mma.sync.m16n8k8, a_lo*w_hi + a_hi*w_lo + a_hi*w_hi, FP32 accumulate: ~2^-21 relative, the
+// FP32 parity bar holds) on the warp's own rows — activations in shared memory rows that only this warp touches,
+// weights read through L1 — so the only CTA barriers are the two around the attention (keys / values of all tokens).
+constexpr int FT_ROWS = 64, FT_LDX = 36, FT_LDH = 132, FT_LDK = 33, FT_THREADS = 128;
+
+__device__ __forceinline__ void ft_split(float x, float& hi, float& lo) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    hi = __uint_as_float(u);
+    lo = x - hi;
+}
+__device__ __forceinline__ void ft_mma(float (&c)[4], const float (&a)[4], float b0, float b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// C[16 x N] = A[16 x K] (shared memory, row stride lda) . W[K x N] (global, row-major) + bias; epi(row, col, value)
+template <int K, int N, class Epi>
+__device__ __forceinline__ void ft_warp_gemm(const float* __restrict__ A, int lda, const float* __restrict__ W,
+                                             const float* __restrict__ bias, int lane, Epi epi) {
+    const int g = lane >> 2, q = lane & 3;
+    float acc[N / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++) {
+        const float b0 = __ldg(bias + nt * 8 + 2 * q), b1 = __ldg(bias + nt * 8 + 2 * q + 1);
+        acc[nt][0] = b0; acc[nt][1] = b1; acc[nt][2] = b0; acc[nt][3] = b1;
+    }
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        float ah[4], al[4];
+        ft_split(A[g * lda + k0 + q], ah[0], al[0]);
+        ft_split(A[(g + 8) * lda + k0 + q], ah[1], al[1]);
+        ft_split(A[g * lda + k0 + q + 4], ah[2], al[2]);
+        ft_split(A[(g + 8) * lda + k0 + q + 4], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < N / 8; nt++) {
+            float bh0, bl0, bh1, bl1;
+            ft_split(__ldg(W + (size_t)(k0 + q) * N + nt * 8 + g), bh0, bl0);
+            ft_split(__ldg(W + (size_t)(k0 + q + 4) * N + nt * 8 + g), bh1, bl1);
+            ft_mma(acc[nt], al, bh0, bh1);
+            ft_mma(acc[nt], ah, bl0, bl1);
+            ft_mma(acc[nt], ah, bh0, bh1);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; nt++) {
+        epi(g, nt * 8 + 2 * q, acc[nt][0]);
+        epi(g, nt * 8 + 2 * q + 1, acc[nt][1]);
+        epi(g + 8, nt * 8 + 2 * q, acc[nt][2]);
+        epi(g + 8, nt * 8 + 2 * q + 1, acc[nt][3]);
+    }
+}
+
+// LayerNorm of the warp's 16 rows of x (stride FT_LDX) into dst (stride ldd): two lanes per row, 16 channels each
+__device__ __forceinline__ void ft_warp_ln(const float* __restrict__ x, float* __restrict__ dst, int ldd,
+                                           const float* __restrict__ lw, const float* __restrict__ lb, float eps, int lane) {
+    const int r = lane >> 1, c0 = (lane & 1) * 16;
+    float v[16], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { v[i] = x[r * FT_LDX + c0 + i]; s += v[i]; }
+    s += __shfl_xor_sync(FULL, s, 1);
+    const float mean = s * (1.0f / 32.0f);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+    var += __shfl_xor_sync(FULL, var, 1);
+    const float rstd = 1.0f / sqrtf(var * (1.0f / 32.0f) + eps);
+#pragma unroll
+    for (int i = 0; i < 16; i++) dst[r * ldd + c0 + i] = (v[i] - mean) * rstd * __ldg(lw + c0 + i) + __ldg(lb + c0 + i);
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 4) forward_e32_tc_kernel(ForwardParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const Gpt2Layout& L = p.lay;
+    constexpr int E = 32, H = 4, HD = 8;
+    const int T = p.T, Tp = p.Tp, Tk = Tp + T;
+    float* x = sm;                              // [64][36]  residual stream
+    float* a = x + FT_ROWS * FT_LDX;            // [64][36]  GEMM input (LayerNorm output, attention output)
+    float* hb = a + FT_ROWS * FT_LDX;           // [64][132] MLP hidden; its first rows are ALSO the q / k / v tiles of the
+    float* qs = hb;                             // [64][33]  attention phase (the two never overlap in time: a CTA barrier
+    float* ks = qs + FT_ROWS * FT_LDK;          // [64][33]  separates the attention from the MLP and the MLP from the next
+    float* vs = ks + FT_ROWS * FT_LDK;          // [64][33]  layer's q|k|v); keys of the window: past rows first
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x;
+    const int r0 = warp * 16;                   // this warp's token rows
+    float* xw = x + r0 * FT_LDX;
+    float* aw = a + r0 * FT_LDX;
+    float* hw = hb + r0 * FT_LDH;
+
+    for (int i = tid; i < FT_ROWS * E; i += FT_THREADS) {
+        const int t = i >> 5, c = i & 31;
+        x[t * FT_LDX + c] = (t < T) ? p.x[((size_t)b * T + t) * E + c] + __ldg(p.pe + (Tp + t) * E + c) : 0.f;
+    }
+    __syncthreads();
+    for (int l = 0; l < L.n_layer; l++) {
+        const float* w = p.blob + (size_t)l * L.layer_stride;
+        if (Tp > 0) {
+            if (l > 0) __syncthreads();         // (the past rows land in the tile the previous MLP used)
+            const float* pk = p.past[l];       // [2][B][H][Tp][hd]
+            for (int i = tid; i < 2 * Tp * E; i += FT_THREADS) {
+                const int which = i / (Tp * E);
+                int r = i - which * Tp * E;
+                const int t = r >> 5, e = r & 31;
+                const int hh = e >> 3, d = e & 7;
+                (which ? vs : ks)[t * FT_LDK + e] = pk[((((size_t)which * p.B + b) * H + hh) * Tp + t) * HD + d];
+            }
+        }
+        ft_warp_ln(xw, aw, FT_LDX, w + L.ln1w, w + L.ln1b, p.eps, lane);
+        __syncwarp();
+        if (l > 0) __syncthreads();             // every warp is done with the previous layer's MLP hidden tile (aliases q|k|v)
+        ft_warp_gemm<E, 3 * E>(aw, FT_LDX, w + L.wqkv, w + L.bqkv, lane, [&](int r, int n, float v) {
+            const int t = r0 + r;
+            if (t >= T) return;
+            if (n < E) qs[t * FT_LDK + n] = v;
+            else if (n < 2 * E) ks[(Tp + t) * FT_LDK + (n - E)] = v;
+            else vs[(Tp + t) * FT_LDK + (n - 2 * E)] = v;
+        });
+        __syncthreads();                        // keys / values of every token are in place
+        if (p.has_presents) {
+            float* pr = p.presents[l];         // [2][B][H][Tk][hd]
+            for (int i = tid; i < 2 * Tk * E; i += FT_THREADS) {
+                const int which = i / (Tk * E);
+                int r = i - which * Tk * E;
+                const int t = r >> 5, e = r & 31;
+                const int hh = e >> 3, d = e & 7;
+                pr[((((size_t)which * p.B + b) * H + hh) * Tk + t) * HD + d] = (which ? vs : ks)[t * FT_LDK + e];
+            }
+        }
+        // causal attention: a lane owns (token r0 + lane/2, heads 2*(lane&1), 2*(lane&1)+1); query t sees keys [0, Tp + t].
+        // Scores in the log2 domain: q is pre-multiplied by log2(e) / sqrt(hd) (attention.py:97-99 divides the scores by
+        // sqrt(hd)), the softmax is ex2.approx(s - m) (2 ulp; the parity tests sit at 1e-6 against the 1e-5 bar).  Both
+        // heads and two keys advance together: four independent dot-product chains per lane instead of one.
+        {
+            const int t = r0 + (lane >> 1);
+            if (t < T) {
+                const int nk = Tp + t + 1;
+                const int h0 = 2 * (lane & 1) * HD;            // first channel of the lane's two heads (adjacent)
+                float qv[2 * HD];
+#pragma unroll
+                for (int d = 0; d < 2 * HD; d++) qv[d] = qs[t * FT_LDK + h0 + d] * (1.4426950408889634f / 2.8284271247461903f);
+                float m0 = -INFINITY, m1 = -INFINITY;
+                for (int j = 0; j < nk; j += 2) {
+                    const float* k0 = ks + j * FT_LDK + h0;
+                    const float* k1 = ks + min(j + 1, nk - 1) * FT_LDK + h0;
+                    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+#pragma unroll
+                    for (int d = 0; d < HD; d++) {
+                        s00 = fmaf(qv[d], k0[d], s00);
+                        s10 = fmaf(qv[HD + d], k0[HD + d], s10);
+                        s01 = fmaf(qv[d], k1[d], s01);
+                        s11 = fmaf(qv[HD + d], k1[HD + d], s11);
+                    }
+                    m0 = fmaxf(m0, fmaxf(s00, s01));
+                    m1 = fmaxf(m1, fmaxf(s10, s11));
+                }
+                float den0 = 0.f, den1 = 0.f, o[2 * HD];
+#pragma unroll
+                for (int d = 0; d < 2 * HD; d++) o[d] = 0.f;
+                for (int j = 0; j < nk; j += 2) {
+                    const bool two = j + 1 < nk;
+                    const float* k0 = ks + j * FT_LDK + h0;
+                    const float* k1 = ks + min(j + 1, nk - 1) * FT_LDK + h0;
+                    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+#pragma unroll
+                    for (int d = 0; d < HD; d++) {
+                        s00 = fmaf(qv[d], k0[d], s00);
+                        s10 = fmaf(qv[HD + d], k0[HD + d], s10);
+                        s01 = fmaf(qv[d], k1[d], s01);
+                        s11 = fmaf(qv[HD + d], k1[HD + d], s11);
+                    }
+                    const float e00 = ex2_approx(s00 - m0), e10 = ex2_approx(s10 - m1);
+                    const float e01 = two ? ex2_approx(s01 - m0) : 0.f, e11 = two ? ex2_approx(s11 - m1) : 0.f;
+                    den0 += e00 + e01;
+                    den1 += e10 + e11;
+                    const float* v0 = vs + j * FT_LDK + h0;
+                    const float* v1 = vs + min(j + 1, nk - 1) * FT_LDK + h0;
+#pragma unroll
+                    for (int d = 0; d < HD; d++) {
+                        o[d] = fmaf(e00, v0[d], o[d]);
+                        o[d] = fmaf(e01, v1[d], o[d]);
+                        o[HD + d] = fmaf(e10, v0[HD + d], o[HD + d]);
+                        o[HD + d] = fmaf(e11, v1[HD + d], o[HD + d]);
+                    }
+                }
+                const float i0 = 1.0f / den0, i1 = 1.0f / den1;
+#pragma unroll
+                for (int d = 0; d < HD; d++) {
+                    a[t * FT_LDX + h0 + d] = o[d] * i0;
+                    a[t * FT_LDX + h0 + HD + d] = o[HD + d] * i1;
+                }
+            }
+        }
+        __syncthreads();                        // all reads of this layer's keys / values are done
+        ft_warp_gemm<E, E>(aw, FT_LDX, w + L.wproj, w + L.bproj, lane, [&](int r, int n, float v) { xw[r * FT_LDX + n] += v; });
+        __syncwarp();
+        ft_warp_ln(xw, aw, FT_LDX, w + L.ln2w, w + L.ln2b, p.eps, lane);
+        __syncwarp();
+        ft_warp_gemm<E, 4 * E>(aw, FT_LDX, w + L.wfc, w + L.bfc, lane, [&](int r, int n, float v) { hw[r * FT_LDH + n] = gelu_new(v); });
+        __syncwarp();
+        ft_warp_gemm<4 * E, E>(hw, FT_LDH, w + L.wpr, w + L.bpr, lane, [&](int r, int n, float v) { xw[r * FT_LDX + n] += v; });
+        __syncwarp();
+    }
+    ft_warp_ln(xw, aw, FT_LDX, p.blob + L.lnfw, p.blob + L.lnfb, p.eps, lane);
+    __syncwarp();
+    ft_warp_gemm<E, E>(aw, FT_LDX, p.blob + L.wf, p.blob + L.bf, lane, [&](int r, int n, float v) {
+        const int t = r0 + r;
+        if (t < T) p.hidden[((size_t)b * T + t) * E + n] = v;
+    });
+}
+
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
     // out[c][r] = in[r][c]
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -3075,6 +3290,14 @@ int trpx_gpt2_forward(trpx_gpt2_t h, const float* x, const float* const* past, i
     p.has_past = past != nullptr; p.has_presents = presents != nullptr; p.has_attn = attn != nullptr;
     p.blob = h->blob; p.pe = h->pe; p.x = x; p.hidden = hidden;
     p.B = B; p.T = T; p.Tp = Tp; p.eps = h->cfg.ln_eps; p.lay = L;
+    // E = 32 / 4 heads / window <= 64 without attention-weight output: tensor-core kernel (3xTF32 mma.sync)
+    if (L.E == 32 && L.n_head == 4 && Tp + T <= FT_ROWS && attn == nullptr && h->tune_variant != 1) {
+        const size_t smem_tc = sizeof(float) * ((size_t)FT_ROWS * (2 * FT_LDX + FT_LDH));
+        TRPX_CUDA(cudaFuncSetAttribute(forward_e32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        forward_e32_tc_kernel<<<B, FT_THREADS, smem_tc, st>>>(p);
+        TRPX_CUDA(cudaGetLastError());
+        return TRPX_OK;
+    }
     const int TPd = ((T + TG - 1) / TG) * TG;
     const size_t smem = sizeof(float) * ((size_t)TPd * L.E * 3 + (size_t)2 * L.n_ctx * L.E + (size_t)TPd * 4 * L.E +
                                          (size_t)GEN_THREADS * TG + (size_t)(GEN_THREADS / 32) * L.n_ctx);

@@ -821,6 +821,7 @@ int trpx_cyl_destroy(trpx_cyl_t h) {
     cudaFree(h->wimg);
     cudaFree(h->U);
     cudaFree(h->uimg);
+    cudaFree(h->eimg);
     cudaFree(h->tws);
     h->magic = 0;
     delete h;
@@ -861,6 +862,16 @@ int trpx_cyl_load_weights(trpx_cyl_t h, const float* const* w, int n, void* stre
             if (rc) return rc;
         }
     }
+    {   // ... and of the encoder layers
+        size_t tot = 0;
+        for (int i = 0; i < UMMA_ENC_LAYERS; i++) { h->eimg_off[i] = tot; tot += umma_enc_wimg_floats(i); }
+        h->eimg_off[UMMA_ENC_LAYERS] = tot;
+        if (h->eimg == nullptr) TRPX_CUDA(cudaMalloc(&h->eimg, tot * sizeof(float)));
+        for (int i = 0; i < UMMA_ENC_LAYERS; i++) {
+            int rc = umma_enc_build_wimg(i, h->blob + h->off[T_ENC + 2 * i], h->eimg + h->eimg_off[i], (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    }
     h->loaded = true;
     return TRPX_OK;
 }
@@ -892,10 +903,28 @@ int trpx_cyl_embed(trpx_cyl_t h, const float* x, const float* visc, float* g, in
     // per-frame activation sizes: normalised input, 4 strided convs, final conv
     const size_t a0 = 4 * HW, a1 = 16 * HW / 4, a2 = 32 * HW / 16, a3 = 64 * HW / 64, a4 = 128 * HW / 256, a5 = (size_t)c4 * 32;
     const size_t per = a0 + a1 + a2 + a3 + a4 + a5;
+    const float* B = h->blob;
+    if (h->conv_mode == 3) {
+        // tcgen05 implicit GEMMs: the stride-2 layers in space-to-depth form, each epilogue writing the next layer's image
+        const int chunk3 = std::min(N, h->chunk_user ? h->chunk : 1024);
+        int rc3 = ensure_ws(h, (umma_enc_ws_floats(chunk3)) * sizeof(float));
+        if (rc3) return rc3;
+        const float* wi[UMMA_ENC_LAYERS];
+        const float* bi[UMMA_ENC_LAYERS];
+        for (int i = 0; i < UMMA_ENC_LAYERS; i++) { wi[i] = h->eimg + h->eimg_off[i]; bi[i] = B + h->off[T_ENC + 2 * i + 1]; }
+        for (int n0 = 0; n0 < N; n0 += chunk3) {
+            const int nn = std::min(chunk3, N - n0);
+            float* z = h->ws + umma_enc_ws_floats(chunk3) - (size_t)chunk3 * 128;
+            if ((rc3 = umma_encoder(x + (size_t)n0 * 3 * HW, visc + n0, B + h->off[T_MU], B + h->off[T_STD], wi, bi, h->ws, z, nn,
+                                    h->sm_count, st))) return rc3;
+            cyl_ln_kernel<<<(nn * 32 + 255) / 256, 256, 0, st>>>(z, B + h->off[T_LNW], B + h->off[T_LNB], g + (size_t)n0 * h->E, nn, h->E, h->eps);
+            TRPX_CUDA(cudaGetLastError());
+        }
+        return TRPX_OK;
+    }
     const int chunk = std::min(N, h->chunk);
     int rc = ensure_ws(h, per * chunk * sizeof(float));
     if (rc) return rc;
-    const float* B = h->blob;
     for (int n0 = 0; n0 < N; n0 += chunk) {
         const int nn = std::min(chunk, N - n0);
         float* p0 = h->ws;

@@ -51,6 +51,8 @@ struct trpx_cyl {
     size_t U_bytes = 0;
     float* uimg = nullptr;               // weight images of the four UMMA layers (mode 3)
     size_t uimg_off[trpx::UMMA_LAYERS + 1] = {0};
+    float* eimg = nullptr;               // weight images of the five UMMA encoder layers (mode 3)
+    size_t eimg_off[trpx::UMMA_ENC_LAYERS + 1] = {0};
     float* tws = nullptr;                // training-step workspace (csrc/cyl_train.cu)
     size_t tws_bytes = 0;
 };

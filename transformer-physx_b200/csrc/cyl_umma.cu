@@ -43,16 +43,24 @@ constexpr int UM_NPT = UM_PROD_WARPS * 32;                                // pro
 constexpr int UM_BLK = 126;                                               // useful rows of a 128-row M block (1 overlap each side)
 constexpr int UM_CHUNK = 16;                                              // output channels per epilogue pass (4 for the 3-channel last layer)
 
-template <int CIN_, int COUT_, int COUT_REAL_, int H_, int W_, bool UP_, int MB_, int NBUF_, int PS_, int LS_, bool FINAL_>
+// EPI_: 0 ReLU -> channels-last-4 (decoder, last strided encoder layer), 1 last decoder layer (un-normalise, mask, planar),
+//       2 ReLU -> the NEXT strided layer's space-to-depth image, 3 plain planar output (last encoder layer)
+// DY0_: first kernel row with non-zero weights (1 for the space-to-depth form of a stride-2 layer); TRIM_: the last row and
+// column of the H x W grid are not outputs (space-to-depth images carry one extra block row / column); KS_: accumulator
+// sets per block, K chunks dealt round-robin (the tensor core truncates its accumulator once per instruction, so a chain
+// of n MMAs carries a ~n * 3e-8 relative bias: splitting long chains keeps the deep, narrow encoder layers at 1e-6)
+template <int CIN_, int COUT_, int COUT_REAL_, int H_, int W_, bool UP_, int MB_, int NBUF_, int PS_, int LS_, int EPI_, int DY0_ = 0, int TRIM_ = 0, int KS_ = 1>
 struct UmmaLayer {
     static constexpr int CIN = CIN_, COUT = COUT_, COUT_REAL = COUT_REAL_, H = H_, W = W_, MB = MB_;
     static constexpr int LS = LS_;                                        // load ring depth (layer-input rows + weight slice of a K chunk)
     static constexpr int PS = PS_;                                        // patch ring depth
     static constexpr int NBUF = NBUF_;                                    // TMEM accumulator buffers (2: the epilogue of item i overlaps the MMAs of item i+1)
-    static constexpr int EC = FINAL_ ? 4 : UM_CHUNK;                      // output channels per epilogue pass
-    static constexpr int NCHUNK = FINAL_ ? 1 : COUT_ / UM_CHUNK;          // epilogue passes per block
+    static constexpr int EPI = EPI_, DY0 = DY0_, TRIM = TRIM_, KS = KS_;
+    static constexpr bool NARROW = (EPI_ == 1 || EPI_ == 3);              // <= 4 real output channels
+    static constexpr int EC = NARROW ? 4 : UM_CHUNK;                      // output channels per epilogue pass
+    static constexpr int NCHUNK = NARROW ? 1 : COUT_ / UM_CHUNK;          // epilogue passes per block
     static constexpr int EPI_GROUPS_PER_BLOCK = (NCHUNK % 2 == 0) ? 2 : 1;   // (block, chunk) units are dealt round-robin to the 2 groups
-    static constexpr bool UP = UP_, FINAL = FINAL_;
+    static constexpr bool UP = UP_, FINAL = (EPI_ == 1);
     static constexpr int HS = UP ? H / 2 : H, WS = UP ? W / 2 : W;        // layer input size
     static constexpr int PW = W + 2, FRAME_POS = (H + 2) * PW;            // flat padded pixels per row / frame
     static constexpr int NPOS = UM_BLK * MB + 2 + 2 * PW;                 // staged positions of one work item
@@ -67,7 +75,7 @@ struct UmmaLayer {
     static constexpr int PATCH_BYTES = 2 * 2 * NPOS * 16;                 // [plane][kc][pos][4 f]
     static constexpr int W_BYTES = 3 * 2 * N6 * 16;                       // [dy][kc][n][4 f]
     static constexpr int LOAD_BYTES = W_BYTES + SRC_BYTES;                // one load-ring slot: [weights][rows]
-    static constexpr int TMEM_USED = NBUF * MB * N6;
+    static constexpr int TMEM_USED = NBUF * MB * KS * N6;
     static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static constexpr int EDGE_FLOATS = 2 * 2 * 2 * 4 * UM_CHUNK;          // [group][parity][left|right][quarter][16]
     static constexpr size_t RING_BYTES = (size_t)PS * PATCH_BYTES + (size_t)LS * LOAD_BYTES;
@@ -87,6 +95,7 @@ struct UmmaArgs {
     const unsigned char* mask;
     int N;
     int nitems;
+    int co_base, co_total;  // EPI 0: the COUT channels of this launch are channels [co_base, co_base + COUT) of co_total
     int debug;              // TRPX_UMMA_DEBUG bits (timing experiments only, results are garbage): 1 producers idle, 2 no MMAs,
                             // 4 epilogue skips the stores, 8 no fence.proxy.async, 16 no layer-input TMA, 32 no weight TMA,
                             // 64 epilogue skips TMEM loads and the edge exchange
@@ -259,9 +268,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                 const int t = q * 32 + lane;                           // row of the block
                 const int lp = lb + UM_BLK * b + t;                    // flat padded position inside the frame
                 const int yp = lp / L::PW, xp = lp - yp * L::PW;
-                const bool valid = t >= 1 && t <= UM_BLK && yp >= 1 && yp <= L::H && xp >= 1 && xp <= L::W;
+                const bool valid = t >= 1 && t <= UM_BLK && yp >= 1 && yp <= L::H - L::TRIM && xp >= 1 && xp <= L::W - L::TRIM;
                 const int y = yp - 1, x = xp - 1;
-                const uint32_t tcol = tmem_base + lane_base + (uint32_t)((buf * L::MB + b) * L::N6);
+                const uint32_t tcol = tmem_base + lane_base + (uint32_t)((buf * L::MB + b) * L::KS * L::N6);
                 if (a.debug & 64) {
                     tc_fence_before();
                     __syncwarp();
@@ -275,17 +284,22 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                     float v[3][EC];
 #pragma unroll
                     for (int dx = 0; dx < 3; dx++) {
-                        uint32_t rh[EC], rs[EC];
-                        if constexpr (EC == 16) {
-                            tmem_ld16(tcol + (uint32_t)(dx * L::COUT + co0), rh);
-                            tmem_ld16(tcol + (uint32_t)(L::N3 + dx * L::COUT + co0), rs);
-                        } else {
-                            tmem_ld4(tcol + (uint32_t)(dx * L::COUT + co0), rh);
-                            tmem_ld4(tcol + (uint32_t)(L::N3 + dx * L::COUT + co0), rs);
-                        }
-                        tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < EC; j++) v[dx][j] = __uint_as_float(rh[j]) + __uint_as_float(rs[j]);
+                        for (int j = 0; j < EC; j++) v[dx][j] = 0.f;
+#pragma unroll
+                        for (int ks = 0; ks < L::KS; ks++) {
+                            uint32_t rh[EC], rs[EC];
+                            if constexpr (EC == 16) {
+                                tmem_ld16(tcol + (uint32_t)(ks * L::N6 + dx * L::COUT + co0), rh);
+                                tmem_ld16(tcol + (uint32_t)(ks * L::N6 + L::N3 + dx * L::COUT + co0), rs);
+                            } else {
+                                tmem_ld4(tcol + (uint32_t)(ks * L::N6 + dx * L::COUT + co0), rh);
+                                tmem_ld4(tcol + (uint32_t)(ks * L::N6 + L::N3 + dx * L::COUT + co0), rs);
+                            }
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < EC; j++) v[dx][j] += __uint_as_float(rh[j]) + __uint_as_float(rs[j]);
+                        }
                     }
                     if (c + CSTEP >= L::NCHUNK) {                      // this group is done with the block's accumulator
                         tc_fence_before();
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                     for (int j = 0; j < EC; j++) o[j] = (lv[j] + v[1][j]) + rv[j];
                     par ^= 1;
                     if (valid && !(a.debug & 4)) {
-                        if constexpr (!L::FINAL) {
+                        if constexpr (L::EPI == 0) {
                             float4* out4 = reinterpret_cast<float4*>(a.out);
 #pragma unroll
                             for (int c4 = 0; c4 < EC / 4; c4++) {
@@ -339,8 +353,40 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                                 w.y = fmaxf(o[4 * c4 + 1] + bz.y, 0.f);
                                 w.z = fmaxf(o[4 * c4 + 2] + bz.z, 0.f);
                                 w.w = fmaxf(o[4 * c4 + 3] + bz.w, 0.f);
-                                out4[(((size_t)n * (L::COUT / 4) + (co >> 2)) * L::H + y) * L::W + x] = w;
+                                out4[(((size_t)n * (a.co_total / 4) + ((a.co_base + co) >> 2)) * (L::H - L::TRIM) + y) * (L::W - L::TRIM) + x] = w;
                             }
+                        } else if constexpr (L::EPI == 2) {
+                            // the next layer is a stride-2 conv: write its space-to-depth image Q[(py,px,co)][Y][X] =
+                            // out[2Y+py-1][2X+px-1][co] (replicate: the border rows / columns are stored twice)
+                            constexpr int HO = L::H - 1, WO = L::W - 1, H2 = HO / 2 + 1, W2 = WO / 2 + 1;
+                            const int QP = a.co_total / 4;                     // quads per parity of the next layer's image
+                            float4* out4 = reinterpret_cast<float4*>(a.out);
+                            int Ys[2], pys[2], ny = 1, Xs[2], pxs[2], nx = 1;
+                            Ys[0] = (y + 1) >> 1; pys[0] = (y + 1) & 1;
+                            Xs[0] = (x + 1) >> 1; pxs[0] = (x + 1) & 1;
+                            if (y == 0) { Ys[1] = 0; pys[1] = 0; ny = 2; }
+                            if (y == HO - 1) { Ys[1] = HO / 2; pys[1] = 1; ny = 2; }
+                            if (x == 0) { Xs[1] = 0; pxs[1] = 0; nx = 2; }
+                            if (x == WO - 1) { Xs[1] = WO / 2; pxs[1] = 1; nx = 2; }
+#pragma unroll
+                            for (int c4 = 0; c4 < EC / 4; c4++) {
+                                const int co = co0 + 4 * c4;
+                                const float4 bz = __ldg(reinterpret_cast<const float4*>(a.bias + co));
+                                float4 w;
+                                w.x = fmaxf(o[4 * c4 + 0] + bz.x, 0.f);
+                                w.y = fmaxf(o[4 * c4 + 1] + bz.y, 0.f);
+                                w.z = fmaxf(o[4 * c4 + 2] + bz.z, 0.f);
+                                w.w = fmaxf(o[4 * c4 + 3] + bz.w, 0.f);
+                                for (int iy = 0; iy < ny; iy++)
+                                    for (int ix = 0; ix < nx; ix++) {
+                                        const int quad = (pys[iy] * 2 + pxs[ix]) * QP + ((a.co_base + co) >> 2);
+                                        out4[(((size_t)n * (4 * QP) + quad) * H2 + Ys[iy]) * W2 + Xs[ix]] = w;
+                                    }
+                            }
+                        } else if constexpr (L::EPI == 3) {
+#pragma unroll
+                            for (int j = 0; j < L::COUT_REAL; j++)
+                                a.out[(((size_t)n * L::COUT_REAL + j) * L::H + y) * L::W + x] = o[j] + __ldg(a.bias + j);
                         } else {
                             const bool masked = a.mask != nullptr && a.mask[y * L::W + x] != 0;
 #pragma unroll
@@ -376,15 +422,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) cyl_umma_conv_kernel(const Umma
                             mbar_wait(&tempty[buf * L::MB + b], tpar ^ 1);
                             tc_fence_after();
                         }
-                        const uint32_t tc = tmem_base + (uint32_t)((buf * L::MB + b) * L::N6);
+                        const uint32_t tc = tmem_base + (uint32_t)(((buf * L::MB + b) * L::KS + (kc % L::KS)) * L::N6);
 #pragma unroll
-                        for (int dy = 0; dy < 3; dy++) {
+                        for (int dy = L::DY0; dy < 3; dy++) {
                             if (a.debug & 2) break;
                             const uint32_t arow = (uint32_t)(UM_BLK * b + dy * L::PW) * 16u;
                             const uint64_t a_hi = umma_desc(sp + arow, LBO_A);
                             const uint64_t a_lo = umma_desc(sp + 2 * L::NPOS * 16 + arow, LBO_A);
                             const uint32_t wb = sw + (uint32_t)dy * (2 * L::N6 * 16);
-                            const uint32_t first = (kc == 0 && dy == 0) ? 0u : 1u;
+                            const uint32_t first = (kc < L::KS && dy == L::DY0) ? 0u : 1u;
                             if constexpr (L::CONCAT) {
                                 umma_tf32(tc, a_hi, umma_desc(wb, LBO_B), idesc6, first);                  // hh | hl
                                 umma_tf32(tc + L::N3, a_lo, umma_desc(wb, LBO_B), idesc3, 1u);              // + lh
@@ -592,11 +638,66 @@ __global__ void umma_wimg_kernel(const float* __restrict__ w, float* __restrict_
     }
 }
 
-//                      CIN COUT real  H    W   UP    MB NBUF PS LS FINAL
-using UL0 = UmmaLayer<128, 64, 64, 16, 32, true, 1, 1, 3, 4, false>;
-using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 1, 3, 5, false>;
-using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 1, 3, 3, false>;
-using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 1, 2, 3, true>;
+// Weight image of a stride-2 layer in its space-to-depth form: the layer reads Q[(py,px,ci)][Y][X] = in[2Y+py-1][2X+px-1][ci]
+// with a 2x2 kernel (DY, DX in {0,1}), written here as the 3x3 image the kernel expects with a zero first row / column:
+// tap (dy', dx') = (DY+1, DX+1) of channel k = (py*2+px)*Cin + ci carries w[co][ci][2DY+py][2DX+px] (zero beyond the 3x3).
+__global__ void umma_wimg_s2d_kernel(const float* __restrict__ w, float* __restrict__ img, int Cin, int COUT, int co_base, int Cout_all) {
+    const int CINQ = 4 * Cin, N6 = 6 * COUT, N3 = 3 * COUT;
+    const int total = (CINQ / 8) * 3 * 2 * N6 * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int r = i;
+        const int e = r % 4; r /= 4;
+        const int n = r % N6; r /= N6;
+        const int kc = r % 2; r /= 2;
+        const int dyp = r % 3; const int k8 = r / 3;
+        const int plane = n / N3, m = n % N3, dxp = m / COUT, co = m % COUT;
+        const int k = k8 * 8 + kc * 4 + e;
+        const int par = k / Cin, ci = k % Cin, py = par >> 1, px = par & 1;
+        float v = 0.f;
+        if (dyp >= 1 && dxp >= 1) {
+            const int ry = 2 * (dyp - 1) + py, rx = 2 * (dxp - 1) + px;
+            if (ry <= 2 && rx <= 2 && co_base + co < Cout_all) v = w[((size_t)(co_base + co) * Cin + ci) * 9 + ry * 3 + rx];
+        }
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        img[i] = plane ? lo : hi;
+    }
+}
+
+// encoder input: cat(x, visc) -> (x - mu) / std (embedding_cylinder.py:149-150, 198-200), written as the space-to-depth
+// image of the first stride-2 layer: Q[n][parity][33][65][4 channels]
+__global__ void umma_enc_prep_kernel(const float* __restrict__ x, const float* __restrict__ visc, const float* __restrict__ mu,
+                                     const float* __restrict__ sd, float4* __restrict__ q, int N) {
+    constexpr int H = 64, W = 128, H2 = H / 2 + 1, W2 = W / 2 + 1;
+    const long long total = (long long)N * 4 * H2 * W2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W2), Y = (int)((i / W2) % H2), par = (int)((i / ((long long)W2 * H2)) % 4);
+        const int n = (int)(i / (4LL * W2 * H2));
+        const int yy = min(max(2 * Y + (par >> 1) - 1, 0), H - 1), xx = min(max(2 * X + (par & 1) - 1, 0), W - 1);
+        const float* xp = x + (size_t)n * 3 * H * W + yy * W + xx;
+        float4 v;
+        v.x = (xp[0] - __ldg(mu + 0)) / __ldg(sd + 0);
+        v.y = (xp[H * W] - __ldg(mu + 1)) / __ldg(sd + 1);
+        v.z = (xp[2 * H * W] - __ldg(mu + 2)) / __ldg(sd + 2);
+        v.w = (visc[n] - __ldg(mu + 3)) / __ldg(sd + 3);
+        q[i] = v;
+    }
+}
+
+//                      CIN COUT real  H    W   UP    MB NBUF PS LS EPI [DY0 TRIM]
+using UL0 = UmmaLayer<128, 64, 64, 16, 32, true, 1, 1, 3, 4, 0>;
+using UL1 = UmmaLayer<64, 32, 32, 32, 64, true, 2, 1, 3, 5, 0>;
+using UL2 = UmmaLayer<32, 16, 16, 64, 128, true, 4, 1, 3, 3, 0>;
+using UL3 = UmmaLayer<16, 16, 3, 64, 128, false, 4, 1, 2, 3, 1>;
+// encoder (embedding_cylinder.py:42-60): four stride-2 layers in space-to-depth form (CIN = 4 x input channels, H x W =
+// the (Ho+1) x (Wo+1) block grid), then the stride-1 128 -> 4 layer
+using UE1 = UmmaLayer<16, 16, 16, 33, 65, false, 4, 1, 2, 3, 2, 1, 1>;      //   4 -> 16, 64x128 -> 32x64
+using UE2 = UmmaLayer<64, 32, 32, 17, 33, false, 1, 1, 3, 4, 2, 1, 1, 2>;   //  16 -> 32, -> 16x32
+using UE3 = UmmaLayer<128, 32, 32, 9, 17, false, 1, 1, 3, 4, 2, 1, 1, 2>;   //  32 -> 64 (two launches of 32 channels), -> 8x16
+using UE4 = UmmaLayer<256, 32, 32, 5, 9, false, 1, 1, 3, 4, 0, 1, 1, 2>;    //  64 -> 128 (four launches of 32 channels), -> 4x8
+using UE5 = UmmaLayer<128, 16, 4, 4, 8, false, 1, 1, 3, 4, 3, 0, 0, 4>;     // 128 -> 4 at 4x8, stride 1
+static_assert(UE1::SMEM <= 227 * 1024 && UE2::SMEM <= 227 * 1024 && UE3::SMEM <= 227 * 1024 && UE4::SMEM <= 227 * 1024 &&
+              UE5::SMEM <= 227 * 1024, "smem");
 static_assert(UL0::SMEM <= 227 * 1024 && UL1::SMEM <= 227 * 1024 && UL2::SMEM <= 227 * 1024 && UL3::SMEM <= 227 * 1024, "smem");
 
 template <class L>
@@ -716,10 +817,76 @@ int umma_build_wimg(int layer, const float* w, float* img, cudaStream_t st) {
     return TRPX_OK;
 }
 
+size_t umma_enc_wimg_floats(int layer) {
+    switch (layer) {
+        case 0: return (size_t)UE1::KCH * UE1::W_BYTES / 4;
+        case 1: return (size_t)UE2::KCH * UE2::W_BYTES / 4;
+        case 2: return 2 * (size_t)UE3::KCH * UE3::W_BYTES / 4;       // two groups of 32 output channels
+        case 3: return 4 * (size_t)UE4::KCH * UE4::W_BYTES / 4;       // four groups of 32 output channels
+        default: return (size_t)UE5::KCH * UE5::W_BYTES / 4;
+    }
+}
+
+int umma_enc_build_wimg(int layer, const float* w, float* img, cudaStream_t st) {
+    const int cin[4] = {4, 16, 32, 64}, cout[4] = {16, 32, 64, 128};
+    TRPX_REQUIRE(layer >= 0 && layer < UMMA_ENC_LAYERS, "bad layer");
+    if (layer == 4) {
+        umma_wimg_kernel<<<64, 256, 0, st>>>(w, img, 128, 16, 4);
+    } else if (layer == 3) {
+        const size_t part = (size_t)UE4::KCH * UE4::W_BYTES / 4;
+        for (int g = 0; g < 4; g++) umma_wimg_s2d_kernel<<<128, 256, 0, st>>>(w, img + g * part, 64, 32, 32 * g, 128);
+    } else if (layer == 2) {
+        const size_t part = (size_t)UE3::KCH * UE3::W_BYTES / 4;
+        for (int g = 0; g < 2; g++) umma_wimg_s2d_kernel<<<128, 256, 0, st>>>(w, img + g * part, 32, 32, 32 * g, 64);
+    } else {
+        umma_wimg_s2d_kernel<<<64, 256, 0, st>>>(w, img, cin[layer], cout[layer], 0, cout[layer]);
+    }
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
+size_t umma_enc_ws_floats(int N) {
+    // Q1 [4 quads][33][65], Q2 [16][17][33], Q3 [32][9][17], Q4 [64][5][9], a4 [32][4][8] (float4 each), z [128]
+    return (size_t)N * (4 * (4 * 33 * 65 + 16 * 17 * 33 + 32 * 9 * 17 + 64 * 5 * 9 + 32 * 4 * 8) + 128);
+}
+
+int umma_encoder(const float* x, const float* visc, const float* mu, const float* sd, const float* const* wimg,
+                 const float* const* bias, float* ws, float* z_out, int N, int sm_count, cudaStream_t st) {
+    float* q1 = ws;
+    float* q2 = q1 + (size_t)N * 4 * 4 * 33 * 65;
+    float* q3 = q2 + (size_t)N * 4 * 16 * 17 * 33;
+    float* q4 = q3 + (size_t)N * 4 * 32 * 9 * 17;
+    float* a4 = q4 + (size_t)N * 4 * 64 * 5 * 9;
+    const long long tot = (long long)N * 4 * 33 * 65;
+    umma_enc_prep_kernel<<<(int)std::min<long long>((tot + 255) / 256, 148 * 16), 256, 0, st>>>(x, visc, mu, sd, reinterpret_cast<float4*>(q1), N);
+    TRPX_CUDA(cudaGetLastError());
+    UmmaArgs a{};
+    a.N = N;
+    int rc;
+    a.in = q1; a.wimg = wimg[0]; a.bias = bias[0]; a.out = q2; a.co_base = 0; a.co_total = 16;
+    if ((rc = launch_umma<UE1>(a, sm_count, st))) return rc;
+    a.in = q2; a.wimg = wimg[1]; a.bias = bias[1]; a.out = q3; a.co_total = 32;
+    if ((rc = launch_umma<UE2>(a, sm_count, st))) return rc;
+    const size_t part3 = (size_t)UE3::KCH * UE3::W_BYTES / 4, part4 = (size_t)UE4::KCH * UE4::W_BYTES / 4;
+    for (int g = 0; g < 2; g++) {
+        a.in = q3; a.wimg = wimg[2] + g * part3; a.bias = bias[2] + g * 32; a.out = q4; a.co_base = g * 32; a.co_total = 64;
+        if ((rc = launch_umma<UE3>(a, sm_count, st))) return rc;
+    }
+    for (int g = 0; g < 4; g++) {
+        a.in = q4; a.wimg = wimg[3] + g * part4; a.bias = bias[3] + g * 32; a.out = a4; a.co_base = g * 32; a.co_total = 128;
+        if ((rc = launch_umma<UE4>(a, sm_count, st))) return rc;
+    }
+    a.co_base = 0; a.co_total = 0;
+    a.in = a4; a.wimg = wimg[4]; a.bias = bias[4]; a.out = z_out;
+    return launch_umma<UE5>(a, sm_count, st);
+}
+
 int umma_conv_layer(int layer, const float* in_cl4, const float* wimg, const float* bias, float* out, int N,
                     const float* mu, const float* sd, const unsigned char* mask, int sm_count, cudaStream_t st) {
     UmmaArgs a{};
     a.in = in_cl4; a.wimg = wimg; a.bias = bias; a.out = out; a.mu = mu; a.sd = sd; a.mask = mask; a.N = N;
+    static const int couts[4] = {64, 32, 16, 16};
+    a.co_base = 0; a.co_total = couts[layer & 3];
     switch (layer) {
         case 0: return launch_umma<UL0>(a, sm_count, st);
         case 1: return launch_umma<UL1>(a, sm_count, st);

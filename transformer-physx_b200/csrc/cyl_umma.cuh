@@ -21,4 +21,16 @@ int umma_build_wimg(int layer, const float* w, float* img, cudaStream_t st);
 int umma_conv_layer(int layer, const float* in_cl4, const float* wimg, const float* bias, float* out, int N,
                     const float* mu, const float* sd, const unsigned char* mask, int sm_count, cudaStream_t st);
 
+// ---- encoder (embedding_cylinder.py:42-60) on the same kernel -----------------------------------------------------
+// The four stride-2 layers run in space-to-depth form (a stride-2 3x3 conv is a 2x2 conv over 2x2 pixel blocks with
+// 4 x the channels), each layer's epilogue writing the next layer's block image directly; the fifth layer is a plain
+// stride-1 conv.  Layers: 0: 4->16, 1: 16->32, 2: 32->64, 3: 64->128, 4: 128->4 (4x8).
+constexpr int UMMA_ENC_LAYERS = 5;
+size_t umma_enc_wimg_floats(int layer);
+int umma_enc_build_wimg(int layer, const float* w, float* img, cudaStream_t st);
+size_t umma_enc_ws_floats(int N);
+// x [N][3][64][128], visc [N] -> z_out [N][128] (the encoder output before observableNetFC's LayerNorm)
+int umma_encoder(const float* x, const float* visc, const float* mu, const float* sd, const float* const* wimg,
+                 const float* const* bias, float* ws, float* z_out, int N, int sm_count, cudaStream_t st);
+
 }  // namespace trpx

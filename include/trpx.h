@@ -41,6 +41,9 @@ int         trpx_probe_tf32_mma(int device, float* tflops_out);
  * accumulators in TMEM) in TFLOP/s: the denominator of the Cylinder decoder's roofline (its error-compensated 3xTF32
  * product runs at a third of it). */
 int         trpx_probe_umma_tf32(int device, float* tflops_out);
+/* Measured tcgen05.ld rate (bytes per clock per SM, 8 warps x 32x32b.x32 loads): what bounds the window read of the
+ * rollout kernel that keeps the KV window in tensor memory (rollout variant 10, csrc/gpt2_tmem.cu). */
+int         trpx_probe_tmem_ld(int device, float* bytes_per_clk_out);
 /* Measured rate (GB/s) of the KV-window access pattern of the cache-mode rollout with the arithmetic removed:
  * 4 trajectories per warp, per (step, layer) two windows of n_ctx rows of 128 B read with 256-bit loads
  * (`rows_in_flight` per lane: 4, 8 or 16) plus two rows appended; `prefetch` adds the bulk L2 prefetch the rollout

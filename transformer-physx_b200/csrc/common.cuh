@@ -130,6 +130,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// cvt.rna.tf32.f32 (round to nearest, ties away, low 13 mantissa bits cleared) in two integer instructions: on sm_100a
+// the PTX instruction compiles to FSETP + predicated IADD + LOP3 because it also passes Inf/NaN through unchanged.
+// Every value split here is finite, for which this form is bit-identical (scripts/probes: SASS of cvt.rna.tf32).
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gpt2_layout.cuh"
 #include "gpt2_handle.cuh"
+#include "gpt2_tmem.cuh"
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -1433,9 +1434,7 @@ constexpr int V4G = 16;
 constexpr int V4QS = 36;          // row stride (floats) of the per-warp q / attention-output staging tile
 
 __device__ __forceinline__ uint32_t tf32_hi(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return u;
+    return tf32_rna_bits(x);
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = tf32_hi(x);
@@ -2565,9 +2564,7 @@ __global__ void __launch_bounds__(GEN_THREADS) forward_kernel(ForwardParams p) {
 constexpr int FT_ROWS = 64, FT_LDX = 36, FT_LDH = 132, FT_LDK = 33, FT_THREADS = 128;
 
 __device__ __forceinline__ void ft_split(float x, float& hi, float& lo) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    hi = __uint_as_float(u);
+    hi = __uint_as_float(tf32_rna_bits(x));
     lo = x - hi;
 }
 __device__ __forceinline__ void ft_mma(float (&c)[4], const float (&a)[4], float b0, float b1) {
@@ -3008,7 +3005,7 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 9, "variant must be 0..9");
+    TRPX_REQUIRE(variant >= 0 && variant <= 10, "variant must be 0..10");
     TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 32, "warps_per_cta must be 0..32");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
                      traj_per_warp == 8 || (traj_per_warp == 16 && (variant == 7 || variant == 9)),
@@ -3104,6 +3101,21 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             h->last_variant = 5; h->last_grid = grid; h->last_block = Wc * 32; h->last_smem = (int)smem; h->last_group = V2G;
             return launch_v2(p, L.n_ctx, grid, Wc * 32, smem, st);
         }
+    }
+    // ---- E=32, KV window on chip in tensor memory (variant 10, gpt2_tmem.cu) ----
+    if (e32_shape && use_cache && h->tune_variant == 10 && tmem_rollout_group(L) > 0 &&
+        tmem_rollout_smem(L) + 1024 <= (size_t)h->smem_optin &&
+        (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (out_stride % 2) == 0 &&
+        (reinterpret_cast<uintptr_t>(presents) & 15) == 0) {
+        const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
+        const int G = tmem_rollout_group(L);
+        const int ngroups = (B + G - 1) / G;
+        const int grid = std::min(sms, ngroups);
+        TmemRolloutParams tp{};
+        tp.blob_sw = h->blob_sw; tp.pe = h->pe; tp.x0 = x0; tp.x0_stride = x0_stride; tp.out = out; tp.out_stride = out_stride;
+        tp.presents = presents; tp.B = B; tp.S = S; tp.eps = h->cfg.ln_eps; tp.lay = L;
+        h->last_variant = 10; h->last_grid = grid; h->last_block = 256; h->last_smem = (int)tmem_rollout_smem(L); h->last_group = G;
+        return launch_rollout_tmem(tp, grid, st);
     }
     // ---- E=32, KV window, TMA-staged attention + weight ring (variant 8) ----
     if (e32_shape && use_cache && (h->tune_variant == 8) && (L.n_ctx == 8 || L.n_ctx == 16 || L.n_ctx % 32 == 0)) {

@@ -243,9 +243,7 @@ constexpr int RTC_THREADS = 384;
 constexpr int RTC_LD = 36;
 
 __device__ __forceinline__ uint32_t rtc_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return u;
+    return tf32_rna_bits(x);
 }
 __device__ __forceinline__ void rtc_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -31,6 +31,7 @@ SIGNATURES = {
     "trpx_probe_fp32_fma": (c_int, [c_int, POINTER(c_float)]),
     "trpx_probe_tf32_mma": (c_int, [c_int, POINTER(c_float)]),
     "trpx_probe_umma_tf32": (c_int, [c_int, POINTER(c_float)]),
+    "trpx_probe_tmem_ld": (c_int, [c_int, POINTER(c_float)]),
     "trpx_gpt2_train_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trpx_gpt2_blob_size": (c_int, [c_void_p]),
     "trpx_gpt2_load_blob": (c_int, [c_void_p, c_void_p, c_void_p]),

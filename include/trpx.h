@@ -58,7 +58,7 @@ typedef struct trpx_gpt2* trpx_gpt2_t;
 
 typedef struct {
     int   n_ctx;     /* PhysConfig.n_ctx   (configuration_phys.py:54) */
-    int   n_embd;    /* PhysConfig.n_embd  (:55)  multiple of 32, <= 256 */
+    int   n_embd;    /* PhysConfig.n_embd  (:55)  multiple of 32, <= 512 (Gray-Scott: 512) */
     int   n_layer;   /* PhysConfig.n_layer (:56) */
     int   n_head;    /* PhysConfig.n_head  (:57)  n_embd % n_head == 0 */
     float ln_eps;    /* PhysConfig.layer_norm_epsilon (:68) */
@@ -227,6 +227,30 @@ int trpx_cyl_train_fwd_bwd(trpx_cyl_t h, const float* states_dev, const float* v
                            float w_rec, float w_dyn, float w_reg, float grad_scale,
                            float* loss2_dev, float* grad_dev, void* stream);
 long long trpx_cyl_num_params(trpx_cyl_t h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gray-Scott Koopman embedding (trphysx/embedding/embedding_grayscott.py:25-218), eval mode: BatchNorm3d uses its
+ * running statistics (folded into the convs at load time).  States are [N, 2, 32, 32, 32].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct trpx_gs* trpx_gs_t;
+
+int trpx_gs_create(int n_embd /*512*/, float ln_eps, int device, trpx_gs_t* out);
+int trpx_gs_destroy(trpx_gs_t h);
+int trpx_gs_num_weight_tensors(trpx_gs_t h);   /* 64 */
+/* 64 device pointers: mu[1] std[1]; for observableNet.{0,3,6,9} then recoveryNet.{0,4,8,12}: conv.{weight,bias} and the
+ * BatchNorm3d that follows it {weight,bias,running_mean,running_var}; observableNetFC.{0,2}.{weight,bias},
+ * observableNetFC.3.{weight,bias} (LayerNorm); recoveryNetFC.{0,2}.{weight,bias}; recoveryNet.15.{weight,bias};
+ * kMatrixDiag[E]; kMatrixUT[sum_{d=1..9}(E-d)].  Conv weights are [Cout,Cin,k,k,k], Linear weights [out,in]. */
+int trpx_gs_load_weights(trpx_gs_t h, const float* const* w_dev, int n_tensors, void* stream);
+/* GrayScottEmbedding.embed (:127-139): x[N,2,32,32,32] -> g[N,E]; g0_dev NULL or [N,64,4,4,4] = observableNet(x),
+ * the third element of forward()'s tuple (:112-125) */
+int trpx_gs_embed(trpx_gs_t h, const float* x_dev, float* g_dev, float* g0_dev, int N, void* stream);
+/* GrayScottEmbedding.recover (:141-153): g[N,E] -> x[N,2,32,32,32]; out0_dev NULL or [N,64,4,4,4] = recoveryNetFC(g) */
+int trpx_gs_recover(trpx_gs_t h, const float* g_dev, float* x_dev, float* out0_dev, int N, void* stream);
+/* unnormalize(recoveryNet(z)) for a latent volume z[N,64,4,4,4] (last element of forward()'s tuple) */
+int trpx_gs_decode_latent(trpx_gs_t h, const float* z_dev, float* x_dev, int N, void* stream);
+/* GrayScottEmbedding.koopmanOperation (:155-175): g[B,E] -> g'[B,E]; kmat_dev NULL or [B,E,E] (self.kMatrix) */
+int trpx_gs_koopman(trpx_gs_t h, const float* g_dev, float* gnext_dev, float* kmat_dev, int B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -379,6 +379,77 @@ def cylinder_train_grads(sd: SD, cfg, states: Tensor, visc: Tensor, **kw):
 # ==================================================================================================
 # helpers used by the tests
 # ==================================================================================================
+# ==================================================================================================
+# Gray-Scott embedding (eval mode)
+# ==================================================================================================
+def _gs_block(sd: SD, p: str, i: int, x: Tensor, k: int, stride: int) -> Tensor:
+    # nn.Conv3d(padding=k//2, padding_mode='circular') + nn.BatchNorm3d (running stats) + LeakyReLU(0.02)
+    # embedding_grayscott.py:46-58,76-96
+    pad = k // 2
+    if pad:
+        x = F.pad(x, (pad,) * 6, mode="circular")
+    x = F.conv3d(x, sd[f"{p}.{i}.weight"], sd[f"{p}.{i}.bias"], stride=stride)
+    b = f"{p}.{i + 1}"
+    x = F.batch_norm(x, sd[b + ".running_mean"], sd[b + ".running_var"], sd[b + ".weight"], sd[b + ".bias"], False, 0.1, 1e-5)
+    return F.leaky_relu(x, 0.02)
+
+
+def grayscott_latent(sd: SD, cfg, x: Tensor) -> Tensor:
+    # observableNet of embedding_grayscott.py:46-59 on the normalised state (:212-214)
+    x = (x - sd["mu"]) / sd["std"]
+    for i, k, s in ((0, 5, 2), (3, 3, 2), (6, 3, 2), (9, 1, 1)):
+        x = _gs_block(sd, "observableNet", i, x, k, s)
+    return x
+
+
+def grayscott_embed(sd: SD, cfg, x: Tensor) -> Tensor:
+    # embedding_grayscott.py:141-153, observableNetFC :61-66
+    g0 = grayscott_latent(sd, cfg, x)
+    h = F.leaky_relu(F.linear(g0.reshape(g0.size(0), -1), sd["observableNetFC.0.weight"], sd["observableNetFC.0.bias"]), 0.02)
+    h = F.linear(h, sd["observableNetFC.2.weight"], sd["observableNetFC.2.bias"])
+    return F.layer_norm(h, (cfg.n_embd,), sd["observableNetFC.3.weight"], sd["observableNetFC.3.bias"], cfg.layer_norm_epsilon)
+
+
+def grayscott_decode_latent(sd: SD, cfg, z: Tensor) -> Tensor:
+    # recoveryNet of embedding_grayscott.py:75-98 + _unnormalize (:216-218)
+    x = _gs_block(sd, "recoveryNet", 0, z, 1, 1)
+    for i in (4, 8, 12):
+        x = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+        x = _gs_block(sd, "recoveryNet", i, x, 3, 1)
+    x = F.conv3d(x, sd["recoveryNet.15.weight"], sd["recoveryNet.15.bias"])
+    return sd["std"] * x + sd["mu"]
+
+
+def grayscott_recover_latent(sd: SD, cfg, g: Tensor) -> Tensor:
+    # recoveryNetFC of embedding_grayscott.py:68-73 (LeakyReLU(1.0) is the identity)
+    h = F.linear(g, sd["recoveryNetFC.0.weight"], sd["recoveryNetFC.0.bias"])
+    h = F.leaky_relu(F.linear(h, sd["recoveryNetFC.2.weight"], sd["recoveryNetFC.2.bias"]), 0.02)
+    return h.view(-1, 64, 4, 4, 4)
+
+
+def grayscott_recover(sd: SD, cfg, g: Tensor) -> Tensor:
+    # embedding_grayscott.py:155-167
+    return grayscott_decode_latent(sd, cfg, grayscott_recover_latent(sd, cfg, g))
+
+
+def grayscott_koopman_matrix(sd: SD, cfg) -> Tensor:
+    # embedding_grayscott.py:100-107,179-186: skew-symmetric bands 1..9 + diagonal
+    E = cfg.n_embd
+    xidx = np.concatenate([np.arange(0, E - i) for i in range(1, 10)])
+    yidx = np.concatenate([np.arange(i, E) for i in range(1, 10)])
+    K = torch.zeros(E, E, dtype=sd["kMatrixUT"].dtype)
+    K[xidx, yidx] = sd["kMatrixUT"]
+    K[yidx, xidx] = -sd["kMatrixUT"]
+    d = np.arange(E)
+    K[d, d] = sd["kMatrixDiag"]
+    return K
+
+
+def grayscott_koopman(sd: SD, cfg, g: Tensor) -> Tensor:
+    K = grayscott_koopman_matrix(sd, cfg)
+    return torch.bmm(K.unsqueeze(0).expand(g.size(0), -1, -1), g.unsqueeze(-1)).squeeze(-1)
+
+
 def rel_l2(a, b) -> float:
     """|| a - b ||_2 / || b ||_2 over the whole tensor (SURVEY.md §8d parity thresholds)."""
     a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).double().reshape(-1)

@@ -41,6 +41,10 @@ CYL_CASES = {
     "cyl": dict(seed=301, N=2),
 }
 
+GS_CASES = {
+    "gs": dict(seed=351, N=2),
+}
+
 TRAIN_CASES = {
     "lorenz":  dict(kind="lorenz", seed=401, B=24, T=6, iters=2),
     "rossler": dict(kind="rossler", seed=402, B=16, T=4, iters=1),

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from tests import synth
 from oracle import ref_shim  # noqa: E402
 from tests.golden.cases import (weights_kw, GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES,  # noqa: E402
-                                CYL_TRAIN_CASES)
+                                CYL_TRAIN_CASES, GS_CASES)
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 torch.set_num_threads(1)          # deterministic reduction order for the fixtures
@@ -108,6 +108,27 @@ def cyl_cases(trphysx):
         print("cyl", name, {k: v.shape for k, v in out.items()})
 
 
+def gs_cases(trphysx):
+    from trphysx.embedding.embedding_grayscott import GrayScottEmbedding
+    from trphysx.config.configuration_phys import PhysConfig
+    for name, c in GS_CASES.items():
+        cfg_ns = synth.make_config("grayscott")
+        cfg = PhysConfig(**vars(cfg_ns))
+        model = GrayScottEmbedding(cfg).eval()
+        model.load_state_dict(_t(synth.grayscott_embedding_weights(cfg_ns, c["seed"])), strict=True)
+        x = torch.from_numpy(synth.grayscott_fields(c["N"], seed=c["seed"]))
+        with torch.no_grad():
+            g = model.embed(x)
+            f_g, f_xhat, f_g0, f_out0, f_x2 = model(x)
+            rec = model.recover(g)
+            kop = model.koopmanOperation(g)
+            out = dict(embed=g.numpy(), recover=rec.numpy(), fwd_g0=f_g0.numpy(), fwd_out0=f_out0.numpy(),
+                       fwd_xhat_ch0=f_xhat[:, 0].numpy(), fwd_x2_ch1=f_x2[:, 1].numpy(), koopman=kop.numpy(),
+                       kmatrix0=model.koopmanOperator[0].detach().numpy())
+        np.savez_compressed(os.path.join(OUT, f"gs_{name}.npz"), **out)
+        print("gs", name, {k: v.shape for k, v in out.items()})
+
+
 def train_cases(trphysx):
     from trphysx.embedding.embedding_lorenz import LorenzEmbeddingTrainer
     from trphysx.config.configuration_phys import PhysConfig
@@ -190,6 +211,8 @@ if __name__ == "__main__":
         gpt2_train_cases(t)                                        # added later: leaves the other fixtures untouched
     elif len(sys.argv) > 1 and sys.argv[1] == "cyltrain":
         cyl_train_cases(t)
+    elif len(sys.argv) > 1 and sys.argv[1] == "gs":
+        gs_cases(t)
     elif len(sys.argv) > 2 and sys.argv[1] == "gpt2":              # python make_golden.py gpt2 <case> [<case> ...]
         gpt2_cases(t, only=sys.argv[2:])
     else:
@@ -199,3 +222,4 @@ if __name__ == "__main__":
         cyl_cases(t)
         train_cases(t)
         gpt2_train_cases(t)
+        gs_cases(t)

@@ -34,6 +34,9 @@ def make_config(kind: str, **over):
     elif kind == "cylinder":
         base.update(n_ctx=16, n_embd=128, n_layer=6, n_head=4, state_dims=[3, 64, 128],
                     initializer_range=0.01)
+    elif kind == "grayscott":                       # configuration_grayscott.py:15-38
+        base.update(n_ctx=128, n_embd=512, n_layer=2, n_head=32, state_dims=[2, 32, 32, 32],
+                    initializer_range=0.01)
     else:
         raise ValueError(kind)
     base.update(over)
@@ -156,6 +159,66 @@ def cylinder_embedding_weights(cfg, seed: int) -> "OrderedDict[str, np.ndarray]"
     lin("kMatrixLT.0", 50, 1)
     lin("kMatrixLT.2", nband, 50)
     return sd
+
+
+def grayscott_embedding_weights(cfg, seed: int) -> "OrderedDict[str, np.ndarray]":
+    """Random Gray-Scott embedding state_dict (embedding_grayscott.py:41-108) with non-trivial BatchNorm3d running
+    statistics; key order = the module's own state_dict order."""
+    rng = np.random.default_rng(seed)
+    E = cfg.n_embd
+    sd = OrderedDict()
+
+    def conv(prefix, cout, cin, k):
+        b = 1.0 / np.sqrt(cin * k ** 3)
+        sd[prefix + ".weight"] = _f32(rng.uniform(-b, b, size=(cout, cin, k, k, k)))
+        sd[prefix + ".bias"] = _f32(rng.uniform(-b, b, size=cout))
+
+    def bn(prefix, c):
+        sd[prefix + ".weight"] = _f32(1.0 + 0.1 * rng.normal(size=c))
+        sd[prefix + ".bias"] = _f32(0.1 * rng.normal(size=c))
+        sd[prefix + ".running_mean"] = _f32(0.1 * rng.normal(size=c))
+        sd[prefix + ".running_var"] = _f32(rng.uniform(0.5, 1.5, size=c))
+        sd[prefix + ".num_batches_tracked"] = np.asarray(7, dtype=np.int64)
+
+    def lin(prefix, fan_out, fan_in):
+        b = 1.0 / np.sqrt(fan_in)
+        sd[prefix + ".weight"] = _f32(rng.uniform(-b, b, size=(fan_out, fan_in)))
+        sd[prefix + ".bias"] = _f32(rng.uniform(-b, b, size=fan_out))
+
+    nband = sum(E - i for i in range(1, 10))
+    sd["kMatrixDiag"] = _f32(rng.uniform(0.5, 1.0, size=E))
+    sd["kMatrixUT"] = _f32(0.01 * rng.uniform(0, 1, size=nband))
+    sd["mu"] = np.asarray(0.3, dtype=np.float32)
+    sd["std"] = np.asarray(0.8, dtype=np.float32)
+    for i, (cout, cin, k) in zip((0, 3, 6, 9), ((64, 2, 5), (128, 64, 3), (128, 128, 3), (64, 128, 1))):
+        conv(f"observableNet.{i}", cout, cin, k)
+        bn(f"observableNet.{i + 1}", cout)
+    lin("observableNetFC.0", 512, 4096)
+    lin("observableNetFC.2", E, 512)
+    sd["observableNetFC.3.weight"] = _f32(1.0 + 0.1 * rng.normal(size=E))
+    sd["observableNetFC.3.bias"] = _f32(0.1 * rng.normal(size=E))
+    lin("recoveryNetFC.0", 512, E)
+    lin("recoveryNetFC.2", 4096, 512)
+    for i, (cout, cin, k) in zip((0, 4, 8, 12), ((128, 64, 1), (128, 128, 3), (64, 128, 3), (64, 64, 3))):
+        conv(f"recoveryNet.{i}", cout, cin, k)
+        bn(f"recoveryNet.{i + 1}", cout)
+    conv("recoveryNet.15", 2, 64, 1)
+    return sd
+
+
+def grayscott_fields(n: int, seed: int = 0) -> np.ndarray:
+    """Synthetic [n, 2, 32, 32, 32] concentration fields in [0, 1] (smooth modes + noise)."""
+    rng = np.random.default_rng(seed)
+    ax = np.linspace(0, 2 * np.pi, 32, endpoint=False)
+    Z, Y, X = np.meshgrid(ax, ax, ax, indexing="ij")
+    out = np.empty((n, 2, 32, 32, 32))
+    for i in range(n):
+        for c in range(2):
+            k = rng.integers(1, 4, size=3)
+            ph = rng.uniform(0, 2 * np.pi, size=3)
+            out[i, c] = 0.5 + 0.3 * np.sin(k[0] * Z + ph[0]) * np.cos(k[1] * Y + ph[1]) * np.sin(k[2] * X + ph[2]) \
+                + 0.05 * rng.normal(size=(32, 32, 32))
+    return _f32(out)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -8,8 +8,8 @@ import torch
 
 from tests import synth
 from oracle import trpx_oracle as O
-from tests.golden.cases import LORENZ_CASES, CYL_CASES, TRAIN_CASES, CYL_TRAIN_CASES
-from tests.util import make_lorenz, make_cylinder, torch_sd
+from tests.golden.cases import LORENZ_CASES, CYL_CASES, TRAIN_CASES, CYL_TRAIN_CASES, GS_CASES
+from tests.util import make_lorenz, make_cylinder, make_grayscott, torch_sd
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -465,3 +465,52 @@ def test_fused_cylinder_step_equals_reference_loop(dev):
         g = m.embed(states[:, 0], visc)
     cur = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     assert O.rel_l2(g.cpu(), O.cylinder_embed(cur, cfg, states_c[:, 0], visc_c)) < TOL        # the kernels use the UPDATED weights
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Gray-Scott embedding: eval-mode network on the kernels of csrc/gs.cu
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(GS_CASES))
+def test_grayscott_embedding_matches_reference(golden_dir, dev, name):
+    c = GS_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"gs_{name}.npz"))
+    cfg = synth.make_config("grayscott")
+    m = make_grayscott(cfg, c["seed"], dev)
+    x = torch.from_numpy(synth.grayscott_fields(c["N"], seed=c["seed"])).to(dev)
+    with torch.no_grad():
+        g = m.embed(x)
+        assert O.rel_l2(g.cpu(), gold["embed"]) < TOL
+        rec = m.recover(g)
+        assert O.rel_l2(rec.cpu(), gold["recover"]) < TOL
+        fg, xhat, g0, out0, x2 = m(x)
+        assert torch.equal(fg, g)
+        assert O.rel_l2(g0.cpu(), gold["fwd_g0"]) < TOL
+        assert O.rel_l2(out0.cpu(), gold["fwd_out0"]) < TOL
+        assert O.rel_l2(xhat[:, 0].cpu(), gold["fwd_xhat_ch0"]) < TOL
+        assert O.rel_l2(x2[:, 1].cpu(), gold["fwd_x2_ch1"]) < TOL
+        assert O.rel_l2(m.koopmanOperation(g).cpu(), gold["koopman"]) < TOL
+        K = m.koopmanOperator
+        assert K.shape == (c["N"], cfg.n_embd, cfg.n_embd)
+        assert np.array_equal(K[0].cpu().numpy(), gold["kmatrix0"]) and torch.equal(K[0], K[-1])
+
+
+@pytest.mark.parametrize("N", [1, 19])
+def test_grayscott_vs_oracle_batches(dev, N):
+    """Ragged batch (more than one 16-frame chunk, a partial 8-sample Linear pass), a different seed, mu/std reassigned."""
+    cfg = synth.make_config("grayscott")
+    w = synth.grayscott_embedding_weights(cfg, 77)
+    m = make_grayscott(cfg, 77, dev)
+    m.mu = torch.tensor(0.45, device=dev)
+    m.std = torch.tensor(0.6, device=dev)
+    sd = O.to_torch(w)
+    sd["mu"], sd["std"] = torch.tensor(0.45), torch.tensor(0.6)
+    x = torch.from_numpy(synth.grayscott_fields(N, seed=5))
+    with torch.no_grad():
+        g = m.embed(x.to(dev))
+        g_ref = O.grayscott_embed(sd, cfg, x)
+        assert O.rel_l2(g.cpu(), g_ref) < TOL
+        assert O.rel_l2(m.recover(g).cpu(), O.grayscott_recover(sd, cfg, g_ref)) < TOL
+        assert O.rel_l2(m.koopmanOperation(g).cpu(), O.grayscott_koopman(sd, cfg, g_ref)) < TOL
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.embed(x.to(dev))

@@ -617,3 +617,18 @@ def test_forward_tensor_core_kernel(dev, kind, B, T, Tp):
             assert O.rel_l2(pres[l].cpu(), pres_ref[l]) < TOL
         outs[variant] = hid
     assert not torch.equal(outs[0], outs[1])          # really two kernels
+
+
+@pytest.mark.parametrize("B,S", [(3, 20), (150, 6)])
+def test_grayscott_transformer_rollout(dev, B, S):
+    """The Gray-Scott decoder stack (configuration_grayscott.py: n_embd 512, 32 heads of 16, 2 layers, n_ctx 128) through
+    the generic rollout kernel, both cache modes, against the oracle."""
+    cfg = synth.make_config("grayscott")
+    w_np = synth.gpt2_weights(cfg, 321, stress=True, stress_sigma=0.05)
+    m = make_gpt2(cfg, 321, True, dev, sigma=0.05)
+    x0 = torch.from_numpy(synth.normal_embeds((B, 1, cfg.n_embd), 91))
+    for uc in (True, False):
+        n, ref = stable_prefix(cfg, w_np, x0, S + 1, uc)
+        out = m.generate(x0.to(dev), max_length=S + 1, use_cache=uc)
+        assert m.last_launch()["variant"] == 1
+        assert n == S + 1 and O.rel_l2(out[0].cpu(), ref) < TOL

@@ -7,8 +7,8 @@ from tests import synth
 from oracle import ref_shim
 from tests.util import torch_sd
 from trphysx_b200 import AutoEmbeddingModel, AutoPhysConfig, AutoPhysTransformer, shard_bounds
-from trphysx_b200.config import CylinderConfig, LorenzConfig, PhysConfig, RosslerConfig
-from trphysx_b200.embedding import CylinderEmbedding, LorenzEmbedding, RosslerEmbedding
+from trphysx_b200.config import CylinderConfig, GrayScottConfig, LorenzConfig, PhysConfig, RosslerConfig
+from trphysx_b200.embedding import CylinderEmbedding, GrayScottEmbedding, LorenzEmbedding, RosslerEmbedding
 from trphysx_b200.transformer import PhysformerGPT2, PhysformerTrain
 from trphysx_b200.transformer.phys_transformer_gpt2 import position_table
 
@@ -58,6 +58,11 @@ def test_state_dict_keys_equal_reference():
     assert sig(PhysformerGPT2(CylinderConfig(), "x")) == sig(RG(RC(), "x"))
     assert sig(LorenzEmbedding(LorenzConfig())) == sig(RLE(RL()))
     assert sig(CylinderEmbedding(CylinderConfig())) == sig(RCE(RC()))
+    from trphysx.config.configuration_grayscott import GrayScottConfig as RGC
+    from trphysx.embedding.embedding_grayscott import GrayScottEmbedding as RGE
+    assert sig(GrayScottEmbedding(GrayScottConfig())) == sig(RGE(RGC()))
+    assert list(GrayScottEmbedding(GrayScottConfig()).state_dict()) == list(RGE(RGC()).state_dict())
+    assert vars(GrayScottConfig()).items() >= {k: v for k, v in vars(RGC()).items() if k in ("n_ctx", "n_embd", "n_layer", "n_head", "state_dims")}.items()
     # a reference config object is accepted as-is, and reference checkpoints load
     ours = PhysformerGPT2(RL(), "lorenz")
     ours.load_state_dict(RG(RL(), "lorenz").state_dict(), strict=True)
@@ -76,6 +81,11 @@ def test_registries_and_errors(tmp_path):
     with pytest.raises(KeyError):
         AutoEmbeddingModel.init_trainer("nope", LorenzConfig())
     assert isinstance(AutoEmbeddingModel.init_model("lorenz", LorenzConfig()), LorenzEmbedding)
+    gs = AutoEmbeddingModel.init_model("grayscott", AutoPhysConfig.load_config("grayscott"))
+    assert isinstance(gs, GrayScottEmbedding) and gs.model_name == "embedding_grayscott" and gs.embed_dims == 512
+    gs.load_state_dict(torch_sd(synth.grayscott_embedding_weights(synth.make_config("grayscott"), 3)), strict=True)
+    with pytest.raises(NotImplementedError):
+        AutoEmbeddingModel.init_trainer("grayscott", GrayScottConfig())(torch.zeros(1, 2, 2, 32, 32, 32))
     assert isinstance(AutoPhysTransformer.init_model("rossler"), PhysformerGPT2)
     m = AutoEmbeddingModel.init_model("lorenz", LorenzConfig())
     m.save_model(str(tmp_path), epoch=3)

@@ -9,7 +9,7 @@ import torch
 from tests import synth
 from oracle import trpx_oracle as O
 from tests.golden.cases import (weights_kw, GPT2_CASES, LORENZ_CASES, CYL_CASES, TRAIN_CASES, GPT2_TRAIN_CASES,
-                                CYL_TRAIN_CASES)
+                                CYL_TRAIN_CASES, GS_CASES)
 
 TOL = 2e-6          # both sides are torch-CPU fp32 executing the same aten ops; only threading differs
 
@@ -104,6 +104,27 @@ def test_cylinder_embedding_oracle(golden_dir, name):
     K, diag = O.cylinder_koopman_matrix(sd, cfg, visc)
     assert O.rel_l2(diag, gold["kdiag"]) < TOL
     assert O.rel_l2(K[0], gold["kmatrix0"]) < TOL
+
+
+@pytest.mark.parametrize("name", list(GS_CASES))
+def test_grayscott_embedding_oracle(golden_dir, name):
+    """Gray-Scott embedding (eval mode) restated in oracle/ against the unmodified reference's outputs."""
+    c = GS_CASES[name]
+    gold = _load(golden_dir, f"gs_{name}.npz")
+    cfg = synth.make_config("grayscott")
+    sd = O.to_torch(synth.grayscott_embedding_weights(cfg, c["seed"]))
+    x = torch.from_numpy(synth.grayscott_fields(c["N"], seed=c["seed"]))
+    g0 = O.grayscott_latent(sd, cfg, x)
+    assert O.rel_l2(g0, gold["fwd_g0"]) < 5 * TOL
+    g = O.grayscott_embed(sd, cfg, x)
+    assert O.rel_l2(g, gold["embed"]) < 5 * TOL
+    assert O.rel_l2(O.grayscott_recover_latent(sd, cfg, g), gold["fwd_out0"]) < 5 * TOL
+    rec = O.grayscott_recover(sd, cfg, g)
+    assert O.rel_l2(rec, gold["recover"]) < 5 * TOL
+    assert O.rel_l2(rec[:, 0], gold["fwd_xhat_ch0"]) < 5 * TOL
+    assert O.rel_l2(O.grayscott_decode_latent(sd, cfg, g0)[:, 1], gold["fwd_x2_ch1"]) < 5 * TOL
+    assert O.rel_l2(O.grayscott_koopman(sd, cfg, g), gold["koopman"]) < 5 * TOL
+    assert np.array_equal(O.grayscott_koopman_matrix(sd, cfg).numpy(), gold["kmatrix0"])
 
 
 @pytest.mark.parametrize("name", list(TRAIN_CASES))

@@ -37,6 +37,15 @@ def make_cylinder(cfg_ns, seed, device=None):
     return m.to(device) if device is not None else m
 
 
+def make_grayscott(cfg_ns, seed, device=None):
+    from trphysx_b200.config import PhysConfig
+    from trphysx_b200.embedding import GrayScottEmbedding
+    cfg = PhysConfig(**vars(cfg_ns))
+    m = GrayScottEmbedding(cfg).eval()
+    m.load_state_dict(torch_sd(synth.grayscott_embedding_weights(cfg_ns, seed)), strict=True)
+    return m.to(device) if device is not None else m
+
+
 _prefix_cache = {}
 
 

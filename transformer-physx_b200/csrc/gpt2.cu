@@ -2896,8 +2896,8 @@ extern "C" {
 
 int trpx_gpt2_create(const trpx_gpt2_config* cfg, int device, trpx_gpt2_t* out) {
     TRPX_REQUIRE(cfg != nullptr && out != nullptr, "trpx_gpt2_create: null argument");
-    TRPX_REQUIRE(cfg->n_embd > 0 && cfg->n_embd % 32 == 0 && cfg->n_embd <= 256,
-                 "n_embd=%d unsupported (multiple of 32, <= 256)", cfg->n_embd);
+    TRPX_REQUIRE(cfg->n_embd > 0 && cfg->n_embd % 32 == 0 && cfg->n_embd <= 512,
+                 "n_embd=%d unsupported (multiple of 32, <= 512)", cfg->n_embd);
     TRPX_REQUIRE(cfg->n_head > 0 && cfg->n_embd % cfg->n_head == 0, "n_embd %% n_head != 0");
     TRPX_REQUIRE(cfg->n_layer > 0 && cfg->n_layer <= 64, "n_layer=%d unsupported", cfg->n_layer);
     TRPX_REQUIRE(cfg->n_ctx > 0 && cfg->n_ctx <= 1024, "n_ctx=%d unsupported", cfg->n_ctx);

@@ -60,6 +60,14 @@ SIGNATURES = {
     "trpx_mlpemb_num_params": (c_longlong, [c_void_p]),
     "trpx_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_float, c_float,
                                c_float, c_float, c_float, c_void_p, c_int, c_void_p]),
+    "trpx_gs_create": (c_int, [c_int, c_float, c_int, POINTER(c_void_p)]),
+    "trpx_gs_destroy": (c_int, [c_void_p]),
+    "trpx_gs_num_weight_tensors": (c_int, [c_void_p]),
+    "trpx_gs_load_weights": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p]),
+    "trpx_gs_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "trpx_gs_recover": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "trpx_gs_decode_latent": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "trpx_gs_koopman": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "trpx_cyl_create": (c_int, [c_int, c_float, c_int, POINTER(c_void_p)]),
     "trpx_cyl_destroy": (c_int, [c_void_p]),
     "trpx_cyl_load_weights": (c_int, [c_void_p, PP, c_int, c_void_p]),

@@ -1,4 +1,4 @@
-from .configuration import (PhysConfig, LorenzConfig, RosslerConfig, CylinderConfig, AutoPhysConfig,
+from .configuration import (PhysConfig, LorenzConfig, RosslerConfig, CylinderConfig, GrayScottConfig, AutoPhysConfig,
                             CONFIG_MAPPING)
 
-__all__ = ["PhysConfig", "LorenzConfig", "RosslerConfig", "CylinderConfig", "AutoPhysConfig", "CONFIG_MAPPING"]
+__all__ = ["PhysConfig", "LorenzConfig", "RosslerConfig", "CylinderConfig", "GrayScottConfig", "AutoPhysConfig", "CONFIG_MAPPING"]

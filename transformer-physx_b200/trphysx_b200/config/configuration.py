@@ -88,7 +88,12 @@ RosslerConfig = _make("RosslerConfig", "rossler", n_ctx=32, n_embd=32, n_layer=4
 CylinderConfig = _make("CylinderConfig", "cylinder", n_ctx=16, n_embd=128, n_layer=6, n_head=4,
                        state_dims=[3, 64, 128], activation_function="gelu_new")
 
-CONFIG_MAPPING = OrderedDict([("lorenz", LorenzConfig), ("rossler", RosslerConfig), ("cylinder", CylinderConfig)])
+# configuration_grayscott.py:15-38 (its model_type really is "cylinder" in the reference)
+GrayScottConfig = _make("GrayScottConfig", "cylinder", n_ctx=128, n_embd=512, n_layer=2, n_head=32,
+                        state_dims=[2, 32, 32, 32], activation_function="gelu_new")
+
+CONFIG_MAPPING = OrderedDict([("lorenz", LorenzConfig), ("rossler", RosslerConfig), ("cylinder", CylinderConfig),
+                              ("grayscott", GrayScottConfig)])
 
 
 class AutoPhysConfig:

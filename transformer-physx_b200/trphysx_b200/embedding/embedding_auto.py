@@ -3,12 +3,14 @@ from collections import OrderedDict
 from typing import Optional
 
 from .embedding_cylinder import CylinderEmbedding, CylinderEmbeddingTrainer
+from .embedding_grayscott import GrayScottEmbedding, GrayScottEmbeddingTrainer
 from .embedding_lorenz import LorenzEmbedding, LorenzEmbeddingTrainer
 from .embedding_rossler import RosslerEmbedding, RosslerEmbeddingTrainer
 
-MODEL_MAPPING = OrderedDict([("lorenz", LorenzEmbedding), ("cylinder", CylinderEmbedding), ("rossler", RosslerEmbedding)])
+MODEL_MAPPING = OrderedDict([("lorenz", LorenzEmbedding), ("cylinder", CylinderEmbedding), ("grayscott", GrayScottEmbedding),
+                             ("rossler", RosslerEmbedding)])
 TRAINING_MAPPING = OrderedDict([("lorenz", LorenzEmbeddingTrainer), ("cylinder", CylinderEmbeddingTrainer),
-                                ("rossler", RosslerEmbeddingTrainer)])
+                                ("grayscott", GrayScottEmbeddingTrainer), ("rossler", RosslerEmbeddingTrainer)])
 
 
 class AutoEmbeddingModel:

@@ -617,6 +617,25 @@ def run_ours(args):
         torch.cuda.synchronize()
         nocache_ms = a.elapsed_time(b)
         nocache_launch = tr.last_launch()
+        # the same workload with the KV window ON CHIP (tensor memory, rollout variant 10): the measured prototype of
+        # BASELINE north_star's "KV cache in shared memory or registers" (profiles/README.md)
+        onchip = None
+        if rank == 0 and cfg.n_ctx in (32, 64) and cfg.n_layer <= 4:
+            tr.set_rollout_tuning(variant=10)
+            for _ in range(2):
+                tr.generate(g0, max_length=S + 1, use_cache=True, return_presents=False)
+            a, b = ev(), ev()
+            a.record()
+            tr.generate(g0, max_length=S + 1, use_cache=True, return_presents=False)
+            b.record()
+            torch.cuda.synchronize()
+            onchip = {"kernel": "rollout_e32t_kernel (KV window in tensor memory, tcgen05.st/ld; not selected automatically)",
+                      "kernel_ms": a.elapsed_time(b), "traj_steps_per_s": B * S / (a.elapsed_time(b) * 1e-3),
+                      "rollout_launch": tr.last_launch(),
+                      "hbm_bytes_per_launch_model": B * S * E * 4 + B * E * 4,
+                      "note": "HBM traffic = tokens only (ncu: profiles/r02_ncu_rollout_tmem.json); slower than the "
+                              "HBM-window kernel because 8 resident trajectories per SM force all warps onto one tile"}
+            tr.set_rollout_tuning()
         # embed / recover alone (median of 5)
         em, rc = [], []
         for _ in range(5):
@@ -711,6 +730,7 @@ def run_ours(args):
                                          "peak_source": "measured mma.sync TF32 rate in this run (trpx_probe_tf32_mma) / 3 "
                                                         "for the error-compensated 3xTF32 product",
                                          "vs_fp32_fma_peak": nc_tf / fp32.value}},
+        "onchip_window": onchip,
         "breakdown_ms": {"embed": embed_ms, "rollout": k_ms, "recover": recover_ms, "rollout_use_cache_false": nocache_ms},
         "probes": {"fp32_fma_tflops": fp32.value, "tf32_mma_sync_tflops": mma.value, "tf32_tcgen05_tflops": umma.value},
         "configs": extras,

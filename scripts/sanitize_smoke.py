@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "transformer-physx_b200")):
     sys.path.insert(0, p)
 import torch
 from tests import synth
-from tests.util import make_gpt2, make_lorenz, make_cylinder
+from tests.util import make_gpt2, make_lorenz, make_cylinder, make_grayscott
 
 dev = torch.device("cuda:0")
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -17,7 +17,7 @@ if which in ("all", "e32"):
         cfg = synth.make_config(kind)
         m = make_gpt2(cfg, 1, True, dev)
         x0 = torch.randn(37, 1, 32, device=dev)
-        for variant, g in ((2, 1), (2, 4), (2, 8), (3, 4), (5, 0), (6, 0), (8, 4), (1, 2)):
+        for variant, g in ((2, 1), (2, 4), (2, 8), (3, 4), (5, 0), (6, 0), (8, 4), (1, 2), (10, 0)):
             m.set_rollout_tuning(variant=variant, traj_per_warp=g)
             for uc in (True, False):
                 out = m.generate(x0, max_length=cfg.n_ctx + 9, use_cache=uc)
@@ -72,3 +72,24 @@ if which in ("all", "emb"):
     cyl.koopmanOperation(gc, visc)
     torch.cuda.synchronize()
     print("emb ok")
+if which in ("all", "gs"):
+    gcfg = synth.make_config("grayscott")
+    gs = make_grayscott(gcfg, 8, dev)
+    xg = torch.rand(3, 2, 32, 32, 32, device=dev)
+    with torch.no_grad():
+        outs = gs(xg)
+        gs.koopmanOperation(outs[0])
+        gs.koopmanOperator
+    tr = make_gpt2(gcfg, 9, True, dev)
+    tr.generate(outs[0].unsqueeze(1), max_length=6, use_cache=True)
+    torch.cuda.synchronize()
+    print("gs ok")
+if which in ("all", "cyl3"):
+    ccfg = synth.make_config("cylinder")
+    cyl = make_cylinder(ccfg, 6, dev)
+    xs = torch.randn(5, 3, 64, 128, device=dev)
+    visc = torch.rand(5, 1, device=dev) * 0.01 + 0.003
+    cyl.set_conv_mode(3)
+    cyl.recover(cyl.embed(xs, visc))
+    torch.cuda.synchronize()
+    print("cyl3 ok")

@@ -14,7 +14,9 @@
 #include "common.cuh"
 #include "gpt2_layout.cuh"
 #include "gpt2_handle.cuh"
+#include "gpt2_train_tc.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 using namespace trpx;
 
@@ -473,6 +475,27 @@ int trpx_gpt2_train_fwd_bwd(trpx_gpt2_t h, const float* x, const float* labels, 
     const Gpt2Layout& L = h->lay;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t TE = (size_t)T * L.E;
+    // E = 32 / 4 heads / T <= 64: every contraction on tensor cores (gpt2_train_tc.cu); TRPX_TRAIN_SIMT=1 keeps the FP32 kernel
+    const char* simt_env = getenv("TRPX_TRAIN_SIMT");
+    if (train_tc_supported(L, T) && !(simt_env && simt_env[0] == '1')) {
+        const size_t aps = train_tc_acts_per_seq(L, T);
+        const size_t need_tc = sizeof(float) * ((size_t)B * (aps + L.total + 1));
+        if (need_tc > h->train_ws_bytes) {
+            if (h->train_ws) TRPX_CUDA(cudaFree(h->train_ws));
+            h->train_ws = nullptr;
+            h->train_ws_bytes = 0;
+            TRPX_CUDA(cudaMalloc(&h->train_ws, need_tc));
+            h->train_ws_bytes = need_tc;
+        }
+        float* gpart = h->train_ws + (size_t)B * aps;
+        float* loss_part = gpart + (size_t)B * L.total;
+        int rc = launch_train_tc(L, h->blob, h->pe, x, labels, hidden_dev, h->train_ws, gpart, loss_part, B, T, h->cfg.ln_eps, st);
+        if (rc) return rc;
+        train_finalize_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(gpart, loss_part, grad_blob_dev, loss_dev, B, L.total,
+                                                                      1.0f / ((float)B * (float)T * (float)L.E));
+        TRPX_CUDA(cudaGetLastError());
+        return TRPX_OK;
+    }
     TRPX_REQUIRE(TE <= 2048, "training step supports T * n_embd <= 2048");   // unit counts of mm_xwT<MAXU>
     TRPX_REQUIRE((L.hd & (L.hd - 1)) == 0, "training step supports power-of-two head sizes");
     const size_t smem = sizeof(float) * (TE * 17 + ((size_t)std::max(T, TR_THREADS / 32) + T) * T + STAGE_FLOATS);

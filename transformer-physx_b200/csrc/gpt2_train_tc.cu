@@ -22,8 +22,8 @@ namespace {
 
 constexpr int TT = 256;                    // threads per CTA (8 warps)
 constexpr int TM = 64;                     // rows of the token tile
-constexpr int LDX = 36, LDQ = 100, LDH = 132, LDP = 65, PHS = 64 * LDP + 8;      // PHS: per-head stride of the P tiles
-constexpr int WORK = 17152;                // floats of the work region (two [64][132] tiles + 256)
+constexpr int LDX = 36, LDQ = 100, LDH = 132, LDP = 68, PHS = 64 * LDP + 8;      // PHS: per-head stride of the P tiles
+constexpr int WORK = 17472;                // floats of the work region: two [64][132] MLP tiles, or 4 score tiles, or the attention-backward set
 constexpr int SM_FLOATS = 2 * TM * LDX + TM * LDQ + WORK;
 
 __device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
@@ -38,59 +38,89 @@ __device__ __forceinline__ void mma_t(float (&c)[4], const uint32_t (&a)[4], uin
 
 // C[b][M x N] = A[b][M x K] * B[b][K x N] on tensor cores (3xTF32), b < nb:
 //   A element (m, k) = A[b*abs + m*ars + k*acs],  B element (k, n) = B[b*bbs + k*brs + n*bcs]   (shared or global memory)
-//   M = 16 * mtiles, N = 8 * ntiles, K = 8 * ksteps.  A unit = (batch, n-tile, group of MT m-tiles); units are dealt
-//   round-robin over the 8 warps, the B fragment of a k-step is split once per unit and reused for its MT m-tiles.
+//   M = 16 * mtiles, N = 8 * ntiles, K = 8 * KS; units are dealt round-robin over the 8 warps.
 //   epi(b, m, n, value) receives every element once.  All 256 threads must call; no synchronisation inside.
-template <int MT, int KS, class Epi>
+//   Register blocking: a unit = (batch, group of MT m-tiles, group of NTG n-tiles); per k-step the A fragments of the MT
+//   m-tiles and the B fragments of the NTG n-tiles are loaded and split ONCE and feed MT*NTG*3 MMAs (the first version,
+//   one n-tile per unit, spent 18 shared-memory loads and 54 split instructions per 12 MMAs and was MIO / issue bound).
+//   Fragment slot q of a k-step holds logical k = 2q (a0, a1, b0) and 2q+1 (a2, a3, b1): any permutation of k inside a
+//   k-step is a valid contraction order, and this one makes the two k of a slot ADJACENT, so an operand whose k runs along
+//   memory (AV: acs == 1, BV: brs == 1) is fetched with one 64-bit load per pair.
+//   B fragments are requested PF k-steps ahead (weights come from L2: shared memory leaves almost no L1).
+template <int MT, int NTG, int KS, bool AV, bool BV, class Epi>
 __device__ __forceinline__ void tc_gemm(const float* A, int abs_, int ars, int acs, const float* B, int bbs, int brs, int bcs,
                                         int nb, int mtiles, int ntiles, Epi epi, int wrot = 0) {
     // wrot rotates the warp -> unit assignment so that consecutive small calls of one phase land on different warps
     const int warp = ((threadIdx.x >> 5) + 8 - wrot) & 7, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int mgroups = mtiles / MT;
-    const int units = nb * ntiles * mgroups;
+    constexpr int PF = KS < 3 ? KS : 3;
+    const int mgroups = mtiles / MT, ngroups = ntiles / NTG;
+    const int units = nb * mgroups * ngroups;
     for (int u = warp; u < units; u += TT / 32) {
-        const int nt = u % ntiles, r = u / ntiles, mg = r % mgroups, b = r / mgroups;
-        const float* Ab = A + (size_t)b * abs_ + (size_t)(mg * MT * 16 + g) * ars + q * acs;
-        const float* Bb = B + (size_t)b * bbs + (size_t)q * brs + (size_t)(nt * 8 + g) * bcs;
-        // the unit's B fragments first, all loads in flight together: the weights come from L2 (shared memory leaves
-        // almost no L1), and one exposed L2 latency per k-step was what bounded the first version
-        float bw[KS][2];
+        const int ng = u % ngroups, r = u / ngroups, mg = r % mgroups, b = r / mgroups;
+        const float* Ab = A + (size_t)b * abs_ + (size_t)(mg * MT * 16 + g) * ars + (size_t)(2 * q) * acs;
+        const float* Bb = B + (size_t)b * bbs + (size_t)(2 * q) * brs + (size_t)(ng * NTG * 8 + g) * bcs;
+        float bw[PF][NTG][2];
+        auto load_b = [&](int ks, float (&dst)[NTG][2]) {
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++) {
-            bw[ks][0] = Bb[(size_t)(8 * ks) * brs];
-            bw[ks][1] = Bb[(size_t)(8 * ks + 4) * brs];
-        }
-        float acc[MT][4], acx[MT][4];                // main (hi*hi) and correction (lo*hi + hi*lo) chains
+            for (int j = 0; j < NTG; j++) {
+                const float* bp = Bb + (size_t)(8 * ks) * brs + (size_t)(8 * j) * bcs;
+                if constexpr (BV) {
+                    const float2 v = *reinterpret_cast<const float2*>(bp);
+                    dst[j][0] = v.x; dst[j][1] = v.y;
+                } else {
+                    dst[j][0] = bp[0]; dst[j][1] = bp[brs];
+                }
+            }
+        };
+#pragma unroll
+        for (int ks = 0; ks < PF; ks++) load_b(ks, bw[ks]);
+        float acc[MT][NTG][4];
 #pragma unroll
         for (int i = 0; i < MT; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) { acc[i][j] = 0.f; acx[i][j] = 0.f; }
+            for (int j = 0; j < NTG; j++) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
-            uint32_t bh0, bl0, bh1, bl1;
-            split3(bw[ks][0], bh0, bl0);
-            split3(bw[ks][1], bh1, bl1);
+            uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
             for (int i = 0; i < MT; i++) {
                 const float* ap = Ab + (size_t)(16 * i) * ars + (size_t)(8 * ks) * acs;
-                uint32_t ah[4], al[4];
-                split3(ap[0], ah[0], al[0]);
-                split3(ap[8 * ars], ah[1], al[1]);
-                split3(ap[4 * acs], ah[2], al[2]);
-                split3(ap[8 * ars + 4 * acs], ah[3], al[3]);
-                mma_t(acx[i], al, bh0, bh1);
-                mma_t(acx[i], ah, bl0, bl1);
-                mma_t(acc[i], ah, bh0, bh1);
+                float a0, a1, a2, a3;
+                if constexpr (AV) {
+                    const float2 lo2 = *reinterpret_cast<const float2*>(ap), hi2 = *reinterpret_cast<const float2*>(ap + 8 * ars);
+                    a0 = lo2.x; a2 = lo2.y; a1 = hi2.x; a3 = hi2.y;
+                } else {
+                    a0 = ap[0]; a1 = ap[8 * ars]; a2 = ap[acs]; a3 = ap[8 * ars + acs];
+                }
+                split3(a0, ah[i][0], al[i][0]);
+                split3(a1, ah[i][1], al[i][1]);
+                split3(a2, ah[i][2], al[i][2]);
+                split3(a3, ah[i][3], al[i][3]);
             }
+#pragma unroll
+            for (int j = 0; j < NTG; j++) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split3(bw[ks % PF][j][0], bh0, bl0);
+                split3(bw[ks % PF][j][1], bh1, bl1);
+#pragma unroll
+                for (int i = 0; i < MT; i++) {
+                    mma_t(acc[i][j], al[i], bh0, bh1);
+                    mma_t(acc[i][j], ah[i], bl0, bl1);
+                    mma_t(acc[i][j], ah[i], bh0, bh1);
+                }
+            }
+            if (ks + PF < KS) load_b(ks + PF, bw[ks % PF]);
         }
 #pragma unroll
-        for (int i = 0; i < MT; i++) {
-            const int m = (mg * MT + i) * 16 + g, n = nt * 8 + 2 * q;
-            epi(b, m, n, acc[i][0] + acx[i][0]);
-            epi(b, m, n + 1, acc[i][1] + acx[i][1]);
-            epi(b, m + 8, n, acc[i][2] + acx[i][2]);
-            epi(b, m + 8, n + 1, acc[i][3] + acx[i][3]);
-        }
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NTG; j++) {
+                const int m = (mg * MT + i) * 16 + g, n = (ng * NTG + j) * 8 + 2 * q;
+                epi(b, m, n, acc[i][j][0]);
+                epi(b, m, n + 1, acc[i][j][1]);
+                epi(b, m + 8, n, acc[i][j][2]);
+                epi(b, m + 8, n + 1, acc[i][j][3]);
+            }
     }
 }
 
@@ -301,21 +331,21 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         __syncthreads();
         {
             const float* bias = w + L.bqkv;
-            tc_gemm<2, 4>(A, 0, LDX, 1, w + L.wqkv, 0, 3 * E, 1, 1, 4, 12,[&](int, int m, int n, float v) { QKV[m * LDQ + n] = v + __ldg(bias + n); });
+            tc_gemm<2, 3, 4, true, false>(A, 0, LDX, 1, w + L.wqkv, 0, 3 * E, 1, 1, 4, 12,[&](int, int m, int n, float v) { QKV[m * LDQ + n] = v + __ldg(bias + n); });
         }
         __syncthreads();
         tile_save(sv + TE, QKV, LDQ, T, 3 * E);
         // scores of the 4 heads at once: S_h = Q_h K_h^T (log2 domain) into the work region
-        tc_gemm<4, 1>(QKV, HD, LDQ, 1, QKV + E, HD, 1, LDQ, H, 4, 8,[&](int hh, int m, int n, float v) { Wk[hh * PHS + m * LDP + n] = v * qscale; });
+        tc_gemm<2, 4, 1, true, true>(QKV, HD, LDQ, 1, QKV + E, HD, 1, LDQ, H, 4, 8,[&](int hh, int m, int n, float v) { Wk[hh * PHS + m * LDP + n] = v * qscale; });
         __syncthreads();
         softmax_rows(Wk, H, T);
         __syncthreads();
-        tc_gemm<2, 8>(Wk, PHS, LDP, 1, QKV + 2 * E, HD, LDQ, 1, H, 4, 1,[&](int hh, int m, int n, float v) { A[m * LDX + hh * HD + n] = v; });
+        tc_gemm<2, 1, 8, true, false>(Wk, PHS, LDP, 1, QKV + 2 * E, HD, LDQ, 1, H, 4, 1,[&](int hh, int m, int n, float v) { A[m * LDX + hh * HD + n] = v; });
         __syncthreads();
         tile_save(sv + 4 * TE, A, LDX, T, E);
         {
             const float* bias = w + L.bproj;
-            tc_gemm<2, 4>(A, 0, LDX, 1, w + L.wproj, 0, E, 1, 1, 4, 4,[&](int, int m, int n, float v) { X[m * LDX + n] += v + __ldg(bias + n); });
+            tc_gemm<1, 2, 4, true, false>(A, 0, LDX, 1, w + L.wproj, 0, E, 1, 1, 4, 4,[&](int, int m, int n, float v) { X[m * LDX + n] += v + __ldg(bias + n); });
         }
         __syncthreads();
         tile_save(sv + 5 * TE, X, LDX, T, E);
@@ -324,7 +354,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         {
             const float* bias = w + L.bfc;
             float* fsave = sv + 6 * TE;
-            tc_gemm<4, 4>(A, 0, LDX, 1, w + L.wfc, 0, 4 * E, 1, 1, 4, 16,[&](int, int m, int n, float v) {
+            tc_gemm<2, 4, 4, true, false>(A, 0, LDX, 1, w + L.wfc, 0, 4 * E, 1, 1, 4, 16,[&](int, int m, int n, float v) {
                 const float f = v + __ldg(bias + n);
                 if (m < T) fsave[(size_t)m * 4 * E + n] = f;
                 H2[m * LDH + n] = gelu_new(f);
@@ -333,7 +363,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         __syncthreads();
         {
             const float* bias = w + L.bpr;
-            tc_gemm<2, 16>(H2, 0, LDH, 1, w + L.wpr, 0, E, 1, 1, 4, 4,[&](int, int m, int n, float v) { X[m * LDX + n] += v + __ldg(bias + n); });
+            tc_gemm<1, 2, 16, true, false>(H2, 0, LDH, 1, w + L.wpr, 0, E, 1, 1, 4, 4,[&](int, int m, int n, float v) { X[m * LDX + n] += v + __ldg(bias + n); });
         }
         __syncthreads();
     }
@@ -347,7 +377,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
     float lsum = 0.f;
     {
         const float* bias = p.blob + L.bf;
-        tc_gemm<2, 4>(A, 0, LDX, 1, p.blob + L.wf, 0, E, 1, 1, 4, 4,[&](int, int m, int n, float v) {
+        tc_gemm<1, 2, 4, true, false>(A, 0, LDX, 1, p.blob + L.wf, 0, E, 1, 1, 4, 4,[&](int, int m, int n, float v) {
             float d = 0.f;
             if (m < T) {
                 const float y = v + __ldg(bias + n);
@@ -372,9 +402,9 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
     // head: y = a_f Wf + bf (blob wf is [in][out]); a_f = LN_f(h_L) is in A, dY in H1 (ld 36), h_L in X
     {
         float* gwf = gp + L.wf;
-        tc_gemm<1, 8>(A, 0, 1, LDX, H1, 0, LDX, 1, 1, 2, 4,[&](int, int m, int n, float v) { gwf[m * E + n] = v; });
+        tc_gemm<1, 1, 8, false, false>(A, 0, 1, LDX, H1, 0, LDX, 1, 1, 2, 4,[&](int, int m, int n, float v) { gwf[m * E + n] = v; });
         colsum(H1, LDX, E, gp + L.bf);
-        tc_gemm<2, 4>(H1, 0, LDX, 1, p.blob + L.wf, 0, 1, E, 1, 4, 4,[&](int, int m, int n, float v) { H2[m * LDX + n] = v; });
+        tc_gemm<1, 2, 4, true, true>(H1, 0, LDX, 1, p.blob + L.wf, 0, 1, E, 1, 4, 4,[&](int, int m, int n, float v) { H2[m * LDX + n] = v; });
     }
     __syncthreads();
     // X (h_L) -> dh in place: ln_bwd reads Xin and writes dH row by row, each lane its own element
@@ -398,21 +428,21 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         __syncthreads();
         {
             float* gw = g + L.wpr;                          // dWpr = gelu_out^T dh   [128][32]
-            tc_gemm<4, 8>(H2, 0, 1, LDH, X, 0, LDX, 1, 1, 8, 4,[&](int, int m, int n, float v) { gw[m * E + n] = v; });
+            tc_gemm<2, 2, 8, false, false>(H2, 0, 1, LDH, X, 0, LDX, 1, 1, 8, 4,[&](int, int m, int n, float v) { gw[m * E + n] = v; });
             colsum(X, LDX, E, g + L.bpr);
         }
         __syncthreads();
         // d fc_pre = (dh Wpr^T) * gelu'(fc_pre) -> H2
-        tc_gemm<4, 4>(X, 0, LDX, 1, w + L.wpr, 0, 1, E, 1, 4, 16,[&](int, int m, int n, float v) { H2[m * LDH + n] = v * gelu_grad(H1[m * LDH + n]); });
+        tc_gemm<2, 4, 4, true, true>(X, 0, LDX, 1, w + L.wpr, 0, 1, E, 1, 4, 16,[&](int, int m, int n, float v) { H2[m * LDH + n] = v * gelu_grad(H1[m * LDH + n]); });
         __syncthreads();
         {
             float* gw = g + L.wfc;                          // dWfc = a2^T d_fc   [32][128]
-            tc_gemm<2, 8>(LNO, 0, 1, LDX, H2, 0, LDH, 1, 1, 2, 16,[&](int, int m, int n, float v) { gw[m * 4 * E + n] = v; });
+            tc_gemm<2, 2, 8, false, false>(LNO, 0, 1, LDX, H2, 0, LDH, 1, 1, 2, 16,[&](int, int m, int n, float v) { gw[m * 4 * E + n] = v; });
             colsum(H2, LDH, 4 * E, g + L.bfc);
             // d a2 = d_fc Wfc^T -> H1 (ld 36); fc_pre is no longer needed
         }
         __syncthreads();
-        tc_gemm<2, 16>(H2, 0, LDH, 1, w + L.wfc, 0, 1, 4 * E, 1, 4, 4,[&](int, int m, int n, float v) { H1[m * LDX + n] = v; });
+        tc_gemm<1, 2, 16, true, true>(H2, 0, LDH, 1, w + L.wfc, 0, 1, 4 * E, 1, 4, 4,[&](int, int m, int n, float v) { H1[m * LDX + n] = v; });
         __syncthreads();
         ln_bwd_tile(X, true, A, H1, LDX, w + L.ln2w, g + L.ln2w, g + L.ln2b, p.eps, H2);                   // d_fc is dead
         __syncthreads();
@@ -427,9 +457,9 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         float* dSh = Ph + TM * LDP;                        // [64][65]  dP, then dS
         {
             float* gw = g + L.wproj;                        // dWproj = att^T dh
-            tc_gemm<1, 8>(A, 0, 1, LDX, X, 0, LDX, 1, 1, 2, 4,[&](int, int m, int n, float v) { gw[m * E + n] = v; });
+            tc_gemm<1, 1, 8, false, false>(A, 0, 1, LDX, X, 0, LDX, 1, 1, 2, 4,[&](int, int m, int n, float v) { gw[m * E + n] = v; });
             colsum(X, LDX, E, g + L.bproj);
-            tc_gemm<2, 4>(X, 0, LDX, 1, w + L.wproj, 0, 1, E, 1, 4, 4,[&](int, int m, int n, float v) { dAtt[m * LDX + n] = v; });
+            tc_gemm<1, 2, 4, true, true>(X, 0, LDX, 1, w + L.wproj, 0, 1, E, 1, 4, 4,[&](int, int m, int n, float v) { dAtt[m * LDX + n] = v; });
         }
         __syncthreads();
         for (int hh = 0; hh < H; hh++) {
@@ -438,8 +468,8 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
             const float* Vh = QKV + 2 * E + hh * HD;
             const float* dOh = dAtt + hh * HD;
             // S = Q K^T (log2 domain) -> Ph ; dP = dO V^T -> dSh
-            tc_gemm<4, 1>(Qh, 0, LDQ, 1, Kh, 0, 1, LDQ, 1, 4, 8,[&](int, int m, int n, float v) { Ph[m * LDP + n] = v * qscale; });
-            tc_gemm<4, 1>(dOh, 0, LDX, 1, Vh, 0, 1, LDQ, 1, 4, 8,[&](int, int m, int n, float v) { dSh[m * LDP + n] = v; });
+            tc_gemm<2, 4, 1, true, true>(Qh, 0, LDQ, 1, Kh, 0, 1, LDQ, 1, 4, 8,[&](int, int m, int n, float v) { Ph[m * LDP + n] = v * qscale; });
+            tc_gemm<2, 4, 1, true, true>(dOh, 0, LDX, 1, Vh, 0, 1, LDQ, 1, 4, 8,[&](int, int m, int n, float v) { dSh[m * LDP + n] = v; }, 4);
             __syncthreads();
             // rows: P = softmax(S) (causal), dS = P (dP - sum_j P dP) / sqrt(hd); 4 lanes per row (rows >= T: all zero;
             // no branch around the shuffles)
@@ -480,9 +510,9 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
             }
             __syncthreads();
             // dQ = dS K ; dK = dS^T Q ; dV = P^T dO
-            tc_gemm<1, 8>(dSh, 0, LDP, 1, Kh, 0, LDQ, 1, 1, 4, 1,[&](int, int m, int n, float v) { D3[m * LDQ + hh * HD + n] = v; });
-            tc_gemm<1, 8>(dSh, 0, 1, LDP, Qh, 0, LDQ, 1, 1, 4, 1,[&](int, int m, int n, float v) { D3[m * LDQ + E + hh * HD + n] = v; }, 4);
-            tc_gemm<1, 8>(Ph, 0, 1, LDP, dOh, 0, LDX, 1, 1, 4, 1,[&](int, int m, int n, float v) { D3[m * LDQ + 2 * E + hh * HD + n] = v; });
+            tc_gemm<1, 1, 8, true, false>(dSh, 0, LDP, 1, Kh, 0, LDQ, 1, 1, 4, 1,[&](int, int m, int n, float v) { D3[m * LDQ + hh * HD + n] = v; });
+            tc_gemm<1, 1, 8, false, false>(dSh, 0, 1, LDP, Qh, 0, LDQ, 1, 1, 4, 1,[&](int, int m, int n, float v) { D3[m * LDQ + E + hh * HD + n] = v; }, 4);
+            tc_gemm<1, 1, 8, false, false>(Ph, 0, 1, LDP, dOh, 0, LDX, 1, 1, 4, 1,[&](int, int m, int n, float v) { D3[m * LDQ + 2 * E + hh * HD + n] = v; });
             __syncthreads();
         }
         // ---- q | k | v = a1 Wqkv + bqkv ; a1 = LN1(x_in) ----
@@ -493,10 +523,10 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         __syncthreads();
         {
             float* gw = g + L.wqkv;                         // dWqkv = a1^T d(qkv)   [32][96]
-            tc_gemm<2, 8>(LNO, 0, 1, LDX, D3, 0, LDQ, 1, 1, 2, 12,[&](int, int m, int n, float v) { gw[m * 3 * E + n] = v; });
+            tc_gemm<1, 3, 8, false, false>(LNO, 0, 1, LDX, D3, 0, LDQ, 1, 1, 2, 12,[&](int, int m, int n, float v) { gw[m * 3 * E + n] = v; });
             colsum(D3, LDQ, 3 * E, g + L.bqkv);
             float* dA1 = Ph;                                // [64][36] (the score tiles are dead)
-            tc_gemm<2, 12>(D3, 0, LDQ, 1, w + L.wqkv, 0, 1, 3 * E, 1, 4, 4,[&](int, int m, int n, float v) { dA1[m * LDX + n] = v; });
+            tc_gemm<1, 2, 12, true, true>(D3, 0, LDQ, 1, w + L.wqkv, 0, 1, 3 * E, 1, 4, 4,[&](int, int m, int n, float v) { dA1[m * LDX + n] = v; });
         }
         __syncthreads();
         ln_bwd_tile(X, true, A, Ph, LDX, w + L.ln1w, g + L.ln1w, g + L.ln1b, p.eps, D3);                   // d(qkv) is dead

@@ -419,6 +419,36 @@ def record_forward(dev, fp32_peak):
     return out
 
 
+def record_transformer_train(dev, mma_peak):
+    """Teacher-forced transformer training step: fused forward + backward of PhysformerTrain.forward for 1,024
+    Lorenz sequences of 64 tokens; the tensor-core kernel (every contraction a 3xTF32 mma.sync tile product) beside the
+    FP32 SIMT kernel it replaces (TRPX_TRAIN_SIMT=1)."""
+    from tests import synth
+    from tests.util import make_gpt2
+    cfg = synth.make_config("lorenz")
+    m = make_gpt2(cfg, 19, False, dev)
+    B, T = 1024, 64
+    x = torch.randn(B, T, cfg.n_embd, device=dev)
+    y = torch.randn(B, T, cfg.n_embd, device=dev)
+    fwd = B * T * cfg.n_layer * (24 * 32 * 32 + 4 * (T / 2) * 32) + B * T * 2 * 32 * 32
+    flops = 3 * fwd                                     # forward + the two backward products of every contraction
+    out = {"workload": f"lorenz transformer training step B={B} T={T}: fused forward + backward (loss and all gradients)"}
+    for env, key in (("0", "train_e32_tc_kernel"), ("1", "train_fwd_bwd_kernel")):
+        os.environ["TRPX_TRAIN_SIMT"] = env
+        ms = timed_ms(lambda: m.fused_loss_and_grads(x, y), 5, 2)
+        out[key] = {"ms": ms, "tokens_per_s": B * T / (ms * 1e-3), "tflops": flops / (ms * 1e-3) / 1e12}
+    os.environ["TRPX_TRAIN_SIMT"] = "0"
+    tf = out["train_e32_tc_kernel"]["tflops"]
+    out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": mma_peak / 3.0, "unit": "TFLOP/s", "frac": tf / (mma_peak / 3.0),
+                       "peak_source": "measured mma.sync TF32 rate in this run (trpx_probe_tf32_mma) / 3 for the error-compensated "
+                                      "3xTF32 product",
+                       "note": "algorithmic FLOPs = 3 x forward (n_layer*(24E^2 + 4*(T/2)*E) + 2E^2 per token); the kernel is a "
+                               "chain of ~35 small tile products per layer and sequence separated by CTA barriers, two sequences "
+                               "per SM: latency bound (ncu: profiles/README.md)"}
+    out["speedup_vs_simt"] = out["train_fwd_bwd_kernel"]["ms"] / out["train_e32_tc_kernel"]["ms"]
+    return out
+
+
 def extra_records(args, dev, world, rank, flush, peaks, fp32_peak, umma_peak):
     """Every other BASELINE config, measured in this run.  All ranks execute this (the training step has a collective)."""
     import torch.distributed as dist
@@ -467,6 +497,7 @@ def extra_records(args, dev, world, rank, flush, peaks, fp32_peak, umma_peak):
                                     f"({groups / max(slots, 1):.2f} waves) + fixed embed/recover launches"}
     if rank == 0 and not args.no_configs:
         rec["forward_teacher_forced"] = record_forward(dev, fp32_peak)
+        rec["transformer_train_step"] = record_transformer_train(dev, peaks.get("_mma_sync_tf32", 278.0))
         rec["lorenz256"] = record_lorenz(dev, "lorenz", 256, 128, flush, peaks, fp32_peak)
         rec["lorenz_sweep"] = [record_lorenz(dev, "lorenz", B, S, flush, peaks, fp32_peak, e2e=False)
                                for B, S in ((1024, 64), (65536, 256), (262144, 128))]
@@ -659,6 +690,8 @@ def run_ours(args):
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
+    peaks = dict(peaks)
+    peaks["_mma_sync_tf32"] = mma.value
     extras = extra_records(args, dev, world, rank, flush, peaks, fp32.value, umma.value)
 
     if rank != 0:

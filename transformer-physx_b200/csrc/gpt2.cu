@@ -3252,8 +3252,12 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
     // ---- generic kernel ----
     int G = h->tune_g;
     if (G == 0) {
+        // every CTA re-streams all weights each step, so few large groups amortise them; but a step is a latency chain,
+        // and one trajectory per CTA is the fastest step (measured, Cylinder: 126 us against 153 us for G = 2 / 4 and
+        // 282 us for G = 8) as long as every CTA gets its own SM
         G = 8;
-        while (G > 1 && (B + G - 1) / G < h->sm_count / 2) G >>= 1;   // every CTA re-streams all weights each step
+        while (G > 1 && (B + G - 1) / G < h->sm_count / 2) G >>= 1;
+        if (B <= h->sm_count) G = 1;
     }
     size_t smem = generic_rollout_smem(L, G);
     while (G > 1 && smem > (size_t)h->smem_optin) {

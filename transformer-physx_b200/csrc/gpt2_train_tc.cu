@@ -124,12 +124,15 @@ __device__ __forceinline__ void tc_gemm(const float* A, int abs_, int ars, int a
     }
 }
 
-__device__ __forceinline__ float gelu_grad(float x) {
-    // d/dx [0.5 x (1 + tanh(u))], u = c (x + 0.044715 x^3)     (transformer/utils.py:57-60)
+// gelu_new and its derivative in sigmoid form (0.5 x (1 + tanh u) == x sigma(2u), u = c (x + 0.044715 x^3);
+// transformer/utils.py:57-60): one __expf + one division for both, relative deviation ~1e-7.
+__device__ __forceinline__ void gelu_and_grad(float x, float& gval, float& grad) {
     const float c = 0.7978845608028654f;
-    const float u = c * (x + 0.044715f * x * x * x);
-    const float t = tanhf(u);
-    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * (1.0f + 3.0f * 0.044715f * x * x);
+    const float x2 = x * x;
+    const float u2 = 2.0f * c * x * (1.0f + 0.044715f * x2);
+    const float sg = __fdividef(1.0f, 1.0f + __expf(-u2));
+    gval = x * sg;
+    grad = sg + x * sg * (1.0f - sg) * (2.0f * c) * (1.0f + 3.0f * 0.044715f * x2);
 }
 
 // LayerNorm over the 64 rows of a tile, all rows at once: thread = (row tid >> 2, quarter tid & 3) owns 8 channels
@@ -259,6 +262,12 @@ __device__ __forceinline__ void tile_fetch(float* dst, int ld, const float* __re
 }
 __device__ __forceinline__ void tile_fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Pull a weight matrix into L1 ahead of the tile product that reads it (fire and forget, one 128-byte line per thread):
+// with 2 x 111 KB of shared memory per SM only ~28 KB of L1 are left, so weights otherwise come from L2 on every use.
+__device__ __forceinline__ void prefetch_l1(const float* p, int nfloats) {
+    for (int i = threadIdx.x * 32; i < nfloats; i += TT * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
+}
+
 struct TcParams {
     const float* blob;
     const float* pe;
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
     for (int l = 0; l < NL; l++) {
         const float* w = p.blob + (size_t)l * L.layer_stride;
         float* sv = acts + l * per_layer;
+        prefetch_l1(w + L.wqkv, 3 * E * E);
         tile_save(sv, X, LDX, T, E);
         ln_fwd_tile(X, LDX, A, LDX, w + L.ln1w, w + L.ln1b, p.eps);
         __syncthreads();
@@ -335,6 +345,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         }
         __syncthreads();
         tile_save(sv + TE, QKV, LDQ, T, 3 * E);
+        prefetch_l1(w + L.wproj, E * E);
         // scores of the 4 heads at once: S_h = Q_h K_h^T (log2 domain) into the work region
         tc_gemm<2, 4, 1, true, true>(QKV, HD, LDQ, 1, QKV + E, HD, 1, LDQ, H, 4, 8,[&](int hh, int m, int n, float v) { Wk[hh * PHS + m * LDP + n] = v * qscale; });
         __syncthreads();
@@ -343,12 +354,14 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         tc_gemm<2, 1, 8, true, false>(Wk, PHS, LDP, 1, QKV + 2 * E, HD, LDQ, 1, H, 4, 1,[&](int hh, int m, int n, float v) { A[m * LDX + hh * HD + n] = v; });
         __syncthreads();
         tile_save(sv + 4 * TE, A, LDX, T, E);
+        prefetch_l1(w + L.wfc, 4 * E * E);
         {
             const float* bias = w + L.bproj;
             tc_gemm<1, 2, 4, true, false>(A, 0, LDX, 1, w + L.wproj, 0, E, 1, 1, 4, 4,[&](int, int m, int n, float v) { X[m * LDX + n] += v + __ldg(bias + n); });
         }
         __syncthreads();
         tile_save(sv + 5 * TE, X, LDX, T, E);
+        prefetch_l1(w + L.wpr, 4 * E * E);
         ln_fwd_tile(X, LDX, A, LDX, w + L.ln2w, w + L.ln2b, p.eps);
         __syncthreads();
         {
@@ -357,7 +370,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
             tc_gemm<2, 4, 4, true, false>(A, 0, LDX, 1, w + L.wfc, 0, 4 * E, 1, 1, 4, 16,[&](int, int m, int n, float v) {
                 const float f = v + __ldg(bias + n);
                 if (m < T) fsave[(size_t)m * 4 * E + n] = f;
-                H2[m * LDH + n] = gelu_new(f);
+                H2[m * LDH + n] = gelu_new_sig(f);
             });
         }
         __syncthreads();
@@ -416,24 +429,29 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         const float* sv = acts + l * per_layer;
         float* LNO = QKV;                                  // [64][36] LayerNorm output of this phase
         // ---- MLP: out = x_mid + gelu(fc_pre) Wpr + bpr ; fc_pre = a2 Wfc + bfc ; a2 = LN2(x_mid) ----
+        prefetch_l1(w + L.wpr, 4 * E * E);
         tile_fetch(H1, LDH, sv + 6 * TE, T, 4 * E);       // fc_pre
         tile_fetch(A, LDX, sv + 5 * TE, T, E);            // x_mid
         tile_fetch_wait();
         __syncthreads();
         for (int i = tid; i < TM * 4 * E; i += TT) {
             const int r = i >> 7, c = i & 127;
-            H2[r * LDH + c] = gelu_new(H1[r * LDH + c]);
+            float gv, gd;
+            gelu_and_grad(H1[r * LDH + c], gv, gd);
+            H2[r * LDH + c] = gv;                          // gelu(fc_pre)
+            H1[r * LDH + c] = gd;                          // gelu'(fc_pre), consumed by the d fc_pre epilogue
         }
         ln_fwd_tile(A, LDX, LNO, LDX, w + L.ln2w, w + L.ln2b, p.eps);
         __syncthreads();
         {
+            prefetch_l1(w + L.wfc, 4 * E * E);
             float* gw = g + L.wpr;                          // dWpr = gelu_out^T dh   [128][32]
             tc_gemm<2, 2, 8, false, false>(H2, 0, 1, LDH, X, 0, LDX, 1, 1, 8, 4,[&](int, int m, int n, float v) { gw[m * E + n] = v; });
             colsum(X, LDX, E, g + L.bpr);
         }
         __syncthreads();
         // d fc_pre = (dh Wpr^T) * gelu'(fc_pre) -> H2
-        tc_gemm<2, 4, 4, true, true>(X, 0, LDX, 1, w + L.wpr, 0, 1, E, 1, 4, 16,[&](int, int m, int n, float v) { H2[m * LDH + n] = v * gelu_grad(H1[m * LDH + n]); });
+        tc_gemm<2, 4, 4, true, true>(X, 0, LDX, 1, w + L.wpr, 0, 1, E, 1, 4, 16,[&](int, int m, int n, float v) { H2[m * LDH + n] = v * H1[m * LDH + n]; });
         __syncthreads();
         {
             float* gw = g + L.wfc;                          // dWfc = a2^T d_fc   [32][128]
@@ -447,6 +465,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
         ln_bwd_tile(X, true, A, H1, LDX, w + L.ln2w, g + L.ln2w, g + L.ln2b, p.eps, H2);                   // d_fc is dead
         __syncthreads();
         // ---- attention block: x_mid = x_in + att Wproj + bproj ----
+        prefetch_l1(w + L.wproj, E * E);
         tile_fetch(A, LDX, sv + 4 * TE, T, E);            // att
         tile_fetch(QKV, LDQ, sv + TE, T, 3 * E);          // q | k | v
         tile_fetch_wait();
@@ -516,6 +535,7 @@ __global__ void __launch_bounds__(TT, 2) train_e32_tc_kernel(TcParams p) {
             __syncthreads();
         }
         // ---- q | k | v = a1 Wqkv + bqkv ; a1 = LN1(x_in) ----
+        prefetch_l1(w + L.wqkv, 3 * E * E);
         tile_fetch(A, LDX, sv, T, E);                      // x_in
         tile_fetch_wait();
         __syncthreads();

@@ -298,11 +298,20 @@ def record_lorenz(dev, kind, B, S, flush, peaks, fp32_peak, e2e=True):
     hbm = peaks.get("hbm_gbs", 6650.0)
     gbs, tf = wbytes / (k_ms * 1e-3) / 1e9, flops / (k_ms * 1e-3) / 1e12
     sm_fill = launch["grid"] * launch["block"] / 32.0 / (148 * 8)
-    rec["roofline"] = {"bound": "hbm" if B >= 4096 else "latency", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                       "fp32_view": {"achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak},
-                       "note": ("KV-window stream model (bench.py window_bytes_per_traj)" if B >= 4096 else
-                                f"{launch['grid']} CTAs x {launch['block'] // 32} warps = {sm_fill:.2f} of the 148 x 8 warp slots: "
-                                "a small batch cannot fill the machine, the launch is latency bound")}
+    if launch["variant"] == 10:
+        # KV window on chip (tensor memory): HBM sees the tokens only; the launch is a latency chain of tile phases
+        tok = B * S * cfg.n_embd * 4
+        rec["roofline"] = {"bound": "latency", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                           "hbm_bytes_model": tok, "hbm_GBps": tok / (k_ms * 1e-3) / 1e9,
+                           "note": f"rollout_e32t_kernel: KV window in tensor memory, {launch['grid']} CTAs x {launch['group']} resident "
+                                   "trajectories, 8 warps per tile; HBM traffic = tokens only (algorithmic minimum); a small batch "
+                                   "cannot fill the machine, so the step latency (4 layers x ~6 barrier phases) is what counts"}
+    else:
+        rec["roofline"] = {"bound": "hbm" if B >= 4096 else "latency", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                           "fp32_view": {"achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak},
+                           "note": ("KV-window stream model (bench.py window_bytes_per_traj)" if B >= 4096 else
+                                    f"{launch['grid']} CTAs x {launch['block'] // 32} warps = {sm_fill:.2f} of the 148 x 8 warp slots: "
+                                    "a small batch cannot fill the machine, the launch is latency bound")}
     if e2e:
         host = torch.empty((B, S + 1, 3), dtype=torch.float32).pin_memory()
         cs = torch.cuda.Stream(device=dev)
@@ -660,12 +669,12 @@ def run_ours(args):
             tr.generate(g0, max_length=S + 1, use_cache=True, return_presents=False)
             b.record()
             torch.cuda.synchronize()
-            onchip = {"kernel": "rollout_e32t_kernel (KV window in tensor memory, tcgen05.st/ld; not selected automatically)",
+            onchip = {"kernel": "rollout_e32t_kernel (KV window in tensor memory, tcgen05.st/ld; the automatic choice only up to two rounds of resident tiles, i.e. B <= 2,368 here)",
                       "kernel_ms": a.elapsed_time(b), "traj_steps_per_s": B * S / (a.elapsed_time(b) * 1e-3),
                       "rollout_launch": tr.last_launch(),
                       "hbm_bytes_per_launch_model": B * S * E * 4 + B * E * 4,
-                      "note": "HBM traffic = tokens only (ncu: profiles/r02_ncu_rollout_tmem.json); slower than the "
-                              "HBM-window kernel because 8 resident trajectories per SM force all warps onto one tile"}
+                      "note": "HBM traffic = tokens only (ncu: profiles/r02_ncu_rollout_tmem.json); at this batch slower than "
+                              "the HBM-window kernel because 8 resident trajectories per SM force all warps onto one tile"}
             tr.set_rollout_tuning()
         # embed / recover alone (median of 5)
         em, rc = [], []
@@ -713,7 +722,7 @@ def run_ours(args):
     model_bytes = window_bytes_per_traj(cfg, S) * B
     achieved_gbs = model_bytes / (k_ms * 1e-3) / 1e9
     kname = {1: "rollout_generic_kernel", 2: "rollout_e32_kernel", 5: "rollout_e32v2_kernel", 6: "rollout_e32v4_kernel",
-             7: "rollout_cluster_kernel", 8: "rollout_e32s_kernel"}
+             7: "rollout_cluster_kernel", 8: "rollout_e32s_kernel", 10: "rollout_e32t_kernel"}
     # dram__bytes of the same launch from a committed ncu capture: reported only when the capture was taken with the very
     # launch configuration this run used (kernel variant, grid, block, group), with its provenance beside it
     traffic, traffic_source = None, None

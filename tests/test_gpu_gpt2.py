@@ -220,6 +220,32 @@ def test_rollout_tmem_window_kernel(dev, kind, B, S):
             assert O.rel_l2(out10[1][l].cpu(), out2[1][l].cpu()) < TOL
 
 
+@pytest.mark.parametrize("kind", ["lorenz", "rossler"])
+def test_rollout_auto_selection_by_batch(dev, kind):
+    """Automatic kernel choice for the KV-window mode: the on-chip (tensor memory) kernel while the batch fits two rounds
+    of resident tiles (latency-bound regime, incl. BASELINE config 1: Lorenz 256 x 128), the streaming kernel beyond; an
+    explicit grouping keeps the streaming kernel.  Both agree within the FP32 bar."""
+    cfg = synth.make_config(kind)
+    m = make_gpt2(cfg, 903, True, dev, sigma=0.1)
+    per_tile = 256 // cfg.n_ctx
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    small, large = 256, 2 * sms * per_tile + 1
+    x_small = torch.from_numpy(synth.normal_embeds((small, 1, cfg.n_embd), 5)).to(dev)
+    x_large = torch.from_numpy(synth.normal_embeds((large, 1, cfg.n_embd), 6)).to(dev)
+    a = m.generate(x_small, max_length=41, use_cache=True)
+    assert m.last_launch()["variant"] == 10, m.last_launch()
+    m.generate(x_large, max_length=5, use_cache=True, return_presents=False)
+    assert m.last_launch()["variant"] == 2, m.last_launch()
+    m.generate(x_small, max_length=5, use_cache=False)
+    assert m.last_launch()["variant"] != 10                       # the on-chip kernel is a KV-window kernel
+    m.set_rollout_tuning(traj_per_warp=4)
+    b = m.generate(x_small, max_length=41, use_cache=True)
+    assert m.last_launch()["variant"] == 2
+    assert O.rel_l2(a[0].cpu(), b[0].cpu()) < TOL
+    for l in range(cfg.n_layer):
+        assert O.rel_l2(a[1][l].cpu(), b[1][l].cpu()) < TOL
+
+
 @pytest.mark.parametrize("variant", [5, 6])
 @pytest.mark.parametrize("kind,B,S", [("lorenz", 19, 90), ("rossler", 37, 70), ("rossler", 16, 3)])
 def test_rollout_v2_kernel_vs_oracle(dev, kind, B, S, variant):
@@ -632,3 +658,30 @@ def test_grayscott_transformer_rollout(dev, B, S):
         out = m.generate(x0.to(dev), max_length=S + 1, use_cache=uc)
         assert m.last_launch()["variant"] == 1
         assert n == S + 1 and O.rel_l2(out[0].cpu(), ref) < TOL
+
+
+@pytest.mark.parametrize("kind,B,T", [("lorenz", 1, 1), ("lorenz", 5, 7), ("rossler", 3, 32), ("lorenz", 2, 33), ("lorenz", 9, 64)])
+def test_train_step_tensor_core_vs_simt(dev, kind, B, T, monkeypatch):
+    """Tensor-core training step (csrc/gpt2_train_tc.cu) against the FP32 SIMT kernel on ragged sequence lengths (rows
+    beyond T of the 64-row tile must stay out of every gradient): loss, hidden states, every parameter gradient."""
+    cfg = synth.make_config(kind)
+    m = make_gpt2(cfg, 77, True, dev, sigma=0.2)
+    x = torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), 12)).to(dev)
+    y = torch.from_numpy(synth.normal_embeds((B, T, cfg.n_embd), 13)).to(dev)
+    monkeypatch.setenv("TRPX_TRAIN_SIMT", "1")
+    l0, h0, g0 = m.fused_loss_and_grads(x, y)
+    monkeypatch.setenv("TRPX_TRAIN_SIMT", "0")
+    l1, h1, g1 = m.fused_loss_and_grads(x, y)
+    assert abs(float(l0) - float(l1)) <= 1e-5 * abs(float(l0))
+    assert O.rel_l2(h1.cpu(), h0.cpu()) < TOL
+    assert len(g0) == len(g1) == 12 * cfg.n_layer + 4
+    for i, (ga, gb) in enumerate(zip(g1, g0)):                      # `_weight_list()` order, 12 tensors per block
+        a, b = ga.cpu(), gb.cpu()
+        if i < 12 * cfg.n_layer and i % 12 == 3:                    # c_attn.bias: its key third is analytically zero
+            E = cfg.n_embd
+            assert float(a[E:2 * E].abs().max()) < 1e-6 * max(1.0, float(b.abs().max()))
+            a, b = torch.cat([a[:E], a[2 * E:]]), torch.cat([b[:E], b[2 * E:]])
+        if float(b.norm()) == 0.0:
+            assert float(a.norm()) == 0.0, i
+            continue
+        assert O.rel_l2(a, b) < TOL, i

@@ -222,14 +222,14 @@ def test_rollout_tmem_window_kernel(dev, kind, B, S):
 
 @pytest.mark.parametrize("kind", ["lorenz", "rossler"])
 def test_rollout_auto_selection_by_batch(dev, kind):
-    """Automatic kernel choice for the KV-window mode: the on-chip (tensor memory) kernel while the batch fits two rounds
-    of resident tiles (latency-bound regime, incl. BASELINE config 1: Lorenz 256 x 128), the streaming kernel beyond; an
+    """Automatic kernel choice for the KV-window mode: the on-chip (tensor memory) kernel while the batch fits a few rounds
+    of resident tiles (4 for n_ctx 32, 2 for n_ctx 64) (latency-bound regime, incl. BASELINE config 1: Lorenz 256 x 128), the streaming kernel beyond; an
     explicit grouping keeps the streaming kernel.  Both agree within the FP32 bar."""
     cfg = synth.make_config(kind)
     m = make_gpt2(cfg, 903, True, dev, sigma=0.1)
     per_tile = 256 // cfg.n_ctx
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    small, large = 256, 2 * sms * per_tile + 1
+    small, large = 256, (4 if cfg.n_ctx <= 32 else 2) * sms * per_tile + 1
     x_small = torch.from_numpy(synth.normal_embeds((small, 1, cfg.n_embd), 5)).to(dev)
     x_large = torch.from_numpy(synth.normal_embeds((large, 1, cfg.n_embd), 6)).to(dev)
     a = m.generate(x_small, max_length=41, use_cache=True)

@@ -3103,17 +3103,18 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         }
     }
     // ---- E=32, KV window on chip in tensor memory (variant 10, gpt2_tmem.cu) ----
-    // Selected automatically in the latency-bound regime: while the batch fills at most two rounds of resident tiles
-    // (B <= 2 x SMs x 8 Rossler / x 4 Lorenz trajectories) its 8 warps per tile finish a step sooner than one warp per
-    // 1-4 trajectories does (measured: Lorenz 256 x 128 — BASELINE config 1 — 1.30 ms against 2.18 ms; Rossler 1,184 x 128
-    // 1.32 against 2.35 ms; beyond two rounds the streaming kernel wins, profiles/README.md).
+    // Selected automatically in the latency-bound regime: while the batch fills only a few rounds of resident tiles
+    // (4 rounds of 8 trajectories per SM for n_ctx <= 32, 2 rounds of 4 for n_ctx = 64) its 8 warps per tile finish a step
+    // sooner than one warp per 1-8 trajectories does (measured: Lorenz 256 x 128 — BASELINE config 1 — 1.16 ms against
+    // 2.18 ms; Rossler 1,184 x 128 1.10 against 2.35 ms, 4,736 x 128 4.29 against 4.52 ms; Lorenz 1,776 x 128 is the tie;
+    // at full batch the streaming kernel is ahead, profiles/README.md).
     const bool tmem_ok = e32_shape && use_cache && tmem_rollout_group(L) > 0 &&
                          tmem_rollout_smem(L) + 1024 <= (size_t)h->smem_optin &&
                          (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (out_stride % 2) == 0 &&
                          (reinterpret_cast<uintptr_t>(presents) & 15) == 0;
     const bool tmem_auto = tmem_ok && h->tune_variant == 0 && h->tune_g == 0 && h->tune_warps == 0 &&
                            (B + tmem_rollout_group(L) - 1) / tmem_rollout_group(L) <=
-                               2 * (h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count);
+                               (L.n_ctx <= 32 ? 4 : 2) * (h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count);
     if (tmem_ok && (h->tune_variant == 10 || tmem_auto)) {
         const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
         const int G = tmem_rollout_group(L);

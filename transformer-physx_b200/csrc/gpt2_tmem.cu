@@ -34,7 +34,7 @@ namespace {
 
 constexpr int TT = 256;                   // threads per CTA
 constexpr int LDH = 36, LDQ = 132, LDR = 40;     // LDQ: q | k | v (K half 0) | v (K half 1) + 4
-constexpr int SCR_FLOATS = 3 * 8 * LDH + 8 * LDQ + 8 * 10 * 32 + 2 * 8 * LDR;
+constexpr int SCR_FLOATS = 3 * 8 * LDH + 8 * LDQ + 8 * 10 * 32 + 2 * 8 * LDR + 2 * 8 * LDH;
 constexpr float QSCALE = 1.4426950408889634f * 0.35355339059327373f;   // log2(e) / sqrt(8)
 
 // Exact two-term split x = hi + lo with hi = x truncated to TF32 (one LOP3 + one FADD; cvt.rna.tf32 is a three-
@@ -117,6 +117,30 @@ __device__ __forceinline__ void ln_frags(const float (&x)[8], const float* lw, c
         a[k] = make_a((x[2 * k] - m) * r * w2.x + b2.x, (x[2 * k + 1] - m) * r * w2.y + b2.y);
     }
 }
+// LayerNorm of one row by the warp that owns it (lane = channel): used where a phase produces a full row anyway, so that
+// no consumer has to recompute the statistics (the first version normalised redundantly in every warp: ~300 cycles per use)
+__device__ __forceinline__ float ln_row(float x, const float* lw, const float* lb, float eps, int lane) {
+    // sum and sum of squares travel through the five xor-shuffle steps together (two independent chains instead of two
+    // dependent reductions), and the reciprocal standard deviation is one MUFU.RSQ: on this latency-bound path the
+    // two-pass / IEEE sqrt + divide form cost ~500 cycles per use.  Residual-stream rows are O(1) with |mean| <~ std,
+    // so E[x^2] - mean^2 loses nothing that matters (parity tests unchanged at ~8e-7 against the 1e-5 bar).
+    float s1 = x, s2 = x * x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(FULL, s1, o);
+        s2 += __shfl_xor_sync(FULL, s2, o);
+    }
+    const float mean = s1 * (1.0f / 32.0f);
+    const float var = fmaxf(fmaf(-mean, mean, s2 * (1.0f / 32.0f)), 0.f);
+    return (x - mean) * rsqrtf(var + eps) * lw[lane] + lb[lane];
+}
+__device__ __forceinline__ void frags_from_rows(const float* X, int ld, int g, int q, AFrag (&a)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float2 v = *reinterpret_cast<const float2*>(X + g * ld + 8 * k + 2 * q);
+        a[k] = make_a(v.x, v.y);
+    }
+}
 __device__ __forceinline__ void load_row_frag(const float* X, int ld, int g, int q, float (&x)[8]) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -194,6 +218,8 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
     float* sQKV = sAO + 8 * LDH;              // q | k | v rows [8][LDQ]
     float* sP = sQKV + 8 * LDQ;               // attention partials [8 warps][10][32] / MLP-out partials [8][8][LDR]
     float* sHm = sP + 8 * 10 * 32;            // residual after the output projection [8][LDH]
+    float* sA1 = sHm + 2 * 8 * LDR;           // LayerNorm-1 (or final LayerNorm) output of the current residual [8][LDH]
+    float* sA2 = sA1 + 8 * LDH;               // LayerNorm-2 output [8][LDH]
 
     if (tid == 0) mbar_init(&bar, 1);
     if (warp == 0) tmem_alloc512(&tmem_slot);
@@ -237,6 +263,7 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
             float v = 0.f;
             if (r < TRAJ && b < p.B) v = p.x0[(size_t)b * p.x0_stride + c] + __ldg(p.pe + c);
             sH[r * LDH + c] = v;
+            sA1[r * LDH + c] = ln_row(v, wsm + L.ln1w, wsm + L.ln1b, p.eps, c);       // LayerNorm 1 of layer 0
         }
         __syncthreads();
 
@@ -249,10 +276,8 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
                 // ---- phase A: LN1 + this warp's share of the QKV product: one full n-tile (q tiles on warps 0..3, k
                 //      tiles on warps 4..7) and HALF the K range of a v tile (two partial v rows, summed by the reader) ----
                 {
-                    float x[8];
-                    load_row_frag(sH, LDH, g, q, x);
                     AFrag a[4];
-                    ln_frags(x, w + L.ln1w, w + L.ln1b, p.eps, q, a);
+                    frags_from_rows(sA1, LDH, g, q, a);                 // LayerNorm 1 was applied by the row owner
                     const int tv = 8 + (warp & 3), kv = 2 * (warp >> 2);
                     float dh[4][4], dl[4][4], eh[2][4], el[2][4];      // one accumulator pair per k-step: no MMA chains
                     const AFrag av[2] = {warp < 4 ? a[0] : a[2], warp < 4 ? a[1] : a[3]};
@@ -392,7 +417,9 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
                             acc[i] = fmaf(av4[i], wp[k * 32 + (lane ^ (((k >> 1) & 3) << 3))], acc[i]);
                         }
                     }
-                    sHm[warp * LDH + lane] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + w[L.bproj + lane] + sH[warp * LDH + lane];
+                    const float hm = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + w[L.bproj + lane] + sH[warp * LDH + lane];
+                    sHm[warp * LDH + lane] = hm;
+                    sA2[warp * LDH + lane] = ln_row(hm, w + L.ln2w, w + L.ln2b, p.eps, lane);     // the warp owns the row
                 }
                 TMEM_TICK(4)
                 __syncthreads();
@@ -402,7 +429,7 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
                     float hm[8];
                     load_row_frag(sHm, LDH, g, q, hm);
                     AFrag a[4];
-                    ln_frags(hm, w + L.ln2w, w + L.ln2b, p.eps, q, a);
+                    frags_from_rows(sA2, LDH, g, q, a);
                     float fh[2][2][4], fl[2][2][4];                   // [tile][k pair]: chains of two
 #pragma unroll
                     for (int k = 0; k < 4; k++)
@@ -453,16 +480,18 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
 #pragma unroll
                     for (int wv = 0; wv < 8; wv++) acc += sP[wv * (8 * LDR) + r * LDR + c];
                     sH[r * LDH + c] = acc;
+                    // what reads the new residual next: LayerNorm 1 of the next layer, or the final LayerNorm of the head
+                    const float* lw = (l + 1 < NL) ? w + L.layer_stride + L.ln1w : gw;
+                    const float* lb = (l + 1 < NL) ? w + L.layer_stride + L.ln1b : gw + 32;
+                    sA1[r * LDH + c] = ln_row(acc, lw, lb, p.eps, c);
                 }
                 __syncthreads();
                 TMEM_TICK(6)
             }
             // ---- final LayerNorm + linear head: warp t < 4 computes output columns 8t .. 8t+8 ----
             if (warp < 4) {
-                float x[8];
-                load_row_frag(sH, LDH, g, q, x);
                 AFrag a[4];
-                ln_frags(x, gw, gw + 32, p.eps, q, a);
+                frags_from_rows(sA1, LDH, g, q, a);                     // final LayerNorm applied by the reduce phase
                 float dh[4][4], dl[4][4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -482,8 +511,10 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
                 *reinterpret_cast<float2*>(sHn + g * LDH + col) = make_float2(y0 + pe.x, y1 + pe.y);
             }
             __syncthreads();
-            TMEM_TICK(7)
             { float* t = sH; sH = sHn; sHn = t; }
+            sA1[warp * LDH + lane] = ln_row(sH[warp * LDH + lane], wsm + L.ln1w, wsm + L.ln1b, p.eps, lane);   // layer 0 of the next step
+            __syncthreads();
+            TMEM_TICK(7)
         }
         // ---- optional: the final windows in chronological order, [n_layer][2][B][H][Tk][hd] (attention.py:188) ----
         if (p.presents != nullptr) {

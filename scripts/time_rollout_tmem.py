@@ -12,6 +12,7 @@ from trphysx_b200 import _native as N
 kind = sys.argv[1] if len(sys.argv) > 1 else "rossler"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+UC = (sys.argv[5] != "0") if len(sys.argv) > 5 else True
 dev = torch.device("cuda:0")
 cfg = synth.make_config(kind)
 m = make_gpt2(cfg, 903, True, dev, sigma=0.1)
@@ -23,16 +24,16 @@ res = {}
 for variant in [int(v) for v in (sys.argv[4].split(",") if len(sys.argv) > 4 else ["10", "2"])]:
     m.set_rollout_tuning(variant=variant)
     for _ in range(2):
-        out = m.generate(x0, max_length=S + 1, use_cache=True, return_presents=False)[0]
+        out = m.generate(x0, max_length=S + 1, use_cache=UC, return_presents=False)[0]
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
-        out = m.generate(x0, max_length=S + 1, use_cache=True, return_presents=False)[0]
+        out = m.generate(x0, max_length=S + 1, use_cache=UC, return_presents=False)[0]
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     res[variant] = out
-    print(f"{kind} B={B} S={S} variant {variant} {m.last_launch()}: {ms:.2f} ms = {B * S / ms / 1e3:.1f} M traj-steps/s")
+    print(f"{kind} use_cache={UC} B={B} S={S} variant {variant} {m.last_launch()}: {ms:.2f} ms = {B * S / ms / 1e3:.1f} M traj-steps/s")
 ks = sorted(res); a, b = res[ks[-1]][:, :65].double(), res[ks[0]][:, :65].double()
 print("rel-L2 variant 10 vs 2 (first 64 steps):", float((a - b).norm() / b.norm()))

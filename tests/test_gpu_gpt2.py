@@ -81,7 +81,8 @@ def test_generate_matches_reference(golden_dir, dev, name, variant):
     elif not e32:
         assert info["variant"] == (7 if variant == 0 else 1)   # auto, small batch: the thread-block-cluster kernel
     else:
-        assert info["variant"] == (variant if variant in (5, 6) else 2)
+        onchip = variant == 0 and cfg.n_ctx in (32, 64) and cfg.n_layer <= 4      # small batch: the cooperative tile kernel
+        assert info["variant"] == (variant if variant in (5, 6) else (10 if onchip else 2))
 
 
 @pytest.mark.parametrize("name", ["rossler_stress", "cylinder_stress", "lorenz_stress"])
@@ -218,6 +219,15 @@ def test_rollout_tmem_window_kernel(dev, kind, B, S):
     if n == S + 1:
         for l in range(cfg.n_layer):
             assert O.rel_l2(out10[1][l].cpu(), out2[1][l].cpu()) < TOL
+    # the reference's default mode (use_cache=False) on the same cooperative tile, without the window phases
+    if B <= 64:
+        m.set_rollout_tuning(variant=10)
+        nc = m.generate(x0.to(dev), max_length=S + 1, use_cache=False)[0]
+        assert m.last_launch()["variant"] == 10
+        n0, ref0 = stable_prefix(cfg, w_np, x0, S + 1, False)
+        e0 = O.rel_l2(nc.cpu()[:, :n0], ref0[:, :n0])
+        print(f"variant 10 {kind} B={B} S={S} use_cache=False: rel-L2 {e0:.2e} over {n0} tokens")
+        assert e0 < TOL, f"stable horizon {n0}"
 
 
 @pytest.mark.parametrize("kind", ["lorenz", "rossler"])
@@ -237,7 +247,10 @@ def test_rollout_auto_selection_by_batch(dev, kind):
     m.generate(x_large, max_length=5, use_cache=True, return_presents=False)
     assert m.last_launch()["variant"] == 2, m.last_launch()
     m.generate(x_small, max_length=5, use_cache=False)
-    assert m.last_launch()["variant"] != 10                       # the on-chip kernel is a KV-window kernel
+    assert m.last_launch()["variant"] == 10                       # one round of tiles: also the default (no-window) mode
+    x_mid = torch.from_numpy(synth.normal_embeds((sms * per_tile + 1, 1, cfg.n_embd), 7)).to(dev)
+    m.generate(x_mid, max_length=5, use_cache=False)
+    assert m.last_launch()["variant"] != 10
     m.set_rollout_tuning(traj_per_warp=4)
     b = m.generate(x_small, max_length=41, use_cache=True)
     assert m.last_launch()["variant"] == 2

@@ -3108,13 +3108,17 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
     // sooner than one warp per 1-8 trajectories does (measured: Lorenz 256 x 128 — BASELINE config 1 — 1.16 ms against
     // 2.18 ms; Rossler 1,184 x 128 1.10 against 2.35 ms, 4,736 x 128 4.29 against 4.52 ms; Lorenz 1,776 x 128 is the tie;
     // at full batch the streaming kernel is ahead, profiles/README.md).
-    const bool tmem_ok = e32_shape && use_cache && tmem_rollout_group(L) > 0 &&
+    const bool tmem_ok = e32_shape && tmem_rollout_group(L) > 0 &&
                          tmem_rollout_smem(L) + 1024 <= (size_t)h->smem_optin &&
                          (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (out_stride % 2) == 0 &&
                          (reinterpret_cast<uintptr_t>(presents) & 15) == 0;
+    // use_cache=False (the reference's default mode) runs on the same cooperative tile without the window phases: ahead of
+    // the warp-per-group kernels only while the batch is ONE round of tiles (Lorenz 256 x 128: 0.86 against 1.42 ms,
+    // Rossler 1,184 x 128: 0.88 against 1.42 ms; two rounds already lose).
     const bool tmem_auto = tmem_ok && h->tune_variant == 0 && h->tune_g == 0 && h->tune_warps == 0 &&
                            (B + tmem_rollout_group(L) - 1) / tmem_rollout_group(L) <=
-                               (L.n_ctx <= 32 ? 4 : 2) * (h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count);
+                               (!use_cache ? 1 : (L.n_ctx <= 32 ? 4 : 2)) *
+                                   (h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count);
     if (tmem_ok && (h->tune_variant == 10 || tmem_auto)) {
         const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
         const int G = tmem_rollout_group(L);
@@ -3122,7 +3126,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         const int grid = std::min(sms, ngroups);
         TmemRolloutParams tp{};
         tp.blob_sw = h->blob_sw; tp.pe = h->pe; tp.x0 = x0; tp.x0_stride = x0_stride; tp.out = out; tp.out_stride = out_stride;
-        tp.presents = presents; tp.B = B; tp.S = S; tp.eps = h->cfg.ln_eps; tp.lay = L;
+        tp.presents = presents; tp.B = B; tp.S = S; tp.use_cache = use_cache ? 1 : 0; tp.eps = h->cfg.ln_eps; tp.lay = L;
         h->last_variant = 10; h->last_grid = grid; h->last_block = 256; h->last_smem = (int)tmem_rollout_smem(L); h->last_group = G;
         return launch_rollout_tmem(tp, grid, st);
     }

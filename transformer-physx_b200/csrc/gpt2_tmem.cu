@@ -26,6 +26,10 @@
 // barrier.  Five CTA barriers per layer, one per step for the head.
 //
 // HBM traffic is the algorithmic minimum: 128 B written per trajectory-step, x0 read once.
+//
+// The LayerNorm of a residual row is applied once, by the phase that owns the row (the projection and the partial-sum
+// reduction run one warp per row), not by every consumer.  CACHE = false is the reference's default generate() mode
+// (no window, position 0) on the same tile without the window phases.
 #include "gpt2_tmem.cuh"
 #include <cstdlib>
 
@@ -197,7 +201,9 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
         }                                                                \
     }
 
-template <int NCTX, bool PROF>
+// CACHE = false is the reference's DEFAULT generate() mode (use_cache=False: a one-token forward at position 0, the head
+// output is v itself): the same cooperative tile without the window phases, for the latency-bound small batches.
+template <int NCTX, bool PROF, bool CACHE = true>
 __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p, long long* prof) {
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = 0;
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
     const int ngroups = (p.B + TRAJ - 1) / TRAJ;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         // ---- group start: clear the warp's window cells, h = x0 + PE(0) ----
-        {
+        if constexpr (CACHE) {
             uint32_t z[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) z[i] = 0u;
@@ -284,22 +290,26 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         float w0, w1;
-                        ldb(w + L.wqkv, 96, k, warp, g, q, w0, w1);
-                        mma2z(dh[k], dl[k], a[k], w0, w1);
+                        if constexpr (CACHE) {
+                            ldb(w + L.wqkv, 96, k, warp, g, q, w0, w1);
+                            mma2z(dh[k], dl[k], a[k], w0, w1);
+                        }
                         if (k < 2) {
                             ldb(w + L.wqkv, 96, kv + k, tv, g, q, w0, w1);
                             mma2z(eh[k], el[k], av[k], w0, w1);
                         }
                     }
-                    const float2 b2 = *reinterpret_cast<const float2*>(w + L.bqkv + 8 * warp + 2 * q);
-                    float2 y;
-                    {
-                        const float2 y0 = fold2(dh[0], dl[0], dh[1], dl[1]), y1 = fold2(dh[2], dl[2], dh[3], dl[3]);
-                        y.x = y0.x + y1.x + b2.x;
-                        y.y = y0.y + y1.y + b2.y;
+                    if constexpr (CACHE) {
+                        const float2 b2 = *reinterpret_cast<const float2*>(w + L.bqkv + 8 * warp + 2 * q);
+                        float2 y;
+                        {
+                            const float2 y0 = fold2(dh[0], dl[0], dh[1], dl[1]), y1 = fold2(dh[2], dl[2], dh[3], dl[3]);
+                            y.x = y0.x + y1.x + b2.x;
+                            y.y = y0.y + y1.y + b2.y;
+                        }
+                        if (warp < 4) { y.x *= QSCALE; y.y *= QSCALE; }
+                        *reinterpret_cast<float2*>(sQKV + g * LDQ + 8 * warp + 2 * q) = y;
                     }
-                    if (warp < 4) { y.x *= QSCALE; y.y *= QSCALE; }
-                    *reinterpret_cast<float2*>(sQKV + g * LDQ + 8 * warp + 2 * q) = y;
                     float2 v = fold2(eh[0], el[0], eh[1], el[1]);
                     if (warp < 4) {
                         const float2 bv = *reinterpret_cast<const float2*>(w + L.bqkv + 8 * tv + 2 * q);
@@ -310,6 +320,7 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
                 TMEM_TICK(0)
                 __syncthreads();
                 TMEM_TICK(1)
+                if constexpr (CACHE) {
                 // ---- phase B: append the new (k, v) row, partial softmax over the thread's 4 slots ----
                 {
                     const float* qrow = sQKV + atraj * LDQ + ahead * 8;
@@ -399,17 +410,22 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
                         sAO[(pr >> 2) * LDH + (pr & 3) * 8 + ch] = __fdividef(O, Ls);
                     }
                 }
+                }
                 TMEM_TICK(3)
                 __syncthreads();
                 // ---- phase C: output projection + residual on the FP32 pipe (8 x 1,024 MACs: one output per thread; an
                 //      MMA version pays two dependent tensor-core latencies for 4 instructions) ----
                 {
-                    const float* ar = sAO + warp * LDH;
+                    const float* ar = CACHE ? sAO + warp * LDH : sQKV + warp * LDQ + 64;   // no window: attention output = v
                     const float* wp = w + L.wproj;
                     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int k4 = 0; k4 < 8; k4++) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(ar + 4 * k4);
+                        float4 a4 = *reinterpret_cast<const float4*>(ar + 4 * k4);
+                        if constexpr (!CACHE) {                        // the two K halves of the v row
+                            const float4 u4 = *reinterpret_cast<const float4*>(ar + 32 + 4 * k4);
+                            a4.x += u4.x; a4.y += u4.y; a4.z += u4.z; a4.w += u4.w;
+                        }
                         const float av4[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
@@ -506,7 +522,7 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
                 const int b = grp * TRAJ + g;
                 if (g < TRAJ && b < p.B)
                     *reinterpret_cast<float2*>(p.out + (size_t)b * p.out_stride + (size_t)s * 32 + col) = make_float2(y0, y1);
-                const int pnext = min(s + 1, NCTX - 1);
+                const int pnext = CACHE ? min(s + 1, NCTX - 1) : 0;
                 const float2 pe = __ldg(reinterpret_cast<const float2*>(p.pe + pnext * 32 + col));
                 *reinterpret_cast<float2*>(sHn + g * LDH + col) = make_float2(y0 + pe.x, y1 + pe.y);
             }
@@ -517,7 +533,7 @@ __global__ void __launch_bounds__(TT, 1) rollout_e32t_kernel(TmemRolloutParams p
             TMEM_TICK(7)
         }
         // ---- optional: the final windows in chronological order, [n_layer][2][B][H][Tk][hd] (attention.py:188) ----
-        if (p.presents != nullptr) {
+        if (CACHE && p.presents != nullptr) {
             const int Tk = min(p.S, NCTX);
             const int b = grp * TRAJ + atraj;
             const size_t per_l = (size_t)2 * p.B * 4 * Tk * 8;
@@ -598,16 +614,19 @@ int tmem_rollout_group(const Gpt2Layout& L) {
 
 size_t tmem_rollout_smem(const Gpt2Layout& L) { return ((size_t)L.total + SCR_FLOATS) * sizeof(float); }
 
-template <int NCTX, bool PROF>
+template <int NCTX, bool PROF, bool CACHE = true>
 int launch_one(const TmemRolloutParams& p, int grid, size_t smem, long long* prof, cudaStream_t st) {
-    TRPX_CUDA(cudaFuncSetAttribute(rollout_e32t_kernel<NCTX, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_e32t_kernel<NCTX, PROF><<<grid, TT, smem, st>>>(p, prof);
+    TRPX_CUDA(cudaFuncSetAttribute(rollout_e32t_kernel<NCTX, PROF, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_e32t_kernel<NCTX, PROF, CACHE><<<grid, TT, smem, st>>>(p, prof);
     TRPX_CUDA(cudaGetLastError());
     return TRPX_OK;
 }
 
 int launch_rollout_tmem(const TmemRolloutParams& p, int grid, cudaStream_t st) {
     const size_t smem = tmem_rollout_smem(p.lay);
+    if (!p.use_cache)
+        return p.lay.n_ctx == 32 ? launch_one<32, false, false>(p, grid, smem, nullptr, st)
+                                 : launch_one<64, false, false>(p, grid, smem, nullptr, st);
     const char* env = getenv("TRPX_TMEM_PROF");
     if (env != nullptr && env[0] == '1') {
         long long* prof = nullptr;

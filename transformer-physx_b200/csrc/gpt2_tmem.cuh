@@ -15,6 +15,7 @@ struct TmemRolloutParams {
     long long out_stride;
     float* presents;          // optional [n_layer][2][B][H][Tk][hd]
     int B, S;
+    int use_cache;            // 0: the reference's default generate() mode (no window, position 0)
     float eps;
     Gpt2Layout lay;
 };

@@ -135,6 +135,85 @@ __global__ void __launch_bounds__(EMB_THREADS) mlp_embed_kernel(const float* __r
     }
 }
 
+// ---- K3a (small N): the same map for batches that cannot fill the machine with one thread per sample -------------------
+// (the Koopman training step embeds 8,192 samples, a 256-trajectory rollout 256: the thread-per-sample kernel then runs
+// 16 CTAs / 1 CTA, and its 500-unit loop is a 78 us latency chain).  Here a WARP owns 8 samples: the lanes first share
+// the 500 hidden units (16 each) and leave relu(W1 x + b1) in shared memory, then lane = output channel streams the units
+// once (two broadcast LDS.128 for the 8 hidden values, one conflict-free word of W2^T, 8 FMAs); LayerNorm over the lanes.
+constexpr int EMS_S = 8;               // samples per warp
+constexpr int EMS_WARPS = 8;
+__global__ void __launch_bounds__(EMS_WARPS * 32) mlp_embed_small_kernel(const float* __restrict__ blob, MlpLayout L,
+                                                                          const float* __restrict__ x, float* __restrict__ g,
+                                                                          long long N, float eps, float* __restrict__ zhat_out,
+                                                                          float* __restrict__ rstd_out) {
+    extern __shared__ float4 sm4[];
+    const int Hd = L.Hd, HP = (Hd + 31) & ~31;
+    float4* sA = sm4;                                   // [Hd]     {W1[u][0..2], b1[u]}
+    const float* sB = reinterpret_cast<const float*>(sm4 + Hd);      // [Hd][32] W2^T
+    float4* hb = sm4 + Hd * 9 + (threadIdx.x >> 5) * (HP * 2);        // [HP][8]  hidden values of the warp's samples
+    {
+        const float4* src = reinterpret_cast<const float4*>(blob + L.encA);
+        for (int i = threadIdx.x; i < Hd * 9; i += blockDim.x) sm4[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * EMS_WARPS + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * EMS_WARPS;
+    float mu[MS], sd[MS];
+#pragma unroll
+    for (int j = 0; j < MS; j++) { mu[j] = __ldg(blob + L.mu + j); sd[j] = __ldg(blob + L.sd + j); }
+    const float b2 = __ldg(blob + L.b2 + lane), lw = __ldg(blob + L.lnw + lane), lb = __ldg(blob + L.lnb + lane);
+    for (long long base = warp * EMS_S; base < N; base += nwarps * EMS_S) {
+        float xn[EMS_S][MS];
+#pragma unroll
+        for (int s = 0; s < EMS_S; s++)
+#pragma unroll
+            for (int j = 0; j < MS; j++) {
+                const float v = (base + s < N) ? __ldg(x + (base + s) * MS + j) : mu[j];
+                xn[s][j] = (v - mu[j]) / sd[j];           // _normalize, embedding_lorenz.py:159-160
+            }
+        for (int u = lane; u < HP; u += 32) {
+            float hid[EMS_S];
+            if (u < Hd) {
+                const float4 a = sA[u];
+#pragma unroll
+                for (int s = 0; s < EMS_S; s++)
+                    hid[s] = fmaxf(fmaf(a.z, xn[s][2], fmaf(a.y, xn[s][1], fmaf(a.x, xn[s][0], a.w))), 0.f);
+            } else {
+#pragma unroll
+                for (int s = 0; s < EMS_S; s++) hid[s] = 0.f;
+            }
+            hb[u * 2] = make_float4(hid[0], hid[1], hid[2], hid[3]);
+            hb[u * 2 + 1] = make_float4(hid[4], hid[5], hid[6], hid[7]);
+        }
+        __syncwarp();
+        float acc[EMS_S];
+#pragma unroll
+        for (int s = 0; s < EMS_S; s++) acc[s] = b2;
+#pragma unroll 4
+        for (int u = 0; u < Hd; u++) {
+            const float4 h0 = hb[u * 2], h1 = hb[u * 2 + 1];
+            const float w = sB[u * ME + lane];
+            acc[0] = fmaf(w, h0.x, acc[0]); acc[1] = fmaf(w, h0.y, acc[1]);
+            acc[2] = fmaf(w, h0.z, acc[2]); acc[3] = fmaf(w, h0.w, acc[3]);
+            acc[4] = fmaf(w, h1.x, acc[4]); acc[5] = fmaf(w, h1.y, acc[5]);
+            acc[6] = fmaf(w, h1.z, acc[6]); acc[7] = fmaf(w, h1.w, acc[7]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < EMS_S; s++) {
+            const float m = warp_sum(acc[s]) * (1.0f / ME);
+            const float d = acc[s] - m;
+            const float rstd = 1.0f / sqrtf(warp_sum(d * d) * (1.0f / ME) + eps);
+            if (base + s < N) {
+                const float z = d * rstd;
+                g[(base + s) * ME + lane] = z * lw + lb;
+                if (zhat_out) zhat_out[(base + s) * ME + lane] = z;
+                if (rstd_out && lane == 0) rstd_out[base + s] = rstd;
+            }
+        }
+    }
+}
+
 // ---- K3b: recover  g[N,32] -> x[N,3] ------------------------------------------------------------------
 // With `target` != null the kernel is the fused `recover + MSE` of Trainer.eval_states (utils/trainer.py:380-390): the
 // recovered states are not written (x may be null); each CTA writes the sum of squared errors of its samples to
@@ -509,6 +588,17 @@ int mlpemb_embed_ex(trpx_mlpemb_t h, const float* x, float* g, long long N, floa
     DeviceGuard guard(h->device);
     const MlpLayout L = MlpLayout::make(h->cfg.hidden);
     const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
+    // batches that give the thread-per-sample kernel less than ~one CTA per SM: the warp-per-8-samples kernel
+    const size_t smem_small = smem + sizeof(float4) * (size_t)EMS_WARPS * (((size_t)L.Hd + 31) & ~(size_t)31) * 2;
+    if (N <= (long long)h->sm_count * EMB_THREADS * SPT && smem_small + 1024 <= (size_t)h->smem_optin) {
+        const long long nwarps = (N + EMS_S - 1) / EMS_S;
+        const int grid = (int)std::min<long long>(h->sm_count, (nwarps + EMS_WARPS - 1) / EMS_WARPS);
+        TRPX_CUDA(cudaFuncSetAttribute(mlp_embed_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        mlp_embed_small_kernel<<<grid, EMS_WARPS * 32, smem_small, (cudaStream_t)stream>>>(h->blob, L, x, g, N, h->cfg.ln_eps,
+                                                                                           zhat, rstd);
+        TRPX_CUDA(cudaGetLastError());
+        return TRPX_OK;
+    }
     TRPX_CUDA(cudaFuncSetAttribute(mlp_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mlp_embed_kernel<<<emb_grid(h, N, 3), EMB_THREADS, smem, (cudaStream_t)stream>>>(h->blob, L, x, g, N, h->cfg.ln_eps,
                                                                                     zhat, rstd);

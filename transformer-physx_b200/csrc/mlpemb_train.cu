@@ -410,6 +410,21 @@ struct FinalArgs {
     float grad_scale;
 };
 
+// sum of n per-CTA partials (stride floats apart) in a FIXED order: four interleaved chains (c mod 4), then
+// (s0 + s1) + (s2 + s3) — deterministic, and four loads in flight instead of one dependent load-add per partial
+__device__ __forceinline__ float sum_partials(const float* __restrict__ p, size_t stride, int n) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= n; c += 4) {
+        s0 += p[(size_t)c * stride];
+        s1 += p[(size_t)(c + 1) * stride];
+        s2 += p[(size_t)(c + 2) * stride];
+        s3 += p[(size_t)(c + 3) * stride];
+    }
+    for (; c < n; c++) s0 += p[(size_t)c * stride];
+    return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void finalize_kernel(const float* __restrict__ blob, MlpLayout L, FinalArgs A, TrainDims D,
                                 float* __restrict__ grad, float* __restrict__ loss2) {
     const int Hd = D.Hd;
@@ -441,12 +456,12 @@ __global__ void finalize_kernel(const float* __restrict__ blob, MlpLayout L, Fin
             for (int c = 0; c < A.n_chain; c++) v += A.chain_part[(size_t)c * 3 * ME + which * ME + idx];
             v += 4.0f * regT * blob[L.ku + o];
         } else if ((o -= 61) < Hd * MS + Hd) {          // observableNet.0.{weight [Hd,3], bias [Hd]}
-            for (int c = 0; c < A.n_enc; c++) v += A.enc_part[(size_t)c * EP + o];
+            v = sum_partials(A.enc_part + o, EP, A.n_enc);
         } else if ((o -= Hd * MS + Hd) < ME * Hd + 3 * ME) {   // observableNet.2.{weight [32,Hd], bias}, .3.{weight, bias}
-            for (int c = 0; c < A.n_enc; c++) v += A.enc_part[(size_t)c * EP + Hd * MS + Hd + o];
+            v = sum_partials(A.enc_part + Hd * MS + Hd + o, EP, A.n_enc);
         } else {                                        // recoveryNet.0.{weight [Hd,32], bias}, .2.{weight [3,Hd], bias}
             o -= ME * Hd + 3 * ME;
-            for (int c = 0; c < A.n_dec; c++) v += A.dec_part[(size_t)c * DP + o];
+            v = sum_partials(A.dec_part + o, DP, A.n_dec);
         }
         grad[i] = v * A.grad_scale;
     }

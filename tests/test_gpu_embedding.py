@@ -164,6 +164,30 @@ def test_train_step_config3_vs_oracle(dev):
     assert O.rel_l2(flat.cpu(), g_ref) < TOL
 
 
+def test_train_step_tensor_core_decoder_opt_in(dev, monkeypatch):
+    """TRPX_KOOPMAN_TC=1: the decoder forward+backward of the Koopman training step as 3xTF32 tile products.  Faster
+    (0.19 vs 0.25 ms at config 3) but this gradient is ill conditioned (1e4 loss weights, ~50x cancellation in the row sums):
+    the 2^-22 per-product error lands it at ~1.1e-5 from the oracle, over the 1e-5 bar, which is why it is opt-in.  Pinned
+    here at 3e-5 (loss at 2e-5) on the config-3 shape and on a ragged small batch (partial tiles, idle CTAs)."""
+    from trphysx_b200.config import PhysConfig
+    from trphysx_b200.embedding import LorenzEmbeddingTrainer
+    monkeypatch.setenv("TRPX_KOOPMAN_TC", "1")
+    cfg_ns = synth.make_config("lorenz")
+    for B, T in ((512, 16), (21, 5)):
+        head = LorenzEmbeddingTrainer(PhysConfig(**vars(cfg_ns)))
+        head.embedding_model.load_state_dict(torch_sd(synth.lorenz_embedding_weights(cfg_ns, 77)))
+        head.to(dev)
+        states = torch.from_numpy(synth.lorenz_trajectories(B, T - 1, seed=77))
+        loss, loss_rec = head(states.to(dev))
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in head.parameters()])
+        sd = O.to_torch(synth.lorenz_embedding_weights(cfg_ns, 77))
+        l_ref, lr_ref, g_ref = O.lorenz_train_grads(sd, cfg_ns, states)
+        assert abs(float(loss.detach()) - float(l_ref)) <= 2e-5 * abs(float(l_ref))
+        assert abs(float(loss_rec) - float(lr_ref)) <= 2e-5 * abs(float(lr_ref))
+        assert O.rel_l2(flat.cpu(), g_ref) < 3e-5
+
+
 def test_fused_koopman_step_equals_autograd_step(dev):
     """FusedKoopmanStep (no autograd graph) gives the same parameters as head(states); backward(); opt.step()."""
     from trphysx_b200.config import PhysConfig

@@ -54,6 +54,26 @@ def test_lorenz_embed_recover_vs_oracle_sizes(dev, N):
         assert m.embed(x[:0].to(dev)).shape == (0, 32)
 
 
+def test_embed_small_and_large_batch_kernels_agree(dev):
+    """`embed` switches from the warp-per-8-samples kernel to the thread-per-sample kernel at N = SMs x 256: the same rows
+    through both must agree (same contraction order; only the LayerNorm reduction differs), and the boundary sizes
+    (N not a multiple of 8, N = threshold, threshold + 1) must be exact against the oracle."""
+    cfg = synth.make_config("lorenz")
+    m = make_lorenz(cfg, 31, "lorenz", dev)
+    sd = O.to_torch(synth.lorenz_embedding_weights(cfg, 31))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    thr = sms * 256
+    x = torch.from_numpy(synth.normal_embeds((thr + 1, 3), 9, scale=9.0)).to(dev)
+    with torch.no_grad():
+        big = m.embed(x)                         # thread-per-sample kernel
+        small = m.embed(x[:thr])                 # warp-per-8-samples kernel
+        assert O.rel_l2(small.cpu(), big[:thr].cpu()) < 1e-6
+        for n in (1, 7, 8, 9, 1001):
+            assert O.rel_l2(m.embed(x[:n]).cpu(), O.lorenz_embed(sd, cfg, x[:n].cpu())) < TOL
+        ref = O.lorenz_embed(sd, cfg, x[-4096:].cpu())
+        assert O.rel_l2(big[-4096:].cpu(), ref) < TOL
+
+
 def test_mu_std_assignment_is_picked_up(dev):
     """Scripts overwrite model.mu / model.std by attribute assignment (examples/lorenz/train_lorenz_enn.py:55-57)."""
     cfg = synth.make_config("lorenz")

@@ -673,7 +673,8 @@ def test_grayscott_transformer_rollout(dev, B, S):
         assert n == S + 1 and O.rel_l2(out[0].cpu(), ref) < TOL
 
 
-@pytest.mark.parametrize("kind,B,T", [("lorenz", 1, 1), ("lorenz", 5, 7), ("rossler", 3, 32), ("lorenz", 2, 33), ("lorenz", 9, 64)])
+@pytest.mark.parametrize("kind,B,T", [("lorenz", 1, 1), ("lorenz", 5, 7), ("rossler", 3, 32), ("lorenz", 2, 33), ("lorenz", 9, 64),
+                                      ("lorenz", 700, 64)])      # 700 sequences: more than two waves of two CTAs per SM
 def test_train_step_tensor_core_vs_simt(dev, kind, B, T, monkeypatch):
     """Tensor-core training step (csrc/gpt2_train_tc.cu) against the FP32 SIMT kernel on ragged sequence lengths (rows
     beyond T of the 64-row tile must stay out of every gradient): loss, hidden states, every parameter gradient."""

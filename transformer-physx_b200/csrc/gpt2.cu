@@ -11,6 +11,8 @@
 #include "gpt2_handle.cuh"
 #include "gpt2_tmem.cuh"
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
@@ -186,6 +188,8 @@ struct RolloutParams {
     Gpt2Layout lay;
     int use_tma;
     int prefetch;
+    int spin_ns;             // back-off between mbarrier probes of the warp-specialised kernel
+    long long* prof;         // WS_PROF builds only: per-warp (wait, total) cycles of CTA 0
 };
 
 template <int G>
@@ -524,7 +528,10 @@ __device__ __forceinline__ void warp_attn_e32(const float* qs, const float* kvl,
 }
 
 template <int G, int MAXI, bool CACHE>
-__global__ void __launch_bounds__((CACHE && G >= 4) ? 256 : 384, 1) rollout_e32_kernel(RolloutParams p) {
+#ifndef TRPX_E32_CACHE_NT
+#define TRPX_E32_CACHE_NT 256
+#endif
+__global__ void __launch_bounds__((CACHE && G >= 4) ? TRPX_E32_CACHE_NT : 384, 1) rollout_e32_kernel(RolloutParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ __align__(8) uint64_t bar;
     const Gpt2Layout& L = p.lay;
@@ -1513,6 +1520,35 @@ __device__ __forceinline__ void frag_ln(const float (&h)[4][4], const float* lw,
         frag_c2a(x, ah[t], al[t]);
     }
 }
+// same LayerNorm, result stored as FP32 rows (row g -> r0, row g + 8 -> r1; the lane's columns 8t + 2q, + 1)
+__device__ __forceinline__ void frag_ln_store(const float (&h)[4][4], const float* lw, const float* lb, float eps, int q,
+                                              float* r0, float* r1) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; t++) { s0 += h[t][0] + h[t][1]; s1 += h[t][2] + h[t][3]; }
+    s0 += __shfl_xor_sync(FULL, s0, 1); s0 += __shfl_xor_sync(FULL, s0, 2);
+    s1 += __shfl_xor_sync(FULL, s1, 1); s1 += __shfl_xor_sync(FULL, s1, 2);
+    const float m0 = s0 * (1.0f / 32.0f), m1 = s1 * (1.0f / 32.0f);
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const float a = h[t][0] - m0, b = h[t][1] - m0, c = h[t][2] - m1, d = h[t][3] - m1;
+        v0 = fmaf(a, a, v0); v0 = fmaf(b, b, v0);
+        v1 = fmaf(c, c, v1); v1 = fmaf(d, d, v1);
+    }
+    v0 += __shfl_xor_sync(FULL, v0, 1); v0 += __shfl_xor_sync(FULL, v0, 2);
+    v1 += __shfl_xor_sync(FULL, v1, 1); v1 += __shfl_xor_sync(FULL, v1, 2);
+    const float i0 = 1.0f / sqrtf(v0 * (1.0f / 32.0f) + eps), i1 = 1.0f / sqrtf(v1 * (1.0f / 32.0f) + eps);
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const float2 w2 = *reinterpret_cast<const float2*>(lw + 8 * t + 2 * q);
+        const float2 b2 = *reinterpret_cast<const float2*>(lb + 8 * t + 2 * q);
+        *reinterpret_cast<float2*>(r0 + 8 * t + 2 * q) =
+            make_float2((h[t][0] - m0) * i0 * w2.x + b2.x, (h[t][1] - m0) * i0 * w2.y + b2.y);
+        *reinterpret_cast<float2*>(r1 + 8 * t + 2 * q) =
+            make_float2((h[t][2] - m1) * i1 * w2.x + b2.x, (h[t][3] - m1) * i1 * w2.y + b2.y);
+    }
+}
 __device__ __forceinline__ void frag_bias(float (&c)[4], const float* b, int t, int q) {
     const float2 b2 = *reinterpret_cast<const float2*>(b + 8 * t + 2 * q);
     c[0] = b2.x; c[1] = b2.y; c[2] = b2.x; c[3] = b2.y;
@@ -1566,7 +1602,7 @@ __global__ void __launch_bounds__(CACHE ? 256 : 384, 1) rollout_e32v4_kernel(Rol
             for (int l = 0; l < NL; l++) {
                 const float* w = wsm + l * L.layer_stride;
                 if constexpr (CACHE) {
-                    if (p.prefetch && lane < 4 && Lk > 1) {      // windows of the first attention pass
+                    if ((p.prefetch & 1) && lane < (NCTX <= 32 ? 8 : 4) && Lk > 1) {      // windows of the first attention pass
                         const float* kp = kvw + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
                         prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
                         prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
@@ -1602,10 +1638,28 @@ __global__ void __launch_bounds__(CACHE ? 256 : 384, 1) rollout_e32v4_kernel(Rol
                     // attention in 4 passes of 4 trajectories: two lanes per (trajectory, head) pair, 16 window rows in
                     // flight per lane (the scheme of rollout_e32_kernel<4>); the windows of the NEXT pass are pulled
                     // into L2 while this pass computes, so only ~32 KB per warp have to survive in L2
+                    if constexpr (NCTX <= 32) {
+                        // two passes of 8 trajectories: a lane owns a (trajectory, head) pair outright (the scheme of
+                        // rollout_e32_kernel<8>), 16 window rows in flight per lane
+#pragma unroll 1
+                        for (int t8 = 0; t8 < 2; t8++) {
+                            const float* kvl = kvw + (size_t)(8 * t8) * kv_per_g + (size_t)(l * 2) * C * 32;
+                            if ((p.prefetch & 2) && t8 < 1 && lane < 8 && Lk > 1) {
+                                const float* kp = kvl + (size_t)(8 + lane) * kv_per_g;
+                                prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
+                                prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+                            }
+                            float* tile = scr + 8 * t8 * V4QS;
+                            if (Lk == NCTX)
+                                warp_attn_e32<8, NCTX, true, V4QS, V4QS>(tile, kvl, kv_per_g, C, Lk, tile, lane);
+                            else
+                                warp_attn_e32<8, NCTX, false, V4QS, V4QS>(tile, kvl, kv_per_g, C, Lk, tile, lane);
+                        }
+                    } else
 #pragma unroll 1
                     for (int t4 = 0; t4 < 4; t4++) {
                         const float* kvl = kvw + (size_t)(4 * t4) * kv_per_g + (size_t)(l * 2) * C * 32;
-                        if (p.prefetch && t4 < 3 && lane < 4 && Lk > 1) {
+                        if ((p.prefetch & 2) && t4 < 3 && lane < 4 && Lk > 1) {
                             const float* kp = kvl + (size_t)(4 + lane) * kv_per_g;
                             prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
                             prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
@@ -1717,6 +1771,358 @@ __global__ void __launch_bounds__(CACHE ? 256 : 384, 1) rollout_e32v4_kernel(Rol
             __syncwarp();
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1w (E = 32, KV window): WARP-SPECIALISED streaming kernel (rollout variant 11).
+// Measured on the kernels above (profiles/README.md, round 2): a warp that does both the dense layer arithmetic and
+// the window attention alternates between a phase that needs no memory and a phase that only waits for memory; with
+// the 8 warps the register file allows, on average 3.5 warps have window rows in flight and the HBM stream runs at
+// 5.1-5.5 TB/s; the tensor-core dense part needs only 4 warps per SM (rollout_e32v4_kernel without the window:
+// 35 ms at 4 warps, 31 ms at 8-12).  Here the two phases run in DIFFERENT warps of a persistent CTA:
+//   * 4 dense warps (one per scheduler): 3xTF32 mma.sync tile arithmetic of rollout_e32v4_kernel for TWO
+//     16-trajectory groups each, alternately (residual streams of both groups in registers);
+//   * 8 attention warps, one per group in flight (8 groups = 128 trajectories per SM): warp_attn_e32<4> over the
+//     group's window, 16 rows in flight per lane, always streaming;
+//   * hand-off per (group, step, layer) through a 16 x 32 query / attention-output tile in shared memory and two
+//     mbarriers (qready: dense -> attention after k, v were appended to the ring and q staged; oready: back);
+//     a group's dense warp and attention warp sit on the same scheduler (warp ids d, 4 + d, 8 + d).
+// Arithmetic (and therefore every result bit) is the one of rollout_e32v4_kernel<NCTX, true>.
+// ------------------------------------------------------------------------------------------------
+constexpr int WS_DW = 4;              // dense warps
+constexpr int WS_NG = 8;              // groups in flight per CTA = attention warps
+constexpr int WS_THREADS = 32 * (WS_DW + WS_NG);
+#ifndef WS_PROF
+#define WS_PROF 0          // 1: per-warp wait / phase cycle counters (TRPX_WS_PROF=1 prints them)
+#endif
+
+template <int NCTX>
+__global__ void __launch_bounds__(WS_THREADS, 1) rollout_e32ws_kernel(RolloutParams p) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t qready[WS_NG];
+    __shared__ __align__(8) uint64_t oready[WS_NG];
+    const Gpt2Layout& L = p.lay;
+    const int C = L.n_ctx, NL = L.n_layer;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* wsm = sm;
+    float* tiles = sm + L.total;                       // [WS_NG][V4G][V4QS]
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        for (int i = 0; i < WS_NG; i++) { mbar_init(&qready[i], 1); mbar_init(&oready[i], 1); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)L.total * 4u;
+        mbar_expect_tx(&bar, bytes);
+        const uint32_t CH = 32768u;
+        for (uint32_t off = 0; off < bytes; off += CH)
+            bulk_g2s(reinterpret_cast<char*>(wsm) + off, reinterpret_cast<const char*>(p.blob_sw) + off,
+                     min(CH, bytes - off), &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const int ngroups = (p.B + V4G - 1) / V4G;
+    const size_t kv_per_g = (size_t)NL * 2 * C * 32;
+    const int nslots = gridDim.x * WS_NG;               // groups in flight on the whole device
+    // L2 prefetch of a group's layer window (4 attention passes of 4 trajectories): the dense warp requests the first
+    // pfD passes when it starts the stage that ends with the hand-over, the attention warp stays pfA passes ahead
+    const int pfD = p.prefetch & 15, pfA = (p.prefetch >> 4) & 15;
+    // slot gi of CTA b works on groups  r * nslots + gi * gridDim.x + b  (r = 0, 1, ...): a partly filled last round
+    // spreads over all SMs
+
+    if (warp >= WS_DW) {
+        // ================= attention warp: one slot =================
+        const int gi = warp - WS_DW;
+        float* tile = tiles + gi * (V4G * V4QS);
+        float* kvs = p.kv + (size_t)(blockIdx.x * WS_NG + gi) * V4G * kv_per_g;
+        uint32_t ph = 0;
+#if WS_PROF
+        long long twait = 0;
+        const long long tstart = clock64();
+#endif
+        for (int grp = gi * gridDim.x + blockIdx.x; grp < ngroups; grp += nslots) {
+            for (int s = 0; s < p.S; s++) {
+                const int Lk = min(s + 1, C);
+                for (int l = 0; l < NL; l++) {
+#if WS_PROF
+                    const long long tw0 = clock64();
+#endif
+                    mbar_wait_backoff(&qready[gi], ph, p.spin_ns);
+                    ph ^= 1u;
+#if WS_PROF
+                    twait += clock64() - tw0;
+#endif
+                    int pfdone = pfD;                  // passes whose windows have been requested into L2
+                    if (pfA > 0 && Lk > 1 && pfdone < pfA) {
+                        const int upto = min(pfA, 4) - 1;
+                        if (lane < 4 * (upto - pfdone + 1)) {
+                            const float* kp = kvs + (size_t)(4 * pfdone + lane) * kv_per_g + (size_t)(l * 2) * C * 32;
+                            prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
+                            prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+                        }
+                        pfdone = upto + 1;
+                    }
+                    {
+                        // ---- q, k, v of the group's 16 trajectories from LN1(h) (3xTF32 tile products) ----
+                        const float* w = wsm + l * L.layer_stride;
+                        const int g = lane >> 2, q = lane & 3;
+                        const int slot = s % C;
+                        uint32_t ah[4][4], al[4][4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            float x[4];
+#pragma unroll
+                            for (int rr = 0; rr < 2; rr++) {
+                                const float2 v2 = *reinterpret_cast<const float2*>(tile + (g + 8 * rr) * V4QS + 8 * t + 2 * q);
+                                x[2 * rr] = v2.x;
+                                x[2 * rr + 1] = v2.y;
+                            }
+                            frag_c2a(x, ah[t], al[t]);
+                        }
+                        __syncwarp();                          // every lane holds its fragments: the tile may take q
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            float f[4][4];
+#pragma unroll
+                            for (int t = 0; t < 4; t++) frag_bias(f[t], w + L.bqkv + 32 * c, t, q);
+                            gemv_mma<4, 4>(f, ah, al, w + L.wqkv, 96, 4 * c, g, q);
+#pragma unroll
+                            for (int rr = 0; rr < 2; rr++) {
+                                float* dst = (c == 0) ? tile + (g + 8 * rr) * V4QS + 2 * q
+                                                      : kvs + (size_t)(g + 8 * rr) * kv_per_g +
+                                                            (size_t)(l * 2 + (c - 1)) * C * 32 + slot * 32 + 2 * q;
+#pragma unroll
+                                for (int t = 0; t < 4; t++)
+                                    *reinterpret_cast<float2*>(dst + 8 * t) = make_float2(f[t][2 * rr], f[t][2 * rr + 1]);
+                            }
+                        }
+                        __syncwarp();                          // q tile and ring rows visible to the whole warp
+                    }
+#pragma unroll 1
+                    for (int t4 = (WS_PROF && (p.prefetch & 256)) ? 4 : 0; t4 < 4; t4++) {
+                        const float* kvl = kvs + (size_t)(4 * t4) * kv_per_g + (size_t)(l * 2) * C * 32;
+                        if (pfA > 0 && Lk > 1) {
+                            const int upto = min(t4 + pfA, 3);
+                            if (pfdone <= upto) {
+                                const int np = 4 * (upto - pfdone + 1);
+                                if (lane < np) {
+                                    const float* kp = kvs + (size_t)(4 * pfdone + lane) * kv_per_g + (size_t)(l * 2) * C * 32;
+                                    prefetch_l2_bulk(kp, (uint32_t)Lk * 128u);
+                                    prefetch_l2_bulk(kp + C * 32, (uint32_t)Lk * 128u);
+                                }
+                                pfdone = upto + 1;
+                            }
+                        }
+                        float* tl = tile + 4 * t4 * V4QS;
+                        if (Lk == NCTX)
+                            warp_attn_e32<4, NCTX, true, V4QS, V4QS>(tl, kvl, kv_per_g, C, Lk, tl, lane);
+                        else
+                            warp_attn_e32<4, NCTX, false, V4QS, V4QS>(tl, kvl, kv_per_g, C, Lk, tl, lane);
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&oready[gi]);
+                }
+            }
+        }
+#if WS_PROF
+        if (p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
+            p.prof[2 * warp] = twait;
+            p.prof[2 * warp + 1] = clock64() - tstart;
+        }
+#endif
+        return;
+    }
+
+    // ================= dense warp: slots `warp` (A) and `warp + 4` (B), alternately =================
+    const int g = lane >> 2, q = lane & 3;
+    const float* gw = wsm + L.lnfw;
+    const int nsteps = p.S * NL;
+    float h[4][4], hB[4][4];           // residual stream of the slot being worked on / of the other slot
+    uint32_t ph = 0, phB = 0;
+#if WS_PROF
+    long long twait = 0, tA = 0, tB = 0, tC = 0;
+    const long long tstart = clock64();
+#endif
+    for (int r = 0;; r++) {
+        const int grp0 = r * nslots + warp * gridDim.x + blockIdx.x;
+        const int grp1 = grp0 + WS_DW * gridDim.x;
+        if (grp0 >= ngroups) break;
+        const bool act1 = grp1 < ngroups;
+        for (int n = 0; n <= nsteps; n++) {
+            const int s = n / NL, l = n - s * NL;
+#pragma unroll 1
+            for (int k = 0; k < 2; k++) {
+                if (k == 0 || act1) {
+                    const int gi = warp + WS_DW * k;
+                    const int grp = k ? grp1 : grp0;
+                    float* tile = tiles + gi * (V4G * V4QS);
+                    float* kvs = p.kv + (size_t)(blockIdx.x * WS_NG + gi) * V4G * kv_per_g;
+                    const int br[2] = {grp * V4G + g, grp * V4G + g + 8};     // the lane's two trajectories
+                    if (n < nsteps && lane < 4 * pfD && s > 0) {      // windows of the first pfD attention passes of (s, l)
+                        const float* kp = kvs + (size_t)lane * kv_per_g + (size_t)(l * 2) * C * 32;
+                        const uint32_t nb = (uint32_t)min(s + 1, C) * 128u;
+                        prefetch_l2_bulk(kp, nb);
+                        prefetch_l2_bulk(kp + C * 32, nb);
+                    }
+                    if (n == 0) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const float2 pe = __ldg(reinterpret_cast<const float2*>(p.pe + 8 * t + 2 * q));
+#pragma unroll
+                            for (int rr = 0; rr < 2; rr++) {
+                                float2 x = make_float2(0.f, 0.f);
+                                if (br[rr] < p.B)
+                                    x = *reinterpret_cast<const float2*>(p.x0 + (size_t)br[rr] * p.x0_stride + 8 * t + 2 * q);
+                                h[t][2 * rr] = x.x + pe.x;
+                                h[t][2 * rr + 1] = x.y + pe.y;
+                            }
+                        }
+                    } else {
+                        // ---- second half of the layer whose attention has just been done ----
+                        const float* w = wsm + (l == 0 ? NL - 1 : l - 1) * L.layer_stride;
+#if WS_PROF
+                        const long long tw0 = clock64();
+#endif
+                        mbar_wait_backoff(&oready[gi], ph, p.spin_ns);
+                        ph ^= 1u;
+#if WS_PROF
+                        const long long tp1 = clock64();
+                        twait += tp1 - tw0;
+#endif
+                        uint32_t ah[4][4], al[4][4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            float o[4];
+#pragma unroll
+                            for (int rr = 0; rr < 2; rr++) {
+                                const float2 v2 = *reinterpret_cast<const float2*>(tile + (g + 8 * rr) * V4QS + 8 * t + 2 * q);
+                                o[2 * rr] = v2.x;
+                                o[2 * rr + 1] = v2.y;
+                            }
+                            frag_c2a(o, ah[t], al[t]);
+                        }
+                        {
+                            float acc[4][4];
+#pragma unroll
+                            for (int t = 0; t < 4; t++) frag_bias(acc[t], w + L.bproj, t, q);
+                            gemv_mma<4, 4>(acc, ah, al, w + L.wproj, 32, 0, g, q);
+#pragma unroll
+                            for (int t = 0; t < 4; t++)
+#pragma unroll
+                                for (int i = 0; i < 4; i++) h[t][i] += acc[t][i];
+                        }
+                        frag_ln(h, w + L.ln2w, w + L.ln2b, p.eps, q, ah, al);
+                        float pr[4][4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) frag_bias(pr[t], w + L.bpr, t, q);
+#pragma unroll 1
+                        for (int tf0 = 0; tf0 < 16; tf0 += 4) {
+                            float fc[4][4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) frag_bias(fc[j], w + L.bfc, tf0 + j, q);
+                            gemv_mma<4, 4>(fc, ah, al, w + L.wfc, 128, tf0, g, q);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) fc[j][i] = gelu_new_sig(fc[j][i]);
+                                uint32_t fh[4], fl[4];
+                                frag_c2a(fc[j], fh, fl);
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    float w0, w1;
+                                    ldb(w + L.wpr, 32, tf0 + j, u, g, q, w0, w1);
+                                    mma3(pr[u], fh, fl, w0, w1);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; t++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++) h[t][i] += pr[t][i];
+#if WS_PROF
+                        const long long tp2 = clock64();
+                        tA += tp2 - tp1;
+#endif
+                        if (l == 0) {
+                            // ---- step s - 1 is complete: final LayerNorm + linear head, next input ----
+                            frag_ln(h, gw, gw + 32, p.eps, q, ah, al);
+                            float y[4][4];
+#pragma unroll
+                            for (int t = 0; t < 4; t++) frag_bias(y[t], gw + 64 + 1024, t, q);
+                            gemv_mma<4, 4>(y, ah, al, gw + 64, 32, 0, g, q);
+                            const int pnext = min(s, C - 1);
+#pragma unroll
+                            for (int t = 0; t < 4; t++) {
+                                const float2 pe = __ldg(reinterpret_cast<const float2*>(p.pe + pnext * 32 + 8 * t + 2 * q));
+#pragma unroll
+                                for (int rr = 0; rr < 2; rr++) {
+                                    if (br[rr] < p.B)
+                                        *reinterpret_cast<float2*>(p.out + (size_t)br[rr] * p.out_stride + (size_t)(s - 1) * 32 +
+                                                                   8 * t + 2 * q) = make_float2(y[t][2 * rr], y[t][2 * rr + 1]);
+                                    h[t][2 * rr] = y[t][2 * rr] + pe.x;
+                                    h[t][2 * rr + 1] = y[t][2 * rr + 1] + pe.y;
+                                }
+                            }
+                        }
+                    }
+#if WS_PROF
+                    const long long tp3 = clock64();
+#endif
+                    if (n < nsteps) {
+                        // ---- first half of layer l of step s: LN1, q / k / v, append to the ring, hand over ----
+                        const float* w = wsm + l * L.layer_stride;
+                        // LN1(h) goes to the tile as plain FP32 rows: the attention warp computes q, k, v from it
+                        frag_ln_store(h, w + L.ln1w, w + L.ln1b, p.eps, q, tile + g * V4QS, tile + (g + 8) * V4QS);
+#if WS_PROF
+                        const long long tp4 = clock64();
+                        tB += tp4 - tp3;
+#endif
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&qready[gi]);
+#if WS_PROF
+                        tC += clock64() - tp4;
+#endif
+                    } else if (p.presents != nullptr) {
+                        const int Tk = min(p.S, C);
+                        const int H = 4, hd = 8;
+                        const size_t per_l = (size_t)2 * p.B * H * Tk * hd;
+                        const int hh = lane >> 3, d = lane & 7;
+                        for (int tg = 0; tg < V4G; tg++) {
+                            const int b = grp * V4G + tg;
+                            if (b >= p.B) break;
+                            for (int rr = 0; rr < NL * 2 * Tk; rr++) {
+                                const int t = rr % Tk, lw = rr / Tk;
+                                const int which = lw & 1, ll = lw >> 1;
+                                const int sl = (p.S - Tk + t) % C;
+                                p.presents[(size_t)ll * per_l + ((((size_t)which * p.B + b) * H + hh) * Tk + t) * hd + d] =
+                                    kvs[(size_t)tg * kv_per_g + ((size_t)lw * C + sl) * 32 + lane];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                // the other slot becomes the current one
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const float x = h[t][i]; h[t][i] = hB[t][i]; hB[t][i] = x; }
+                { const uint32_t x = ph; ph = phB; phB = x; }
+            }
+        }
+    }
+#if WS_PROF
+    if (p.prof != nullptr && blockIdx.x == 0 && lane == 0) {
+        p.prof[2 * warp] = twait;
+        p.prof[2 * warp + 1] = clock64() - tstart;
+        p.prof[32 + 3 * warp] = tA;
+        p.prof[32 + 3 * warp + 1] = tB;
+        p.prof[32 + 3 * warp + 2] = tC;
+    }
+#endif
 }
 
 // swizzled weight image for the tensor-core kernel: every [K][N] matrix element (k, n) moves to column
@@ -2853,6 +3259,14 @@ int launch_v4(const RolloutParams& p, int n_ctx, int grid, int block, size_t sme
     return launch_v4_one<64, true>(p, grid, block, smem, st);
 }
 
+template <int NCTX>
+int launch_ws_one(const RolloutParams& p, int grid, size_t smem, cudaStream_t st) {
+    TRPX_CUDA(cudaFuncSetAttribute(rollout_e32ws_kernel<NCTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_e32ws_kernel<NCTX><<<grid, WS_THREADS, smem, st>>>(p);
+    TRPX_CUDA(cudaGetLastError());
+    return TRPX_OK;
+}
+
 int ensure_kv(trpx_gpt2_t h, size_t bytes) {
     if (bytes <= h->kv_bytes) return TRPX_OK;
     if (h->kv) {
@@ -3005,7 +3419,7 @@ int trpx_gpt2_load_weights(trpx_gpt2_t h, const float* const* w, int n, const fl
 
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp, int max_ctas) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(variant >= 0 && variant <= 10, "variant must be 0..10");
+    TRPX_REQUIRE(variant >= 0 && variant <= 11, "variant must be 0..11");
     TRPX_REQUIRE(warps_per_cta >= 0 && warps_per_cta <= 32, "warps_per_cta must be 0..32");
     TRPX_REQUIRE(traj_per_warp == 0 || traj_per_warp == 1 || traj_per_warp == 2 || traj_per_warp == 4 ||
                      traj_per_warp == 8 || (traj_per_warp == 16 && (variant == 7 || variant == 9)),
@@ -3073,8 +3487,58 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
                 if (rc) return rc;
             }
             p.kv = h->kv;
+            p.prefetch = h->tune_prefetch ? 3 : 0;       // bit 0: first pass at layer start, bit 1: next pass during a pass
+            if (const char* e = getenv("TRPX_V4_PF")) p.prefetch = atoi(e);      // tuning knob (scripts/sweep_rollout.py)
             h->last_variant = 6; h->last_grid = grid; h->last_block = Wc * 32; h->last_smem = (int)smem; h->last_group = V4G;
             return launch_v4(p, L.n_ctx, grid, Wc * 32, smem, st);
+        }
+    }
+    // ---- warp-specialised streaming kernel (variant 11): dense warps + attention warps ----
+    if (e32_shape && use_cache && h->tune_variant == 11 && (L.n_ctx == 8 || L.n_ctx == 16 || L.n_ctx == 32 || L.n_ctx == 64)) {
+        const int sms = h->tune_max_ctas > 0 ? std::min(h->tune_max_ctas, h->sm_count) : h->sm_count;
+        const int ngroups = (B + V4G - 1) / V4G;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(out)) & 7) == 0 &&
+                             (x0_stride % 2) == 0 && (out_stride % 2) == 0;
+        const size_t smem = wbytes + (size_t)WS_NG * V4G * V4QS * sizeof(float);
+        if (aligned && smem + 1024 <= (size_t)h->smem_optin) {
+            const int grid = std::min(sms, ngroups);
+            int rc = ensure_kv(h, (size_t)grid * WS_NG * V4G * kv_per_traj);
+            if (rc) return rc;
+            p.kv = h->kv;
+            h->last_variant = 11; h->last_grid = grid; h->last_block = WS_THREADS; h->last_smem = (int)smem; h->last_group = V4G;
+            p.prefetch = 0x11;                            // low nibble: passes requested by the dense warp, high: attention look-ahead
+            if (const char* e = getenv("TRPX_WS_PF")) p.prefetch = (int)strtol(e, nullptr, 0);      // tuning knob
+            p.spin_ns = 100;
+            if (const char* e = getenv("TRPX_WS_NS")) p.spin_ns = atoi(e);
+#if WS_PROF
+            static long long* prof_dev = nullptr;
+            if (getenv("TRPX_WS_PROF")) {
+                if (!prof_dev) TRPX_CUDA(cudaMalloc(&prof_dev, 64 * sizeof(long long)));
+                p.prof = prof_dev;
+                int rc2;
+                switch (L.n_ctx) {
+                    case 8: rc2 = launch_ws_one<8>(p, grid, smem, st); break;
+                    case 16: rc2 = launch_ws_one<16>(p, grid, smem, st); break;
+                    case 32: rc2 = launch_ws_one<32>(p, grid, smem, st); break;
+                    default: rc2 = launch_ws_one<64>(p, grid, smem, st); break;
+                }
+                if (rc2) return rc2;
+                long long hp[64];
+                TRPX_CUDA(cudaStreamSynchronize(st));
+                TRPX_CUDA(cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost));
+                for (int w = 0; w < WS_DW + WS_NG; w++)
+                    fprintf(stderr, "ws prof B=%d S=%d warp %2d (%s): wait %lld of %lld cycles (%.1f %%)\n", B, S, w, w < WS_DW ? "dense" : "attn ",
+                            hp[2 * w], hp[2 * w + 1], 100.0 * (double)hp[2 * w] / (double)hp[2 * w + 1]);
+                fprintf(stderr, "ws prof B=%d dense warp 0: proj+MLP %lld, LN1+QKV+stores %lld, fence+arrive %lld cycles\n", B, hp[32], hp[33], hp[34]);
+                return TRPX_OK;
+            }
+#endif
+            switch (L.n_ctx) {
+                case 8: return launch_ws_one<8>(p, grid, smem, st);
+                case 16: return launch_ws_one<16>(p, grid, smem, st);
+                case 32: return launch_ws_one<32>(p, grid, smem, st);
+                default: return launch_ws_one<64>(p, grid, smem, st);
+            }
         }
     }
     // ---- second-generation kernel (16 trajectories per warp, 2-D lane tiling): large batches ----
@@ -3168,7 +3632,7 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
             while (G > 1 && (long long)(B + G - 1) / G < (long long)sms * 4) G >>= 1;
         }
         const int ngroups = (B + G - 1) / G;
-        const int max_w = (int)std::min<size_t>((use_cache && G >= 4) ? 8 : 12,
+        const int max_w = (int)std::min<size_t>((use_cache && G >= 4) ? TRPX_E32_CACHE_NT / 32 : 12,
                                                 ((size_t)h->smem_optin - 1024 - wbytes) / ((size_t)64 * G * sizeof(float)));
         if (max_w < 1) {
             use_e32 = false;

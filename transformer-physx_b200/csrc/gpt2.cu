@@ -3092,68 +3092,54 @@ __global__ void __launch_bounds__(FT_THREADS, 4) forward_e32_tc_kernel(ForwardPa
                 pr[((((size_t)which * p.B + b) * H + hh) * Tk + t) * HD + d] = (which ? vs : ks)[t * FT_LDK + e];
             }
         }
-        // causal attention: a lane owns (token r0 + lane/2, heads 2*(lane&1), 2*(lane&1)+1); query t sees keys [0, Tp + t].
+        // causal attention: query t sees keys [0, Tp + t].  A thread owns one head of the token pair (i, T - 1 - i): every
+        // thread of the CTA walks T + 1 (+ 2 Tp) keys, whatever its tokens (a thread per token walked 1 ... T keys and the
+        // CTA waited for the longest), and the lanes of a warp read the same key row at the same time (broadcast).
         // Scores in the log2 domain: q is pre-multiplied by log2(e) / sqrt(hd) (attention.py:97-99 divides the scores by
-        // sqrt(hd)), the softmax is ex2.approx(s - m) (2 ulp; the parity tests sit at 1e-6 against the 1e-5 bar).  Both
-        // heads and two keys advance together: four independent dot-product chains per lane instead of one.
+        // sqrt(hd)), the softmax is ex2.approx(s - m) (2 ulp; the parity tests sit at 1e-6 against the 1e-5 bar).  One pass
+        // over the keys in chunks of 8 with a running maximum (accumulators rescaled once per chunk).
         {
-            const int t = r0 + (lane >> 1);
-            if (t < T) {
+            const int pi = tid >> 2, h0 = (tid & 3) * HD;
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                const int t = side ? T - 1 - pi : pi;
+                if (side ? (2 * pi >= T - 1) : (2 * pi > T - 1)) continue;    // tokens 0 .. T-1 once each (odd T: the middle one on side 0)
                 const int nk = Tp + t + 1;
-                const int h0 = 2 * (lane & 1) * HD;            // first channel of the lane's two heads (adjacent)
-                float qv[2 * HD];
+                float qv[HD];
 #pragma unroll
-                for (int d = 0; d < 2 * HD; d++) qv[d] = qs[t * FT_LDK + h0 + d] * (1.4426950408889634f / 2.8284271247461903f);
-                float m0 = -INFINITY, m1 = -INFINITY;
-                for (int j = 0; j < nk; j += 2) {
-                    const float* k0 = ks + j * FT_LDK + h0;
-                    const float* k1 = ks + min(j + 1, nk - 1) * FT_LDK + h0;
-                    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+                for (int d = 0; d < HD; d++) qv[d] = qs[t * FT_LDK + h0 + d] * (1.4426950408889634f / 2.8284271247461903f);
+                float m0 = -INFINITY, den0 = 0.f, o[HD];
 #pragma unroll
-                    for (int d = 0; d < HD; d++) {
-                        s00 = fmaf(qv[d], k0[d], s00);
-                        s10 = fmaf(qv[HD + d], k0[HD + d], s10);
-                        s01 = fmaf(qv[d], k1[d], s01);
-                        s11 = fmaf(qv[HD + d], k1[HD + d], s11);
+                for (int d = 0; d < HD; d++) o[d] = 0.f;
+                for (int j0 = 0; j0 < nk; j0 += 8) {
+                    float s0[8], c0 = -INFINITY;
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const float* kr = ks + min(j0 + jj, nk - 1) * FT_LDK + h0;
+                        float u = 0.f;
+#pragma unroll
+                        for (int d = 0; d < HD; d++) u = fmaf(qv[d], kr[d], u);
+                        s0[jj] = (j0 + jj < nk) ? u : -INFINITY;
+                        c0 = fmaxf(c0, s0[jj]);
                     }
-                    m0 = fmaxf(m0, fmaxf(s00, s01));
-                    m1 = fmaxf(m1, fmaxf(s10, s11));
-                }
-                float den0 = 0.f, den1 = 0.f, o[2 * HD];
+                    const float n0 = fmaxf(m0, c0);
+                    const float r0 = ex2_approx(m0 - n0);      // 0 for the first chunk
+                    m0 = n0;
+                    den0 *= r0;
 #pragma unroll
-                for (int d = 0; d < 2 * HD; d++) o[d] = 0.f;
-                for (int j = 0; j < nk; j += 2) {
-                    const bool two = j + 1 < nk;
-                    const float* k0 = ks + j * FT_LDK + h0;
-                    const float* k1 = ks + min(j + 1, nk - 1) * FT_LDK + h0;
-                    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+                    for (int d = 0; d < HD; d++) o[d] *= r0;
 #pragma unroll
-                    for (int d = 0; d < HD; d++) {
-                        s00 = fmaf(qv[d], k0[d], s00);
-                        s10 = fmaf(qv[HD + d], k0[HD + d], s10);
-                        s01 = fmaf(qv[d], k1[d], s01);
-                        s11 = fmaf(qv[HD + d], k1[HD + d], s11);
-                    }
-                    const float e00 = ex2_approx(s00 - m0), e10 = ex2_approx(s10 - m1);
-                    const float e01 = two ? ex2_approx(s01 - m0) : 0.f, e11 = two ? ex2_approx(s11 - m1) : 0.f;
-                    den0 += e00 + e01;
-                    den1 += e10 + e11;
-                    const float* v0 = vs + j * FT_LDK + h0;
-                    const float* v1 = vs + min(j + 1, nk - 1) * FT_LDK + h0;
+                    for (int jj = 0; jj < 8; jj++) {
+                        const float e0 = ex2_approx(s0[jj] - m0);                  // masked keys: 2^-inf = 0
+                        den0 += e0;
+                        const float* vr = vs + min(j0 + jj, nk - 1) * FT_LDK + h0;
 #pragma unroll
-                    for (int d = 0; d < HD; d++) {
-                        o[d] = fmaf(e00, v0[d], o[d]);
-                        o[d] = fmaf(e01, v1[d], o[d]);
-                        o[HD + d] = fmaf(e10, v0[HD + d], o[HD + d]);
-                        o[HD + d] = fmaf(e11, v1[HD + d], o[HD + d]);
+                        for (int d = 0; d < HD; d++) o[d] = fmaf(e0, vr[d], o[d]);
                     }
                 }
-                const float i0 = 1.0f / den0, i1 = 1.0f / den1;
+                const float i0 = 1.0f / den0;
 #pragma unroll
-                for (int d = 0; d < HD; d++) {
-                    a[t * FT_LDX + h0 + d] = o[d] * i0;
-                    a[t * FT_LDX + h0 + HD + d] = o[HD + d] * i1;
-                }
+                for (int d = 0; d < HD; d++) a[t * FT_LDX + h0 + d] = o[d] * i0;
             }
         }
         __syncthreads();                        // all reads of this layer's keys / values are done
@@ -3161,7 +3147,7 @@ __global__ void __launch_bounds__(FT_THREADS, 4) forward_e32_tc_kernel(ForwardPa
         __syncwarp();
         ft_warp_ln(xw, aw, FT_LDX, w + L.ln2w, w + L.ln2b, p.eps, lane);
         __syncwarp();
-        ft_warp_gemm<E, 4 * E>(aw, FT_LDX, w + L.wfc, w + L.bfc, lane, [&](int r, int n, float v) { hw[r * FT_LDH + n] = gelu_new(v); });
+        ft_warp_gemm<E, 4 * E>(aw, FT_LDX, w + L.wfc, w + L.bfc, lane, [&](int r, int n, float v) { hw[r * FT_LDH + n] = gelu_new_sig(v); });
         __syncwarp();
         ft_warp_gemm<4 * E, E>(hw, FT_LDH, w + L.wpr, w + L.bpr, lane, [&](int r, int n, float v) { xw[r * FT_LDX + n] += v; });
         __syncwarp();

@@ -158,8 +158,9 @@ int trpx_mlpemb_load_weights(trpx_mlpemb_t h, const float* const* w_dev, int n_t
 int trpx_mlpemb_embed(trpx_mlpemb_t h, const float* x_dev, float* g_dev, long long N, void* stream);
 /* LorenzEmbedding.recover (:107-118): g[N,32] -> x[N,3] */
 int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g_dev, float* x_dev, long long N, void* stream);
-/* recover kernel selection: 0 automatic (tensor-core 3xTF32 kernel for N >= 16384, FP32 SIMT kernel below),
- * 1 FP32 SIMT kernel only (A/B measurements, bit-stable results). */
+/* recover kernel selection: 0 automatic (tcgen05 kind::tf32 kernel, csrc/mlpemb_umma.cu, for N >= 4 x 128 x SM count;
+ * 3xTF32 mma.sync kernel for N >= 16384; FP32 SIMT kernel below), 1 FP32 SIMT kernel only (A/B measurements,
+ * bit-stable results), 2 never the tcgen05 kernel (A/B), 3 same as 0. */
 int trpx_mlpemb_set_recover_mode(trpx_mlpemb_t h, int mode);
 /* Fused `recover` + MSE of Trainer.eval_states (trphysx/utils/trainer.py:380-390):
  * mse = mean((recover(g) - target)^2) over N*3 values, written to mse_dev (device scalar).  The recovered states

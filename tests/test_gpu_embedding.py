@@ -376,6 +376,36 @@ def test_recover_tensor_core_kernel(dev, kind, n):
     assert abs(float(got) - float(want)) <= 5e-6 * float(want)
 
 
+@pytest.mark.parametrize("kind,n", [("rossler", 75776), ("lorenz", 200001), ("rossler", 75775)])
+def test_recover_tcgen05_kernel(dev, kind, n):
+    """recover for N >= 4 x 128 x (SM count) samples runs on the tcgen05 kernel (csrc/mlpemb_umma.cu: layer 1 as
+    error-compensated kind::tf32 MMAs with accumulators in tensor memory, layer 2 in FP32 in the epilogue): against the
+    oracle at the FP32 bar and against the other two kernels; exact tile multiple, ragged last tile, and one sample below
+    the switch (which must take the mma.sync kernel)."""
+    cfg = synth.make_config(kind)
+    w = synth.lorenz_embedding_weights(cfg, 921)
+    emb = make_lorenz(cfg, 921, kind, dev)
+    g = torch.from_numpy(synth.normal_embeds((n, cfg.n_embd), 922)) * 1.5
+    ref = O.lorenz_recover(O.to_torch(w), cfg, g)
+    outs = {}
+    for mode in (0, 2, 1):
+        emb.set_recover_mode(mode)
+        outs[mode] = emb.recover(g.to(dev))
+    emb.set_recover_mode(0)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    if n >= 4 * 128 * sms:
+        assert not torch.equal(outs[0], outs[2])          # really the tcgen05 kernel
+    else:
+        assert torch.equal(outs[0], outs[2])
+    for mode in (0, 2, 1):
+        e = O.rel_l2(outs[mode].cpu(), ref)
+        print(f"recover {kind} N={n} mode {mode}: rel-L2 {e:.2e}")
+        assert e < TOL
+    assert float((outs[0] - outs[1]).abs().max()) < 1e-4 * float(ref.abs().max())
+    # rows of the last (partial) tile and the first rows of the next tile of another CTA
+    assert O.rel_l2(outs[0][-200:].cpu(), ref[-200:]) < TOL and O.rel_l2(outs[0][:300].cpu(), ref[:300]) < TOL
+
+
 def test_rollout_to_host_pipeline(dev):
     """evaluation.rollout_to_host: pinned x0 -> embed -> generate -> chunked recover with overlapped D2H equals the
     three public calls done one after the other."""

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libtrpx.so")
-SOURCES = ["api.cu", "gpt2.cu", "gpt2_tmem.cu", "gpt2_train.cu", "gpt2_train_tc.cu", "mlpemb.cu", "mlpemb_train.cu", "cyl.cu", "cyl_umma.cu", "cyl_train.cu", "gs.cu"]
+SOURCES = ["api.cu", "gpt2.cu", "gpt2_tmem.cu", "gpt2_train.cu", "gpt2_train_tc.cu", "mlpemb.cu", "mlpemb_umma.cu", "mlpemb_train.cu", "cyl.cu", "cyl_umma.cu", "cyl_train.cu", "gs.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

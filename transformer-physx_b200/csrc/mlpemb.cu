@@ -2,6 +2,7 @@
 // Reference: trphysx/embedding/embedding_lorenz.py:94-105 (embed), :107-118 (recover), :120-142
 // (koopmanOperation), :144-157 (koopmanOperator); enn_trainer.py:97-99 (clip_grad_norm_ + optimizer.step).
 #include "mlpemb.cuh"
+#include "mlpemb_umma.cuh"
 #include <cmath>
 #include <algorithm>
 
@@ -625,6 +626,8 @@ int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g, float* x, long long N, 
     TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int Hp = (L.Hd + 7) & ~7;
     const size_t smem_tc = sizeof(float) * ((size_t)2 * Hp * RTC_LD + (size_t)4 * Hp);
+    if ((h->recover_mode == 0 || h->recover_mode == 3) && mlp_recover_umma_ok(h, N))
+        return mlp_recover_umma(h, g, x, N, (cudaStream_t)stream);      // tcgen05 kernel (mlpemb_umma.cu)
     if (h->recover_mode != 1 && N >= 16384 && smem_tc + 1024 <= (size_t)h->smem_optin) {
         // tensor-core kernel: one persistent CTA per SM, 12 warps, 16 samples per warp-tile
         TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
@@ -642,7 +645,7 @@ int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g, float* x, long long N, 
 
 int trpx_mlpemb_set_recover_mode(trpx_mlpemb_t h, int mode) {
     TRPX_REQUIRE(valid(h), "invalid handle");
-    TRPX_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (automatic) or 1 (FP32 SIMT kernel only)");
+    TRPX_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (automatic), 1 (FP32 SIMT kernel only), 2 (no tcgen05 kernel) or 3 (same as 0)");
     h->recover_mode = mode;
     return TRPX_OK;
 }

@@ -99,7 +99,8 @@ class LorenzEmbedding(EmbeddingModel):
         return x
 
     def set_recover_mode(self, mode: int = 0):
-        """0: automatic (3xTF32 tensor-core kernel for N >= 16384 samples), 1: FP32 SIMT kernel only."""
+        """0: automatic (tcgen05 kernel for N >= 4 x 128 x SM count samples, 3xTF32 mma.sync kernel for N >= 16384),
+        1: FP32 SIMT kernel only, 2: never the tcgen05 kernel (A/B)."""
         self._recover_mode = mode
         for h, _ in self._handles.values():
             N.check(N.lib().trpx_mlpemb_set_recover_mode(h, mode))

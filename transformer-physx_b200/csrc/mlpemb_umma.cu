@@ -5,7 +5,7 @@
 // Layer 1 ([N x 32] . [32 x 500]) is 91 % of the FLOPs.  A persistent CTA per SM keeps the layer-1 weights as TF32 hi / lo
 // planes in shared memory (K-major no-swizzle core-matrix order [k/4][n][4 floats], hidden width padded to 512 with zero
 // rows) and runs 128-sample tiles through
-//   * 4 producer warps: thread = sample row; loads the 32 inputs, splits them into TF32 hi / lo and stores the two
+//   * 2 producer warps: thread = two sample rows; loads the 32 inputs, splits them into TF32 hi / lo and stores the two
 //     A planes ([k/4][row][4 floats]) of a two-stage ring (generic-proxy stores + fence.proxy.async);
 //   * 1 MMA warp (one lane): per half of the hidden units (256 columns of tensor memory each, so the epilogue of one half
 //     overlaps the MMAs of the other) 12 MMAs M128 x N256 x K8 kind::tf32 = the error-compensated product
@@ -17,15 +17,16 @@
 #include "mlpemb.cuh"
 #include "mlpemb_umma.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 using namespace trpx;
 
 namespace {
 
-constexpr int RU_EPI_WARPS = 16, RU_PROD_WARPS = 4;
+constexpr int RU_EPI_WARPS = 16, RU_PROD_WARPS = 2;
 constexpr int RU_MMA_WARP = RU_EPI_WARPS;
 constexpr int RU_PROD_WARP0 = RU_EPI_WARPS + 1;
-constexpr int RU_THREADS = (RU_EPI_WARPS + 1 + RU_PROD_WARPS) * 32;       // 672
+constexpr int RU_THREADS = (RU_EPI_WARPS + 1 + RU_PROD_WARPS) * 32;       // 608 (<= 104 registers per thread)
 constexpr int RU_M = 128;                                                 // samples per tile
 constexpr int RU_NP = 512;                                                // hidden width, padded
 constexpr int RU_B_PLANE = 8 * RU_NP * 16;                                // bytes of one weight plane [8][512][4 f]
@@ -72,6 +73,38 @@ __device__ __forceinline__ void ru_fence_proxy_async() { asm volatile("fence.pro
 __device__ __forceinline__ void ru_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// packed FP32 (f32x2), element-wise: (d0, d1) += (a0, a1) * (b0, b1)   and   (d0, d1) = (a0, a1) + (b0, b1)
+__device__ __forceinline__ void ru_ffma2v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n.reg .b64 ra, rb, rc;\n"
+        "mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%0, %1};\n"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rc;\n}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void ru_fadd2v(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n.reg .b64 ra, rb, rc;\n"
+        "mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n"
+        "add.rn.f32x2 rc, ra, rb;\n"
+        "mov.b64 {%0, %1}, rc;\n}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// 16 accumulator columns (hidden units u .. u + 15, u even) of a sample row through bias, ReLU and layer 2: two hidden
+// units per packed instruction, even / odd partial sums (y[0..1] output 0, y[2..3] output 1, y[4..5] output 2)
+__device__ __forceinline__ void ru_layer2_16(const uint32_t (&r)[16], const float4* __restrict__ tab, float (&y)[6]) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+        const float4 wa = tab[c], wb = tab[c + 1];           // {w0a, w0b, w1a, w1b}, {w2a, w2b, ba, bb}
+        float va, vb;
+        ru_fadd2v(va, vb, __uint_as_float(r[c]), __uint_as_float(r[c + 1]), wb.z, wb.w);
+        va = fmaxf(va, 0.f);
+        vb = fmaxf(vb, 0.f);
+        ru_ffma2v(y[0], y[1], va, vb, wa.x, wa.y);
+        ru_ffma2v(y[2], y[3], va, vb, wa.z, wa.w);
+        ru_ffma2v(y[4], y[5], va, vb, wb.x, wb.y);
+    }
+}
 __device__ __forceinline__ void ru_split4(const float4 v, float4& hi, float4& lo) {
     hi.x = __uint_as_float(tf32_rna_bits(v.x)); lo.x = v.x - hi.x;
     hi.y = __uint_as_float(tf32_rna_bits(v.y)); lo.y = v.y - hi.y;
@@ -81,7 +114,7 @@ __device__ __forceinline__ void ru_split4(const float4 v, float4& hi, float4& lo
 
 __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const float* __restrict__ blob, MlpLayout L,
                                                                          const float* __restrict__ g,
-                                                                         float* __restrict__ x, long long N) {
+                                                                         float* __restrict__ x, long long N, int debug) {
     extern __shared__ __align__(128) unsigned char ru_smem[];
     unsigned char* b_hi = ru_smem;
     unsigned char* b_lo = b_hi + RU_B_PLANE;
@@ -89,7 +122,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
     float4* decB = reinterpret_cast<float4*>(a_st + RU_STAGES * 2 * RU_A_PLANE);   // [512] {V2[0][u], V2[1][u], V2[2][u], c1[u]}
     float4* ypart = decB + RU_NP;                                         // [tile parity][slice 1..3][row]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ypart + 2 * 3 * RU_M);
-    uint64_t* a_full = bars;                 // [stage]  producers -> MMA           (4 arrivals: one per producer warp)
+    uint64_t* a_full = bars;                 // [stage]  producers -> MMA           (one arrival per producer warp)
     uint64_t* a_empty = bars + 2;            // [stage]  tcgen05.commit -> producers
     uint64_t* tfull = bars + 4;              // [half]   tcgen05.commit -> epilogue
     uint64_t* tempty = bars + 6;             // [half]   epilogue -> MMA            (16 arrivals: one per epilogue warp)
@@ -113,8 +146,14 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
         reinterpret_cast<float4*>(b_hi)[i] = hi;
         reinterpret_cast<float4*>(b_lo)[i] = lo;
     }
-    for (int i = tid; i < RU_NP; i += RU_THREADS)
-        decB[i] = i < Hd ? __ldg(reinterpret_cast<const float4*>(blob + L.decB) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // layer-2 table in pairs of hidden units (a = 2p, b = 2p + 1): decB[2p] = {w0a, w0b, w1a, w1b}, decB[2p + 1] = {w2a, w2b, c1a, c1b}
+    for (int p2 = tid; p2 < RU_NP / 2; p2 += RU_THREADS) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 ua = 2 * p2 < Hd ? __ldg(reinterpret_cast<const float4*>(blob + L.decB) + 2 * p2) : z;
+        const float4 ub = 2 * p2 + 1 < Hd ? __ldg(reinterpret_cast<const float4*>(blob + L.decB) + 2 * p2 + 1) : z;
+        decB[2 * p2] = make_float4(ua.x, ub.x, ua.y, ub.y);
+        decB[2 * p2 + 1] = make_float4(ua.z, ub.z, ua.w, ub.w);
+    }
     ru_fence_proxy_async();
     ru_fence_before();
     __syncthreads();
@@ -131,38 +170,33 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
         const float sd0 = __ldg(blob + L.sd), sd1 = __ldg(blob + L.sd + 1), sd2 = __ldg(blob + L.sd + 2);
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-            float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+            float y[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int hf = 0; hf < 2; hf++) {
                 mbar_wait_backoff(&tfull[hf], it & 1, 32);
                 ru_fence_after();
                 const int u0 = hf * 256 + e * 64;
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)u0;
-#pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t ra[16], rb[16];
-                    ru_tmem_ld16(tcol + c0, ra);
-                    ru_tmem_ld16(tcol + c0 + 16, rb);
-                    ru_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 16; c++) {
-                        const float4 wb = decB[u0 + c0 + c];
-                        const float v = fmaxf(__uint_as_float(ra[c]) + wb.w, 0.f);
-                        ffma2(y0, y1, wb.x, wb.y, v);
-                        y2 = fmaf(v, wb.z, y2);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 16; c++) {
-                        const float4 wb = decB[u0 + c0 + 16 + c];
-                        const float v = fmaxf(__uint_as_float(rb[c]) + wb.w, 0.f);
-                        ffma2(y0, y1, wb.x, wb.y, v);
-                        y2 = fmaf(v, wb.z, y2);
-                    }
-                }
+                // 16 columns at a time, the next tcgen05.ld in flight under the arithmetic of the previous one; the
+                // accumulator half goes back to the MMA warp as soon as its last columns are in registers
+                uint32_t ra[16], rb[16];
+                ru_tmem_ld16(tcol, ra);
+                ru_wait_ld();
+                ru_tmem_ld16(tcol + 16, rb);
+                if (!(debug & 1)) ru_layer2_16(ra, decB + u0, y);
+                ru_wait_ld();
+                ru_tmem_ld16(tcol + 32, ra);
+                if (!(debug & 1)) ru_layer2_16(rb, decB + u0 + 16, y);
+                ru_wait_ld();
+                ru_tmem_ld16(tcol + 48, rb);
+                if (!(debug & 1)) ru_layer2_16(ra, decB + u0 + 32, y);
+                ru_wait_ld();
                 ru_fence_before();
                 __syncwarp();
                 if (lane == 0) ru_arrive(&tempty[hf]);
+                if (!(debug & 1)) ru_layer2_16(rb, decB + u0 + 48, y);
             }
+            float y0 = y[0] + y[1], y1 = y[2] + y[3], y2 = y[4] + y[5];
             // the four column slices of a row: slices 1..3 go through shared memory, slice 0 finishes the row
             float4* yp = ypart + (it & 1) * 3 * RU_M;
             if (e > 0) yp[(e - 1) * RU_M + row] = make_float4(y0, y1, y2, 0.f);
@@ -196,7 +230,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
                     ru_fence_after();
                     const uint32_t tc = tmem_base + (uint32_t)(hf * 256);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {                     // k = 8 ks .. 8 ks + 7: chunks 2 ks, 2 ks + 1
+                    for (int ks = (debug & 2) ? 4 : 0; ks < 4; ks++) {   // k = 8 ks .. 8 ks + 7: chunks 2 ks, 2 ks + 1
                         const uint64_t ah = ru_desc(sa_hi + ks * 2 * (RU_M * 16), RU_M * 16);
                         const uint64_t al = ru_desc(sa_lo + ks * 2 * (RU_M * 16), RU_M * 16);
                         const uint64_t bh = ru_desc(sb_hi + ks * 2 * (RU_NP * 16) + hf * 256 * 16, RU_NP * 16);
@@ -212,24 +246,28 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
         }
     } else {
         // =============================== producers ===============================
-        const int row = (warp - RU_PROD_WARP0) * 32 + lane;
+        const int row0 = (warp - RU_PROD_WARP0) * 32 + lane;            // rows row0 and row0 + 64 of the tile
         int it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             const int st = it & 1;
-            const long long i = tile * RU_M + row;
-            float4 v[8];
-#pragma unroll
-            for (int kc = 0; kc < 8; kc++)
-                v[kc] = i < N ? __ldg(reinterpret_cast<const float4*>(g + i * ME) + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
-            mbar_wait_backoff(&a_empty[st], ((it >> 1) & 1) ^ 1, 32);
             float4* ah = reinterpret_cast<float4*>(a_st + (size_t)st * 2 * RU_A_PLANE);
             float4* al = ah + RU_A_PLANE / 16;
+#pragma unroll 1
+            for (int hr = 0; hr < 2; hr++) {
+                const int row = row0 + 64 * hr;
+                const long long i = tile * RU_M + row;
+                float4 v[8];
 #pragma unroll
-            for (int kc = 0; kc < 8; kc++) {
-                float4 hi, lo;
-                ru_split4(v[kc], hi, lo);
-                ah[kc * RU_M + row] = hi;
-                al[kc * RU_M + row] = lo;
+                for (int kc = 0; kc < 8; kc++)
+                    v[kc] = (i < N && !(debug & 4)) ? __ldg(reinterpret_cast<const float4*>(g + i * ME) + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (hr == 0) mbar_wait_backoff(&a_empty[st], ((it >> 1) & 1) ^ 1, 32);
+#pragma unroll
+                for (int kc = 0; kc < 8; kc++) {
+                    float4 hi, lo;
+                    ru_split4(v[kc], hi, lo);
+                    ah[kc * RU_M + row] = hi;
+                    al[kc * RU_M + row] = lo;
+                }
             }
             ru_fence_proxy_async();
             __syncwarp();
@@ -257,7 +295,9 @@ int mlp_recover_umma(trpx_mlpemb_t h, const float* g, float* x, long long N, cud
     TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RU_SMEM));
     const long long ntiles = (N + RU_M - 1) / RU_M;
     const int grid = (int)std::min<long long>(h->sm_count, ntiles);
-    mlp_recover_umma_kernel<<<grid, RU_THREADS, RU_SMEM, st>>>(h->blob, L, g, x, N);
+    int debug = 0;          // timing experiments only (results are garbage): 1 epilogue skips its arithmetic, 2 no MMAs, 4 no input loads
+    if (const char* e = getenv("TRPX_RU_DEBUG")) debug = atoi(e);
+    mlp_recover_umma_kernel<<<grid, RU_THREADS, RU_SMEM, st>>>(h->blob, L, g, x, N, debug);
     TRPX_CUDA(cudaGetLastError());
     return TRPX_OK;
 }

@@ -404,6 +404,13 @@ def test_recover_tcgen05_kernel(dev, kind, n):
     assert float((outs[0] - outs[1]).abs().max()) < 1e-4 * float(ref.abs().max())
     # rows of the last (partial) tile and the first rows of the next tile of another CTA
     assert O.rel_l2(outs[0][-200:].cpu(), ref[-200:]) < TOL and O.rel_l2(outs[0][:300].cpu(), ref[:300]) < TOL
+    # the fused recover + MSE (Trainer.eval_states) takes the same kernel at this size: value, and the states it can return
+    target = ref + 0.1 * torch.from_numpy(synth.normal_embeds((n, 3), 923))
+    want = torch.nn.functional.mse_loss(ref, target)
+    got = emb.recover_mse(g.to(dev), target.to(dev))
+    assert abs(float(got) - float(want)) <= 5e-6 * float(want)
+    got2, states = emb.recover_mse(g.to(dev), target.to(dev), return_states=True)
+    assert abs(float(got2) - float(want)) <= 5e-6 * float(want) and torch.equal(states, outs[0])
 
 
 def test_rollout_to_host_pipeline(dev):

@@ -627,7 +627,7 @@ int trpx_mlpemb_recover(trpx_mlpemb_t h, const float* g, float* x, long long N, 
     const int Hp = (L.Hd + 7) & ~7;
     const size_t smem_tc = sizeof(float) * ((size_t)2 * Hp * RTC_LD + (size_t)4 * Hp);
     if ((h->recover_mode == 0 || h->recover_mode == 3) && mlp_recover_umma_ok(h, N))
-        return mlp_recover_umma(h, g, x, N, (cudaStream_t)stream);      // tcgen05 kernel (mlpemb_umma.cu)
+        return mlp_recover_umma(h, g, x, N, nullptr, nullptr, (cudaStream_t)stream);      // tcgen05 kernel (mlpemb_umma.cu)
     if (h->recover_mode != 1 && N >= 16384 && smem_tc + 1024 <= (size_t)h->smem_optin) {
         // tensor-core kernel: one persistent CTA per SM, 12 warps, 16 samples per warp-tile
         TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
@@ -660,17 +660,22 @@ int trpx_mlpemb_recover_mse(trpx_mlpemb_t h, const float* g, const float* target
     const size_t smem = sizeof(float4) * (size_t)L.Hd * 9;
     const int Hp = (L.Hd + 7) & ~7;
     const size_t smem_tc = sizeof(float) * ((size_t)2 * Hp * RTC_LD + (size_t)4 * Hp);
+    const bool umma = (h->recover_mode == 0 || h->recover_mode == 3) && mlp_recover_umma_ok(h, N);
     const bool tc = h->recover_mode != 1 && N >= 16384 && smem_tc + 1024 <= (size_t)h->smem_optin;
     const long long ntiles = (N + 15) / 16;
-    const int grid = tc ? (int)std::min<long long>(h->sm_count, (ntiles + RTC_THREADS / 32 - 1) / (RTC_THREADS / 32))
-                        : emb_grid(h, N, 3);
+    const int grid = umma ? mlp_recover_umma_grid(h, N)
+                     : tc ? (int)std::min<long long>(h->sm_count, (ntiles + RTC_THREADS / 32 - 1) / (RTC_THREADS / 32))
+                          : emb_grid(h, N, 3);
     if (h->mse_partial == nullptr || h->mse_partial_n < grid) {
         if (h->mse_partial) TRPX_CUDA(cudaFree(h->mse_partial));
         h->mse_partial = nullptr;
         TRPX_CUDA(cudaMalloc(&h->mse_partial, sizeof(float) * grid));
         h->mse_partial_n = grid;
     }
-    if (tc) {
+    if (umma) {
+        int rc = mlp_recover_umma(h, g, states_or_null, N, target, h->mse_partial, (cudaStream_t)stream);
+        if (rc) return rc;
+    } else if (tc) {
         TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         mlp_recover_tc_kernel<<<grid, RTC_THREADS, smem_tc, (cudaStream_t)stream>>>(h->blob, L, g, states_or_null, N, target,
                                                                                      h->mse_partial);

@@ -17,7 +17,6 @@
 #include "mlpemb.cuh"
 #include "mlpemb_umma.cuh"
 #include <algorithm>
-#include <cstdlib>
 
 using namespace trpx;
 
@@ -32,8 +31,11 @@ constexpr int RU_NP = 512;                                                // hid
 constexpr int RU_B_PLANE = 8 * RU_NP * 16;                                // bytes of one weight plane [8][512][4 f]
 constexpr int RU_A_PLANE = 8 * RU_M * 16;                                 // bytes of one input plane  [8][128][4 f]
 constexpr int RU_STAGES = 2;
+#ifndef RU_DEBUG
+#define RU_DEBUG 0      // timing experiments only (results are garbage): 1 epilogue skips its arithmetic, 2 no MMAs, 4 no input loads
+#endif
 constexpr size_t RU_SMEM = 2 * (size_t)RU_B_PLANE + RU_STAGES * 2 * (size_t)RU_A_PLANE + RU_NP * 16 /* decB */ +
-                           2 * 3 * RU_M * 16 /* partial sums */ + 256 /* barriers */;
+                           2 * 3 * RU_M * 16 /* partial sums */ + 256 /* barriers, TMEM slot, MSE sums */;
 
 __device__ __forceinline__ uint64_t ru_desc(uint32_t saddr, uint32_t lbo_bytes) {
     // K-major, no swizzle: start >> 4 | LBO >> 4 (stride between the two 16-byte K chunks) | SBO = 128 B (stride between
@@ -114,7 +116,9 @@ __device__ __forceinline__ void ru_split4(const float4 v, float4& hi, float4& lo
 
 __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const float* __restrict__ blob, MlpLayout L,
                                                                          const float* __restrict__ g,
-                                                                         float* __restrict__ x, long long N, int debug) {
+                                                                         float* __restrict__ x, long long N,
+                                                                         const float* __restrict__ target,
+                                                                         float* __restrict__ partial, int debug) {
     extern __shared__ __align__(128) unsigned char ru_smem[];
     unsigned char* b_hi = ru_smem;
     unsigned char* b_lo = b_hi + RU_B_PLANE;
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
     uint64_t* tfull = bars + 4;              // [half]   tcgen05.commit -> epilogue
     uint64_t* tempty = bars + 6;             // [half]   epilogue -> MMA            (16 arrivals: one per epilogue warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* red = reinterpret_cast<float*>(bars + 9);       // [4] squared-error sums of the finishing warps (fused recover + MSE)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Hd = L.Hd;
     const long long ntiles = (N + RU_M - 1) / RU_M;
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
         const float mu0 = __ldg(blob + L.mu), mu1 = __ldg(blob + L.mu + 1), mu2 = __ldg(blob + L.mu + 2);
         const float sd0 = __ldg(blob + L.sd), sd1 = __ldg(blob + L.sd + 1), sd2 = __ldg(blob + L.sd + 2);
         int it = 0;
+        float sq = 0.f;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
             float y[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -208,11 +214,23 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
                 y2 = (y2 + p1.z) + (p2.z + p3.z);
                 const long long i = tile * RU_M + row;
                 if (i < N) {
-                    x[i * MS + 0] = sd0 * (y0 + c20) + mu0;
-                    x[i * MS + 1] = sd1 * (y1 + c21) + mu1;
-                    x[i * MS + 2] = sd2 * (y2 + c22) + mu2;
+                    const float x0 = sd0 * (y0 + c20) + mu0, x1 = sd1 * (y1 + c21) + mu1, x2 = sd2 * (y2 + c22) + mu2;
+                    if (x != nullptr) {
+                        x[i * MS + 0] = x0;
+                        x[i * MS + 1] = x1;
+                        x[i * MS + 2] = x2;
+                    }
+                    if (target != nullptr) {
+                        const float d0 = x0 - __ldg(target + i * MS), d1 = x1 - __ldg(target + i * MS + 1),
+                                    d2 = x2 - __ldg(target + i * MS + 2);
+                        sq += d0 * d0 + d1 * d1 + d2 * d2;
+                    }
                 }
             }
+        }
+        if (target != nullptr && e == 0) {
+            sq = warp_sum(sq);
+            if (lane == 0) red[q] = sq;
         }
     } else if (warp == RU_MMA_WARP) {
         // =============================== MMA issue ===============================
@@ -280,6 +298,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) mlp_recover_umma_kernel(const f
         ru_fence_after();
         ru_tmem_dealloc(tmem_base, 512);
     }
+    if (target != nullptr && tid == 0) partial[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);     // fixed order
 }
 
 }  // namespace
@@ -290,14 +309,16 @@ bool mlp_recover_umma_ok(trpx_mlpemb_t h, long long N) {
     return h->cfg.hidden <= RU_NP && N >= 4LL * RU_M * h->sm_count && RU_SMEM + 1024 <= (size_t)h->smem_optin;
 }
 
-int mlp_recover_umma(trpx_mlpemb_t h, const float* g, float* x, long long N, cudaStream_t st) {
+int mlp_recover_umma_grid(trpx_mlpemb_t h, long long N) {
+    return (int)std::min<long long>(h->sm_count, (N + RU_M - 1) / RU_M);
+}
+
+// target != null: fused recover + MSE (x may then be null); per-CTA squared-error sums go to partial[0 .. grid)
+int mlp_recover_umma(trpx_mlpemb_t h, const float* g, float* x, long long N, const float* target, float* partial,
+                     cudaStream_t st) {
     const MlpLayout L = MlpLayout::make(h->cfg.hidden);
     TRPX_CUDA(cudaFuncSetAttribute(mlp_recover_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RU_SMEM));
-    const long long ntiles = (N + RU_M - 1) / RU_M;
-    const int grid = (int)std::min<long long>(h->sm_count, ntiles);
-    int debug = 0;          // timing experiments only (results are garbage): 1 epilogue skips its arithmetic, 2 no MMAs, 4 no input loads
-    if (const char* e = getenv("TRPX_RU_DEBUG")) debug = atoi(e);
-    mlp_recover_umma_kernel<<<grid, RU_THREADS, RU_SMEM, st>>>(h->blob, L, g, x, N, debug);
+    mlp_recover_umma_kernel<<<mlp_recover_umma_grid(h, N), RU_THREADS, RU_SMEM, st>>>(h->blob, L, g, x, N, target, partial, RU_DEBUG);
     TRPX_CUDA(cudaGetLastError());
     return TRPX_OK;
 }

@@ -4,5 +4,7 @@
 
 namespace trpx {
 bool mlp_recover_umma_ok(trpx_mlpemb_t h, long long N);
-int mlp_recover_umma(trpx_mlpemb_t h, const float* g, float* x, long long N, cudaStream_t st);
+int mlp_recover_umma_grid(trpx_mlpemb_t h, long long N);
+int mlp_recover_umma(trpx_mlpemb_t h, const float* g, float* x, long long N, const float* target, float* partial,
+                     cudaStream_t st);
 }  // namespace trpx

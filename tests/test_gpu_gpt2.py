@@ -47,6 +47,27 @@ def test_forward_matches_reference(golden_dir, dev, name):
         assert torch.equal(only_hidden, hid)
 
 
+@pytest.mark.parametrize("T", [1, 2, 3, 7, 33, 63])
+def test_forward_tensor_core_kernel_short_and_odd_lengths(dev, T):
+    """Teacher-forced forward on the tensor-core kernel for sequence lengths that leave threads of the balanced causal
+    attention (a thread owns one head of the token pair (i, T - 1 - i)) without a second token, with a middle token
+    (odd T), or idle; against the oracle and the block-GEMV kernel."""
+    cfg = synth.make_config("lorenz")
+    w_np = synth.gpt2_weights(cfg, 931, stress=True, stress_sigma=0.2)
+    m = make_gpt2(cfg, 931, True, dev, sigma=0.2)
+    x = torch.from_numpy(synth.normal_embeds((5, T, cfg.n_embd), 932))
+    ref = O.gpt2_forward(O.to_torch(w_np), cfg, x, use_cache=True)
+    with torch.no_grad():
+        hid, presents = m(x.to(dev), use_cache=True)
+        m.set_rollout_tuning(variant=1)                        # block-GEMV kernel
+        hid1, _ = m(x.to(dev), use_cache=True)
+        m.set_rollout_tuning(variant=0)
+    assert O.rel_l2(hid.cpu(), ref[0]) < TOL and O.rel_l2(hid1.cpu(), ref[0]) < TOL
+    assert not torch.equal(hid, hid1)                          # really two kernels
+    for l in range(cfg.n_layer):
+        assert O.rel_l2(presents[l].cpu(), ref[1][l]) < TOL
+
+
 @pytest.mark.parametrize("variant", [0, 1, 3, 5, 6, 7, 8])   # auto, generic, E=32 w/o TMA staging, E=32 v2, E=32 3xTF32 MMA, cluster, TMA-staged window
 @pytest.mark.parametrize("name", list(GPT2_CASES))
 def test_generate_matches_reference(golden_dir, dev, name, variant):

@@ -3458,10 +3458,11 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
                              (x0_stride % 2) == 0 && (out_stride % 2) == 0;
         const size_t scr_w = use_cache ? (size_t)V4G * V4QS * sizeof(float) : 0;
         const bool fits = wbytes + scr_w + 1024 <= (size_t)h->smem_optin;
-        // measured (profiles/): without the KV window the tensor-core kernel is 1.7x the SIMT kernels; with it the
-        // 4-trajectories-per-warp SIMT kernel hides the window latency better (more warps per trajectory)
+        // measured (profiles/): without the KV window the tensor-core kernel is 1.7x the SIMT kernels from ~3.5 groups of 16
+        // trajectories per SM on (B = 8,192: 411 against 333 M/s, 16,384: 540 against 312; B = 4,096: 208 against 257);
+        // with the window the SIMT kernel hides the window latency better (more warps per trajectory)
         const bool want = h->tune_variant == 6 ||
-                          (h->tune_variant == 0 && !use_cache && (long long)ngroups >= (long long)sms * 8);
+                          (h->tune_variant == 0 && !use_cache && 4LL * ngroups >= 13LL * sms);
         if (e32_shape && aligned && fits && want) {
             const int max_w = scr_w ? (int)std::min<size_t>(8, ((size_t)h->smem_optin - 1024 - wbytes) / scr_w) : 12;
             const int grid = std::min(sms, ngroups);

@@ -3626,7 +3626,16 @@ int trpx_gpt2_rollout(trpx_gpt2_t h, const float* x0, long long x0_stride, float
         } else {
             const int grid = std::min(sms, ngroups);
             const int want = h->tune_warps > 0 ? h->tune_warps : ((use_cache && L.n_ctx <= 32) ? 11 : 8);
-            const int Wc = std::max(1, std::min(std::min(want, max_w), (ngroups + grid - 1) / grid));
+            int Wc = std::max(1, std::min(std::min(want, max_w), (ngroups + grid - 1) / grid));
+            if (use_cache && h->tune_warps == 0) {
+                // Wave quantisation: a warp runs its group at about the same speed whether the round is full or not, so the
+                // pass takes `rounds` rounds; the FEWEST warps per CTA that still need only that many rounds make every
+                // round faster (measured, Rossler G = 8: B = 12,288: 6 warps 22.8 ms against 25.1 with 8; 16,384: 7 warps
+                // 24.3 against 25.9; 32,768: 49.1 against 52.6; 65,536 keeps 8)
+                const long long slots = (long long)grid;
+                const long long rounds = (ngroups + slots * Wc - 1) / (slots * Wc);
+                while (Wc > 1 && (ngroups + slots * (Wc - 1) - 1) / (slots * (Wc - 1)) == rounds) Wc--;
+            }
             const size_t smem = wbytes + (size_t)Wc * 64 * G * sizeof(float);
             if (use_cache) {
                 int rc = ensure_kv(h, (size_t)grid * Wc * G * kv_per_traj);

@@ -12,8 +12,9 @@ literal config[1] (65,536 trajectories in total, 65,536/N per GPU) is reported b
 
   value    trajectory-steps/s, whole job, inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e      same metric through the public module API with HOST buffers: pinned x0 -> H2D, ..., states -> D2H
-           (recover runs in 4 trajectory chunks; a chunk's states travel to the pinned host buffer on a copy stream
-           while the next chunk decodes; the step ends when the last state has reached the host)
+           (generate + recover run per slice of one round of resident trajectories; a slice's states travel to the
+           pinned host buffer on a copy stream while the next slice decodes; the step ends when the last state has
+           reached the host)
   roofline the rollout kernel alone (CUDA events around it): KV-window stream bytes / duration vs the measured HBM peak
   configs  the other BASELINE configs, each device-timed in this run with its own roofline record: Lorenz 256 x 128
            (config 0), Cylinder 400-step rollouts (config 3), the Koopman training step with its all-reduce (config 2),
@@ -587,8 +588,8 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
 
     def pass_e2e():
-        # ONE public call: pinned x0 -> H2D -> embed -> generate -> recover in 4 trajectory chunks, each chunk's states
-        # going device -> host on the copy stream while the next chunk decodes
+        # ONE public call: pinned x0 -> H2D -> embed -> [generate -> recover] per slice of one round of resident
+        # trajectories, each slice's states going device -> host on the copy stream while the next slice decodes
         rollout_to_host(emb, tr, x0_host, S + 1, states_host, device=dev, use_cache=True, chunks=4,
                         copy_stream=copy_stream)
 

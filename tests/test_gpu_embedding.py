@@ -431,6 +431,20 @@ def test_rollout_to_host_pipeline(dev):
     ref = emb.recover(out.view(B * (S + 1), cfg.n_embd)).view(B, S + 1, 3)
     # chunks of 5,271 samples take the FP32 recover kernel, the single call (21,063 samples) the tensor-core one
     assert O.rel_l2(host, ref.cpu()) < 1e-6
+    # large batch: generate() itself runs slice by slice (one round of resident trajectories each) under the copies
+    B2, S2 = 2 * tr.rollout_round_trajectories(dev) + 1234, 6
+    x1 = torch.from_numpy(synth.rossler_trajectories(B2, 0, seed=924)[:, 0].copy()).pin_memory()
+    host2 = torch.empty((B2, S2 + 1, 3), dtype=torch.float32).pin_memory()
+    rollout_to_host(emb, tr, x1, S2 + 1, host2, device=dev, chunks=4)
+    torch.cuda.synchronize()
+    assert tr.last_launch()["grid"] * 64 >= (B2 + 2) // 3          # the last generate() call saw a third of the batch
+    host3 = torch.empty_like(host2).pin_memory()
+    rollout_to_host(emb, tr, x1, S2 + 1, host3, device=dev, chunks=4, pipeline=False)
+    torch.cuda.synchronize()
+    assert O.rel_l2(host2, host3) < 1e-6
+    out1 = tr.generate(emb.embed(x1.to(dev)).unsqueeze(1), max_length=S2 + 1, use_cache=True)[0]
+    ref1 = emb.recover(out1.view(B2 * (S2 + 1), cfg.n_embd)).view(B2, S2 + 1, 3)
+    assert O.rel_l2(host2, ref1.cpu()) < 1e-6
 
 
 @pytest.mark.parametrize("B,S,auto_variant", [(6, 400, 7), (64, 400, 7), (160, 200, 1)])

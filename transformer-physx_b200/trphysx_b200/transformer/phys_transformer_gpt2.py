@@ -224,6 +224,16 @@ class PhysformerGPT2(PhysformerBase):
                                                 gblob.data_ptr(), N.stream_ptr(x.device)))
         return loss, hidden, self._blob_views(gblob)
 
+    def rollout_round_trajectories(self, device, use_cache: bool = True):
+        """Trajectories the window kernel keeps resident per round on `device` (one persistent CTA per SM, 8 warps, 8
+        trajectories per warp for n_ctx <= 32, 4 for n_ctx = 64: csrc/gpt2.cu, trpx_gpt2_rollout), or None where the rollout
+        is not organised in such rounds.  Callers that pipeline work around generate() slice large batches by it."""
+        c = self.config
+        if not use_cache or c.n_embd != 32 or c.n_head != 4 or c.n_ctx > 64 or getattr(self, "_tuning", (0, 0, 0, 0)) != (0, 0, 0, 0):
+            return None
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        return sms * 8 * (8 if c.n_ctx <= 32 else 4)
+
     def set_rollout_tuning(self, variant: int = 0, warps_per_cta: int = 0, traj_per_warp: int = 0, max_ctas: int = 0):
         """Kernel tuning knobs (0 = automatic); see trpx_gpt2_set_rollout_tuning in include/trpx.h."""
         self._tuning = (variant, warps_per_cta, traj_per_warp, max_ctas)

@@ -115,7 +115,11 @@ int trpx_gpt2_load_blob(trpx_gpt2_t h, const float* blob_dev, void* stream);
  * mma.sync; chosen automatically for large batches without the KV window), 7 = thread-block-cluster kernel
  * (8 CTAs per trajectory group, column-split GEMVs, DSMEM exchange, TMA weight ring; chosen automatically for
  * shapes other than E=32 when one trajectory per cluster fits in a single wave; groups of 1-2 trajectories exchange
- * with st.async + mbarrier complete_tx instead of cluster barriers), 9 = 7 with the cluster-barrier exchange (A/B). */
+ * with st.async + mbarrier complete_tx instead of cluster barriers), 9 = 7 with the cluster-barrier exchange (A/B),
+ * 8 = E=32 window kernel with TMA-staged attention and a per-layer weight ring, 10 = E=32 kernel with the KV window on
+ * chip in tensor memory (chosen automatically for small batches), 11 = warp-specialised E=32 window kernel (dense
+ * tensor-core warps + attention warps; KV-window mode only, A/B).  With warps_per_cta = 0 the window kernel takes the
+ * fewest warps per CTA that need no more rounds over the batch than the maximum (8) would. */
 int trpx_gpt2_set_rollout_tuning(trpx_gpt2_t h, int variant, int warps_per_cta, int traj_per_warp,
                                  int max_ctas);
 /* What the last trpx_gpt2_rollout launched: variant (1 generic, 2 E=32 warp kernel, 5 E=32 2-D tiling, 6 E=32 tensor-core,
